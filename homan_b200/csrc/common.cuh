@@ -1,0 +1,111 @@
+// Shared helpers of the homan_b200 CUDA library (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/homan_b200.h"
+
+void hm_set_error(const char *fmt, ...);
+
+#define HM_REQUIRE(cond, ...)                 \
+    do {                                      \
+        if (!(cond)) {                        \
+            hm_set_error(__VA_ARGS__);        \
+            return HM_ERR_INVALID;            \
+        }                                     \
+    } while (0)
+
+#define HM_UNSUPPORTED(cond, ...)             \
+    do {                                      \
+        if (cond) {                           \
+            hm_set_error(__VA_ARGS__);        \
+            return HM_ERR_UNSUPPORTED;        \
+        }                                     \
+    } while (0)
+
+// cudaPeekAtLastError is legal during stream capture and does not clear sticky errors.
+#define HM_CHECK_LAUNCH(name)                                                         \
+    do {                                                                              \
+        cudaError_t e__ = cudaPeekAtLastError();                                      \
+        if (e__ != cudaSuccess) {                                                     \
+            hm_set_error("%s: CUDA error %s", name, cudaGetErrorString(e__));         \
+            (void)cudaGetLastError();                                                 \
+            return HM_ERR_CUDA;                                                       \
+        }                                                                             \
+    } while (0)
+
+static inline cudaStream_t hm_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_min(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum of N values per thread; result valid in thread 0 (and broadcast through `out`).
+// `scratch` must hold N * 32 floats. All threads of the block must call it.
+template <int N>
+__device__ __forceinline__ void block_sum(float (&v)[N], float *scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = warp_sum(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) scratch[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            float x = lane < nwarps ? scratch[i * 32 + lane] : 0.f;
+            x = warp_sum(x);
+            if (lane == 0) scratch[i * 32] = x;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = scratch[i * 32];
+    __syncthreads();
+}
+
+// 1-D bulk asynchronous copy global -> shared through the TMA unit (cp.async.bulk, SASS UBLKCP),
+// completion signalled on an mbarrier. Addresses and size must be multiples of 16 bytes.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(phase)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}

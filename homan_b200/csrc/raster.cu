@@ -1,0 +1,727 @@
+// Silhouette rasteriser (forward + approximate backward) and pin-hole projection for sm_100a.
+//
+// Replaces the `neural_renderer` CUDA extension on the reference's hot path:
+//   nr.projection                       -> project_fwd_kernel / project_bwd_kernel
+//   fill_back + vertices_to_faces       -> face_setup_kernel (front-facing winding only, no doubling)
+//   forward_face_index_map + alpha,
+//   vertical flip, 2x2 avg-pool (AA)    -> raster_fwd_kernel (64x64 tile, shared-memory z-buffer)
+//   backward_pixel_map + scatter-add    -> grad_prep_kernel + raster_bwd_kernel
+// Call sites in the reference: homan/losses.py:34-41,73-77,172-176,187; homan/homan.py:168-176.
+//
+// The file is compiled with -fmad=false: coverage / ownership predicates are evaluated with the same
+// individually rounded fp32 operations as the CPU oracle so that face_index maps agree bit for bit.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE = 64;
+constexpr int NTHREADS = 256;
+constexpr int NWARPS = NTHREADS / 32;
+
+struct __align__(16) FaceRec {
+    float c[9];   // x0 y0 z0 x1 y1 z1 x2 y2 z2 in NDC, front-facing winding
+    int fn;       // face number in the doubled (fill_back) numbering, -1 = culled
+    int v[3];     // vertex indices in that winding
+    short bb[4];  // pixel bbox x0 y0 x1 y1 (clamped), empty when x0 > x1
+    int pad;
+};
+static_assert(sizeof(FaceRec) == HM_FACE_RECORD_BYTES, "record size");
+
+struct __align__(8) FaceBox {
+    short x0, y0, x1, y1;
+};
+static_assert(sizeof(FaceBox) == HM_FACE_BBOX_BYTES, "bbox size");
+
+// ------------------------------------------------------------------------------------------ projection
+__global__ void project_fwd_kernel(const float *__restrict__ verts, const float *__restrict__ K, int K_batch,
+                                   const float *__restrict__ R, const float *__restrict__ t,
+                                   const float *__restrict__ dist, int dist_batch, float orig_size, float eps,
+                                   int B, int V, float *__restrict__ ndc) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * V) return;
+    const int b = (int)(i / V);
+    float x = verts[3 * i], y = verts[3 * i + 1], z = verts[3 * i + 2];
+    if (R) {
+        const float X = R[0] * x + R[1] * y + R[2] * z, Y = R[3] * x + R[4] * y + R[5] * z,
+                    Z = R[6] * x + R[7] * y + R[8] * z;
+        x = X; y = Y; z = Z;
+    }
+    if (t) { x += t[0]; y += t[1]; z += t[2]; }
+    const float x_ = x / (z + eps), y_ = y / (z + eps);
+    float x__ = x_, y__ = y_;
+    if (dist) {
+        const float *d = dist + (dist_batch > 1 ? 5 * b : 0);
+        const float k1 = d[0], k2 = d[1], p1 = d[2], p2 = d[3], k3 = d[4];
+        const float r = sqrtf(x_ * x_ + y_ * y_);
+        const float r2 = r * r, r4 = r2 * r2, r6 = r4 * r2;
+        const float rad = 1.f + k1 * r2 + k2 * r4 + k3 * r6;
+        x__ = x_ * rad + 2.f * p1 * x_ * y_ + p2 * (r2 + 2.f * x_ * x_);
+        y__ = y_ * rad + p1 * (r2 + 2.f * y_ * y_) + 2.f * p2 * x_ * y_;
+    }
+    const float *Kb = K + (K_batch > 1 ? 9 * b : 0);
+    float u = Kb[0] * x__ + Kb[1] * y__ + Kb[2];
+    float v = Kb[3] * x__ + Kb[4] * y__ + Kb[5];
+    v = orig_size - v;
+    u = 2.f * (u - orig_size / 2.f) / orig_size;
+    v = 2.f * (v - orig_size / 2.f) / orig_size;
+    ndc[3 * i] = u;
+    ndc[3 * i + 1] = v;
+    ndc[3 * i + 2] = z;
+}
+
+__global__ void project_bwd_kernel(const float *__restrict__ verts, const float *__restrict__ K, int K_batch,
+                                   const float *__restrict__ R, const float *__restrict__ t, float orig_size,
+                                   float eps, int B, int V, const float *__restrict__ grad_ndc,
+                                   float *__restrict__ grad_verts, int accumulate) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * V) return;
+    const int b = (int)(i / V);
+    float x = verts[3 * i], y = verts[3 * i + 1], z = verts[3 * i + 2];
+    if (R) {
+        const float X = R[0] * x + R[1] * y + R[2] * z, Y = R[3] * x + R[4] * y + R[5] * z,
+                    Z = R[6] * x + R[7] * y + R[8] * z;
+        x = X; y = Y; z = Z;
+    }
+    if (t) { x += t[0]; y += t[1]; z += t[2]; }
+    const float iz = 1.f / (z + eps);
+    const float x_ = x * iz, y_ = y * iz;
+    const float *Kb = K + (K_batch > 1 ? 9 * b : 0);
+    const float gu = grad_ndc[3 * i] * (2.f / orig_size), gv = -grad_ndc[3 * i + 1] * (2.f / orig_size);
+    const float gx_ = gu * Kb[0] + gv * Kb[3], gy_ = gu * Kb[1] + gv * Kb[4];
+    float gX = gx_ * iz, gY = gy_ * iz, gZ = -(gx_ * x_ + gy_ * y_) * iz + grad_ndc[3 * i + 2];
+    if (R) {
+        const float a = R[0] * gX + R[3] * gY + R[6] * gZ, c = R[1] * gX + R[4] * gY + R[7] * gZ,
+                    d = R[2] * gX + R[5] * gY + R[8] * gZ;
+        gX = a; gY = c; gZ = d;
+    }
+    if (accumulate) {
+        grad_verts[3 * i] += gX; grad_verts[3 * i + 1] += gY; grad_verts[3 * i + 2] += gZ;
+    } else {
+        grad_verts[3 * i] = gX; grad_verts[3 * i + 1] = gY; grad_verts[3 * i + 2] = gZ;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ face setup
+__device__ __forceinline__ float to_pix(float v, int is) { return 0.5f * (v * is + is - 1); }
+
+__global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *__restrict__ faces, int faces_batch,
+                                  int B, int V, int F, int is, int fill_back, FaceRec *__restrict__ recs,
+                                  FaceBox *__restrict__ boxes) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * F) return;
+    const int b = (int)(i / F), f = (int)(i % F);
+    const int32_t *fc = faces + ((faces_batch > 1 ? (long)b * F : 0) + f) * 3;
+    int vi[3] = {fc[0], fc[1], fc[2]};
+    float p[3][3];
+    bool ok = true;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        if (vi[k] < 0 || vi[k] >= V) { ok = false; vi[k] = 0; }
+        const float *q = ndc + ((long)b * V + vi[k]) * 3;
+        p[k][0] = q[0]; p[k][1] = q[1]; p[k][2] = q[2];
+    }
+    int fn = -1;
+    bool rev = false;
+    // back-face test of the original winding, then of the reversed copy appended by fill_back
+    if (!((p[2][1] - p[0][1]) * (p[1][0] - p[0][0]) < (p[1][1] - p[0][1]) * (p[2][0] - p[0][0]))) {
+        fn = f;
+    } else if (fill_back &&
+               !((p[0][1] - p[2][1]) * (p[1][0] - p[2][0]) < (p[1][1] - p[2][1]) * (p[0][0] - p[2][0]))) {
+        fn = F + f;
+        rev = true;
+    }
+    if (!ok) fn = -1;
+    FaceRec r;
+    const int o0 = rev ? 2 : 0, o2 = rev ? 0 : 2;
+    const int ord[3] = {o0, 1, o2};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        r.c[3 * k] = p[ord[k]][0]; r.c[3 * k + 1] = p[ord[k]][1]; r.c[3 * k + 2] = p[ord[k]][2];
+        r.v[k] = vi[ord[k]];
+    }
+    // conservative pixel bbox, 1 px of slack (covers every in/out pixel of backward_pixel_map too)
+    const float px0 = to_pix(p[0][0], is), px1 = to_pix(p[1][0], is), px2 = to_pix(p[2][0], is);
+    const float py0 = to_pix(p[0][1], is), py1 = to_pix(p[1][1], is), py2 = to_pix(p[2][1], is);
+    const float xmin = fminf(fminf(px0, px1), px2), xmax = fmaxf(fmaxf(px0, px1), px2);
+    const float ymin = fminf(fminf(py0, py1), py2), ymax = fmaxf(fmaxf(py0, py1), py2);
+    if (!(px0 == px0) || !(px1 == px1) || !(px2 == px2) || !(py0 == py0) || !(py1 == py1) || !(py2 == py2)) fn = -1;
+    int x0 = __float2int_rz(floorf(xmin)) - 1, x1 = __float2int_rz(ceilf(xmax)) + 1;
+    int y0 = __float2int_rz(floorf(ymin)) - 1, y1 = __float2int_rz(ceilf(ymax)) + 1;
+    if (fn < 0 || x1 < 0 || y1 < 0 || x0 > is - 1 || y0 > is - 1) {
+        x0 = 1; x1 = 0; y0 = 1; y1 = 0;  // empty
+        if (fn >= 0) fn = -2 - fn;       // off-screen: no pixel, no crossing (kept negative => skipped)
+    } else {
+        x0 = max(x0, 0); y0 = max(y0, 0); x1 = min(x1, is - 1); y1 = min(y1, is - 1);
+    }
+    r.fn = fn;
+    r.bb[0] = (short)x0; r.bb[1] = (short)y0; r.bb[2] = (short)x1; r.bb[3] = (short)y1;
+    r.pad = 0;
+    recs[i] = r;
+    FaceBox bx;
+    bx.x0 = (short)x0; bx.y0 = (short)y0; bx.x1 = (short)x1; bx.y1 = (short)y1;
+    boxes[i] = bx;
+}
+
+// Collect into `list` the faces [base, base+NTHREADS) whose bbox touches the tile. Returns the count.
+__device__ __forceinline__ int collect_faces(const FaceBox *__restrict__ boxes, int base, int F, int tx0, int ty0,
+                                             int *list, int *cnt) {
+    const int f = base + threadIdx.x;
+    bool hit = false;
+    if (f < F) {
+        const FaceBox bx = boxes[f];
+        hit = bx.x0 <= bx.x1 && bx.x0 <= tx0 + TILE - 1 && bx.x1 >= tx0 && bx.y0 <= ty0 + TILE - 1 && bx.y1 >= ty0;
+    }
+    if (threadIdx.x == 0) *cnt = 0;
+    __syncthreads();
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    const int lane = threadIdx.x & 31;
+    int wbase = 0;
+    if (lane == 0 && m) wbase = atomicAdd(cnt, __popc(m));
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    if (hit) list[wbase + __popc(m & ((1u << lane) - 1))] = f;
+    __syncthreads();
+    return *cnt;
+}
+
+// ------------------------------------------------------------------------------------------ forward
+__global__ void __launch_bounds__(NTHREADS)
+raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ boxes, int F, int is, int aa,
+                  float near_, float far_, int32_t *__restrict__ face_index, float *__restrict__ alpha,
+                  uint32_t *__restrict__ cov_row, uint32_t *__restrict__ cov_col) {
+    __shared__ unsigned long long keys[TILE * TILE];
+    __shared__ int list[NTHREADS];
+    __shared__ int cnt;
+    __shared__ uint32_t roww[TILE][2];
+    const int b = blockIdx.y;
+    const int tiles_x = is / TILE;
+    const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long empty = ((unsigned long long)__float_as_uint(far_) << 32) | 0xffffffffull;
+    for (int i = threadIdx.x; i < TILE * TILE; i += NTHREADS) keys[i] = empty;
+    recs += (long)b * F;
+    boxes += (long)b * F;
+
+    for (int base = 0; base < F; base += NTHREADS) {
+        const int n = collect_faces(boxes, base, F, tx0, ty0, list, &cnt);
+        for (int li = warp; li < n; li += NWARPS) {
+            const FaceRec *rp = recs + list[li];
+            const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rp));
+            const float4 q1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
+            const float4 q2 = __ldg(reinterpret_cast<const float4 *>(rp) + 2);
+            const int4 q3 = __ldg(reinterpret_cast<const int4 *>(rp) + 3);
+            const float f0 = q0.x, f1 = q0.y, f2 = q0.z, f3 = q0.w, f4 = q1.x, f5 = q1.y, f6 = q1.z, f7 = q1.w,
+                        f8 = q2.x;
+            const int fn = __float_as_int(q2.y);
+            const int bx0 = (short)(q3.y & 0xffff), by0 = (short)(q3.y >> 16);
+            const int bx1 = (short)(q3.z & 0xffff), by1 = (short)(q3.z >> 16);
+            const int X0 = max(bx0, tx0), X1 = min(bx1, tx0 + TILE - 1);
+            const int Y0 = max(by0, ty0), Y1 = min(by1, ty0 + TILE - 1);
+            const int w = X1 - X0 + 1, h = Y1 - Y0 + 1;
+            if (w <= 0 || h <= 0) continue;
+            // barycentric matrix in pixel coordinates (same expressions as the oracle)
+            const float p00 = to_pix(f0, is), p01 = to_pix(f1, is), p10 = to_pix(f3, is), p11 = to_pix(f4, is),
+                        p20 = to_pix(f6, is), p21 = to_pix(f7, is);
+            float inv[9] = {p11 - p21, p20 - p10, p10 * p21 - p20 * p11,
+                            p21 - p01, p00 - p20, p20 * p01 - p00 * p21,
+                            p01 - p11, p10 - p00, p00 * p11 - p10 * p01};
+            const float den = p20 * (p01 - p11) + p00 * (p11 - p21) + p10 * (p21 - p01);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) inv[k] /= den;
+            const float e0x = f3 - f0, e0y = f4 - f1, e1x = f6 - f3, e1y = f7 - f4, e2x = f0 - f6, e2y = f1 - f7;
+            const int n_px = w * h;
+            const float inv_w = 1.f / (float)w;
+            for (int i = lane; i < n_px; i += 32) {
+                const int row = __float2int_rz(((float)i + 0.5f) * inv_w);
+                const int xi = X0 + (i - row * w), yi = Y0 + row;
+                const float yp = (float)(2 * yi + 1 - is) / (float)is;
+                const float xp = (float)(2 * xi + 1 - is) / (float)is;
+                if ((yp - f1) * e0x < (xp - f0) * e0y) continue;
+                if ((yp - f4) * e1x < (xp - f3) * e1y) continue;
+                if ((yp - f7) * e2x < (xp - f6) * e2y) continue;
+                float w0 = inv[0] * xi + inv[1] * yi + inv[2];
+                float w1 = inv[3] * xi + inv[4] * yi + inv[5];
+                float w2 = inv[6] * xi + inv[7] * yi + inv[8];
+                w0 = fminf(fmaxf(w0, 0.f), 1.f);
+                w1 = fminf(fmaxf(w1, 0.f), 1.f);
+                w2 = fminf(fmaxf(w2, 0.f), 1.f);
+                const float ws = w0 + w1 + w2;
+                w0 /= ws; w1 /= ws; w2 /= ws;
+                const float zp = 1.f / (w0 / f2 + w1 / f5 + w2 / f8);
+                if (zp <= near_ || far_ <= zp) continue;  // also rejects NaN
+                if (!(zp == zp)) continue;
+                const unsigned long long key = ((unsigned long long)__float_as_uint(zp) << 32) | (unsigned)fn;
+                atomicMin(&keys[(yi - ty0) * TILE + (xi - tx0)], key);
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- write-out: face_index rows (coalesced), coverage words
+    for (int i = threadIdx.x; i < TILE * TILE; i += NTHREADS) {
+        const int yl = i / TILE, xl = i % TILE;
+        const unsigned lo = (unsigned)(keys[i] & 0xffffffffull);
+        const bool cov = lo != 0xffffffffu;
+        face_index[((long)b * is + (ty0 + yl)) * is + tx0 + xl] = cov ? (int)lo : -1;
+        const unsigned m = __ballot_sync(0xffffffffu, cov);
+        if (lane == 0) {
+            roww[yl][xl >> 5] = m;
+            if (cov_row) cov_row[((long)b * is + (ty0 + yl)) * (is / 32) + ((tx0 + xl) >> 5)] = m;
+        }
+    }
+    __syncthreads();
+    if (aa) {
+        const int R = is / 2;
+        const int rtop = R - 1 - (ty0 >> 1);
+        for (int i = threadIdx.x; i < (TILE / 2) * (TILE / 2); i += NTHREADS) {
+            const int m = i / (TILE / 2), cc = i % (TILE / 2);
+            const int xl = 2 * cc;
+            const unsigned a = roww[2 * m][xl >> 5] >> (xl & 31), c = roww[2 * m + 1][xl >> 5] >> (xl & 31);
+            const float s = (float)((a & 1u) + ((a >> 1) & 1u) + (c & 1u) + ((c >> 1) & 1u));
+            alpha[((long)b * R + (rtop - m)) * R + (tx0 >> 1) + cc] = s * 0.25f;
+        }
+    } else {
+        for (int i = threadIdx.x; i < TILE * TILE; i += NTHREADS) {
+            const int yl = i / TILE, xl = i % TILE;
+            const unsigned a = roww[yl][xl >> 5] >> (xl & 31);
+            alpha[((long)b * is + (is - 1 - ty0 - yl)) * is + tx0 + xl] = (a & 1u) ? 1.f : 0.f;
+        }
+    }
+    if (cov_col && threadIdx.x < 2 * TILE) {
+        const int xl = threadIdx.x % TILE, yw = threadIdx.x / TILE;
+        unsigned word = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; ++j) word |= ((roww[yw * 32 + j][xl >> 5] >> (xl & 31)) & 1u) << j;
+        cov_col[((long)b * is + (tx0 + xl)) * (is / 32) + (ty0 >> 5) + yw] = word;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ sweep masks
+// m_row[b][0] = uncovered & grad < 0 ("missing coverage"), m_row[b][1] = covered & grad > 0 ("excess"),
+// at raster resolution in the raster frame; m_col the same, transposed (one line per column).
+__global__ void __launch_bounds__(NTHREADS)
+grad_prep_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restrict__ cov_row,
+                 const uint32_t *__restrict__ cov_col, int is, int aa, uint32_t *__restrict__ m_row,
+                 uint32_t *__restrict__ m_col) {
+    __shared__ float gs[TILE][TILE + 1];
+    const int b = blockIdx.y;
+    const int tiles_x = is / TILE;
+    const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int W = is / 32;
+    if (aa) {
+        const int R = is / 2, rtop = R - 1 - (ty0 >> 1);
+        for (int i = threadIdx.x; i < (TILE / 2) * (TILE / 2); i += NTHREADS) {
+            const int m = i / (TILE / 2), cc = i % (TILE / 2);
+            gs[m][cc] = grad_alpha[((long)b * R + (rtop - m)) * R + (tx0 >> 1) + cc];
+        }
+    } else {
+        for (int i = threadIdx.x; i < TILE * TILE; i += NTHREADS) {
+            const int yl = i / TILE, xl = i % TILE;
+            gs[yl][xl] = grad_alpha[((long)b * is + (is - 1 - ty0 - yl)) * is + tx0 + xl];
+        }
+    }
+    __syncthreads();
+    const int sh = aa ? 1 : 0;
+    const long plane = (long)is * W;
+    for (int task = warp; task < 2 * TILE; task += NWARPS) {
+        {   // row words: line = raster row, bit = x
+            const int yl = task >> 1, w = task & 1, xl = w * 32 + lane;
+            const float g = gs[yl >> sh][xl >> sh];
+            const unsigned neg = __ballot_sync(0xffffffffu, g < 0.f), pos = __ballot_sync(0xffffffffu, g > 0.f);
+            if (lane == 0) {
+                const long o = ((long)b * 2 * is + (ty0 + yl)) * W + (tx0 >> 5) + w;
+                const unsigned A = cov_row[((long)b * is + (ty0 + yl)) * W + (tx0 >> 5) + w];
+                m_row[o] = neg & ~A;
+                m_row[o + plane] = pos & A;
+            }
+        }
+        {   // column words: line = raster column, bit = y
+            const int xl = task >> 1, w = task & 1, yl = w * 32 + lane;
+            const float g = gs[yl >> sh][xl >> sh];
+            const unsigned neg = __ballot_sync(0xffffffffu, g < 0.f), pos = __ballot_sync(0xffffffffu, g > 0.f);
+            if (lane == 0) {
+                const long o = ((long)b * 2 * is + (tx0 + xl)) * W + (ty0 >> 5) + w;
+                const unsigned A = cov_col[((long)b * is + (tx0 + xl)) * W + (ty0 >> 5) + w];
+                m_col[o] = neg & ~A;
+                m_col[o + plane] = pos & A;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ backward
+struct BwdCtx {
+    const float *grad;  // grad_alpha of this image [R,R]
+    int is, aa, R;
+    float eps;
+};
+
+__device__ __forceinline__ float fetch_grad(const BwdCtx &c, int y, int x) {
+    if (c.aa) return 0.25f * __ldg(c.grad + (long)((c.is - 1 - y) >> 1) * c.R + (x >> 1));
+    return __ldg(c.grad + (long)(c.is - 1 - y) * c.R + x);
+}
+
+// Visits the set bits of `line` (one raster row or column, W words) in [a, c] and accumulates the
+// two vertex contributions of backward_pixel_map for the crossing (d0, d1_cross).
+template <int AXIS>
+__device__ __forceinline__ void sweep(const uint32_t *line, int a, int c, int d0, float d1_cross, float ka,
+                                      float p0d0, float p1d0, const BwdCtx &ctx, float &acc0, float &acc1) {
+    if (a > c) return;
+    const float fd0 = (float)d0;
+    const bool has0 = p1d0 != fd0, has1 = p0d0 != fd0;
+    const float c0 = ka / (p1d0 - fd0), c1 = ka / (fd0 - p0d0);
+    const int wa = a >> 5, wc = c >> 5;
+    for (int w = wa; w <= wc; ++w) {
+        unsigned bits = line[w];
+        if (w == wa) bits &= 0xffffffffu << (a & 31);
+        if (w == wc) bits &= 0xffffffffu >> (31 - (c & 31));
+        while (bits) {
+            const int bit = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int d1 = w * 32 + bit;
+            const float g = AXIS == 0 ? fetch_grad(ctx, d1, d0) : fetch_grad(ctx, d0, d1);
+            const float diff = fabsf(g);
+            const float dd = (float)d1 - d1_cross;
+            if (has0) {
+                float dist = c0 * dd * 2.f / (float)ctx.is;
+                dist = (0.f < dist) ? dist + ctx.eps : dist - ctx.eps;
+                acc0 -= diff / dist;
+            }
+            if (has1) {
+                float dist = c1 * dd * 2.f / (float)ctx.is;
+                dist = (0.f < dist) ? dist + ctx.eps : dist - ctx.eps;
+                acc1 -= diff / dist;
+            }
+        }
+    }
+}
+
+struct BwdSmem {
+    const int *fi;                                // [TILE*TILE] face_index tile
+    const uint32_t *a_row, *mn_row, *mp_row;      // [TILE][W] lines through the tile rows
+    const uint32_t *a_col, *mn_col, *mp_col;      // [TILE][W] lines through the tile columns
+};
+
+// One (edge, axis) of one face, crossings whose in-pixel lies in this tile.
+template <int AXIS>
+__device__ __forceinline__ void edge_axis(const float (&pp)[3][2], int e, int fn, int tx0, int ty0, int W,
+                                          const BwdSmem &s, const BwdCtx &ctx, float &acc0, float &acc1) {
+    const int lane = threadIdx.x & 31;
+    const int i0 = e, i1 = (e + 1) % 3, i2 = (e + 2) % 3;
+    const float p0d0 = pp[i0][AXIS], p0d1 = pp[i0][1 - AXIS];
+    const float p1d0 = pp[i1][AXIS], p1d1 = pp[i1][1 - AXIS];
+    const float p2d0 = pp[i2][AXIS], p2d1 = pp[i2][1 - AXIS];
+    const int is = ctx.is;
+    int dir;
+    if (AXIS == 0) dir = (p0d0 < p1d0) ? -1 : 1;
+    else dir = (p0d0 < p1d0) ? 1 : -1;
+    const int d0_from = __float2int_rz(fmaxf(ceilf(fminf(p0d0, p1d0)), 0.f));
+    const int d0_to = __float2int_rz(fminf(fmaxf(p0d0, p1d0), (float)(is - 1)));
+    const int t0 = AXIS == 0 ? tx0 : ty0;  // tile origin along d0
+    const int t1 = AXIS == 0 ? ty0 : tx0;  // tile origin along d1
+    const int lo = max(d0_from, t0), hi = min(d0_to, t0 + TILE - 1);
+    const float ka = p1d0 - p0d0;
+    const float slope = (p1d1 - p0d1) / ka;
+    for (int d0 = lo + lane; d0 <= hi; d0 += 32) {
+        const float d1_cross = slope * ((float)d0 - p0d0) + p0d1;
+        const int d1_in = __float2int_rz(dir > 0 ? floorf(d1_cross) : ceilf(d1_cross));
+        const int d1_out = d1_in + dir;
+        if (d1_in < 0 || is <= d1_in) continue;
+        if (d1_out < 0 || is <= d1_out) continue;
+        if (d1_in < t1 || d1_in >= t1 + TILE) continue;  // another tile owns this crossing
+        const int l0 = d0 - t0;                          // line index inside the tile
+        const uint32_t *A = (AXIS == 0 ? s.a_col : s.a_row) + l0 * W;
+        const uint32_t *Mn = (AXIS == 0 ? s.mn_col : s.mn_row) + l0 * W;
+        const uint32_t *Mp = (AXIS == 0 ? s.mp_col : s.mp_row) + l0 * W;
+        const int fi_in = AXIS == 0 ? s.fi[(d1_in - t1) * TILE + l0] : s.fi[l0 * TILE + (d1_in - t1)];
+        // out-sweep: from the out pixel to the image border, only when this face owns the in pixel
+        if (fi_in == fn) {
+            const int lim = dir > 0 ? is - 1 : 0;
+            sweep<AXIS>(Mn, min(d1_out, lim), max(d1_out, lim), d0, d1_cross, ka, p0d0, p1d0, ctx, acc0, acc1);
+        }
+        // in-sweep: from the in pixel to the opposite edge of the triangle
+        {
+            const float fd0 = (float)d0;
+            float c2;
+            if ((fd0 - p0d0) * (fd0 - p2d0) < 0.f) c2 = (p2d1 - p0d1) / (p2d0 - p0d0) * (fd0 - p0d0) + p0d1;
+            else c2 = (p1d1 - p2d1) / (p1d0 - p2d0) * (fd0 - p2d0) + p2d1;
+            const int lim = __float2int_rz(dir > 0 ? ceilf(c2) : floorf(c2));
+            int a = min(d1_in, lim), c = max(d1_in, lim);
+            a = max(a, 0);
+            c = min(c, is - 1);
+            const bool alpha_out = (A[d1_out >> 5] >> (d1_out & 31)) & 1u;
+            sweep<AXIS>(alpha_out ? Mn : Mp, a, c, d0, d1_cross, ka, p0d0, p1d0, ctx, acc0, acc1);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS)
+raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
+                  float eps, const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
+                  const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ cov_col,
+                  const uint32_t *__restrict__ m_row, const uint32_t *__restrict__ m_col,
+                  float *__restrict__ grad_ndc) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ int list[NTHREADS];
+    __shared__ int cnt;
+    __shared__ float wacc[NWARPS][6];
+    __shared__ __align__(8) uint64_t bar;
+    const int W = is / 32;
+    int *fi = reinterpret_cast<int *>(smem_raw);
+    uint32_t *lines = reinterpret_cast<uint32_t *>(smem_raw + TILE * TILE * sizeof(int));
+    const int LW = TILE * W;  // words per line block
+    const int b = blockIdx.y;
+    const int tiles_x = is / TILE;
+    const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    // ---- stage the tile's face_index rows and the six bit-line blocks with TMA bulk copies
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (lane == 0) mbar_expect_tx(&bar, (uint32_t)(TILE * TILE * 4 + 6 * LW * 4));
+        __syncwarp();
+        for (int r = lane; r < TILE; r += 32)
+            tma_bulk_g2s(fi + r * TILE, face_index + ((long)b * is + ty0 + r) * is + tx0, TILE * 4, &bar);
+        if (lane < 6) {
+            const long plane = (long)is * W;
+            const uint32_t *src;
+            switch (lane) {
+                case 0: src = cov_row + ((long)b * is + ty0) * W; break;
+                case 1: src = m_row + ((long)b * 2 * is + ty0) * W; break;
+                case 2: src = m_row + ((long)b * 2 * is + ty0) * W + plane; break;
+                case 3: src = cov_col + ((long)b * is + tx0) * W; break;
+                case 4: src = m_col + ((long)b * 2 * is + tx0) * W; break;
+                default: src = m_col + ((long)b * 2 * is + tx0) * W + plane; break;
+            }
+            tma_bulk_g2s(lines + lane * LW, src, (uint32_t)(LW * 4), &bar);
+        }
+    }
+    BwdSmem s;
+    s.fi = fi;
+    s.a_row = lines; s.mn_row = lines + LW; s.mp_row = lines + 2 * LW;
+    s.a_col = lines + 3 * LW; s.mn_col = lines + 4 * LW; s.mp_col = lines + 5 * LW;
+    BwdCtx ctx;
+    ctx.is = is; ctx.aa = aa; ctx.R = aa ? is / 2 : is; ctx.eps = eps;
+    ctx.grad = grad_alpha + (long)b * ctx.R * ctx.R;
+    recs += (long)b * F;
+    boxes += (long)b * F;
+    grad_ndc += (long)b * V * 3;
+    bool staged = false;
+
+    for (int base = 0; base < F; base += NTHREADS) {
+        const int n = collect_faces(boxes, base, F, tx0, ty0, list, &cnt);
+        if (n > 0 && !staged) {
+            mbar_wait(&bar, 0);
+            staged = true;
+        }
+        for (int li = warp; li < n; li += NWARPS) {
+            const FaceRec *rp = recs + list[li];
+            const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rp));
+            const float4 q1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
+            const float4 q2 = __ldg(reinterpret_cast<const float4 *>(rp) + 2);
+            const int4 q3 = __ldg(reinterpret_cast<const int4 *>(rp) + 3);
+            const int fn = __float_as_int(q2.y);
+            const int vid[3] = {__float_as_int(q2.z), __float_as_int(q2.w), q3.x};
+            float pp[3][2];
+            pp[0][0] = to_pix(q0.x, is); pp[0][1] = to_pix(q0.y, is);
+            pp[1][0] = to_pix(q0.w, is); pp[1][1] = to_pix(q1.x, is);
+            pp[2][0] = to_pix(q1.z, is); pp[2][1] = to_pix(q1.w, is);
+            if (lane < 6) wacc[warp][lane] = 0.f;
+            __syncwarp();
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                // axis 0: d0 = x, sweeps along y, gradient on the y slot; axis 1: the transpose
+                float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+                edge_axis<0>(pp, e, fn, tx0, ty0, W, s, ctx, a0, a1);
+                edge_axis<1>(pp, e, fn, tx0, ty0, W, s, ctx, b0, b1);
+                const bool any = (a0 != 0.f) | (a1 != 0.f) | (b0 != 0.f) | (b1 != 0.f);
+                if (__ballot_sync(0xffffffffu, any)) {
+                    a0 = warp_sum(a0); a1 = warp_sum(a1); b0 = warp_sum(b0); b1 = warp_sum(b1);
+                    if (lane == 0) {
+                        const int i0 = e, i1 = (e + 1) % 3;
+                        wacc[warp][i0 * 2 + 1] += a0;  // slot pi0*3 + (1 - axis), axis 0 -> y
+                        wacc[warp][i1 * 2 + 1] += a1;
+                        wacc[warp][i0 * 2 + 0] += b0;  // axis 1 -> x
+                        wacc[warp][i1 * 2 + 0] += b1;
+                    }
+                }
+                __syncwarp();
+            }
+            if (lane < 6) {
+                const float g = wacc[warp][lane];
+                if (g != 0.f) atomicAdd(grad_ndc + (long)vid[lane >> 1] * 3 + (lane & 1), g);
+            }
+            __syncwarp();
+        }
+        __syncthreads();
+    }
+    if (!staged) mbar_wait(&bar, 0);  // never exit with bulk copies in flight
+}
+
+// ------------------------------------------------------------------------------------------ silhouette loss
+__global__ void __launch_bounds__(NTHREADS)
+sil_loss_kernel(const float *__restrict__ alpha, const int8_t *__restrict__ target, const float *__restrict__ norm,
+                float weight, int npix, float *__restrict__ loss_img, int loss_stride, float *__restrict__ iou_img,
+                int iou_stride, float *__restrict__ grad_alpha) {
+    __shared__ float scratch[3 * 32];
+    const int b = blockIdx.x;
+    const float nb = norm[b];
+    const float gscale = 2.f * weight * nb;
+    const float4 *a4 = reinterpret_cast<const float4 *>(alpha + (long)b * npix);
+    const char4 *t4 = reinterpret_cast<const char4 *>(target + (long)b * npix);
+    float4 *g4 = reinterpret_cast<float4 *>(grad_alpha + (long)b * npix);
+    float acc[3] = {0.f, 0.f, 0.f};  // sum sq, intersection, union
+    for (int i = threadIdx.x; i < npix / 4; i += NTHREADS) {
+        const float4 a = a4[i];
+        const char4 t = t4[i];
+        const float av[4] = {a.x, a.y, a.z, a.w};
+        const int tv[4] = {t.x, t.y, t.z, t.w};
+        float gv[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float keep = tv[k] >= 0 ? 1.f : 0.f, ref = tv[k] > 0 ? 1.f : 0.f;
+            const float img = keep * av[k];
+            const float d = img - ref;
+            acc[0] += d * d;
+            acc[1] += img * ref;
+            acc[2] += fminf(fmaxf(img + ref, 0.f), 1.f);
+            gv[k] = gscale * keep * d;
+        }
+        if (grad_alpha) g4[i] = make_float4(gv[0], gv[1], gv[2], gv[3]);
+    }
+    block_sum<3>(acc, scratch);
+    if (threadIdx.x == 0) {
+        if (loss_img) loss_img[(long)b * loss_stride] = acc[0] * nb;
+        if (iou_img) iou_img[(long)b * iou_stride] = acc[1] / (acc[2] + 1e-6f);
+    }
+}
+
+int check_raster_size(int image_size, int aa, int *is_out) {
+    const int is = aa ? 2 * image_size : image_size;
+    HM_REQUIRE(image_size > 0, "image_size must be positive");
+    HM_UNSUPPORTED(is % TILE != 0 || is > 16384, "raster size %d must be a multiple of %d (<= 16384)", is, TILE);
+    *is_out = is;
+    return HM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hm_project_fwd(const float *verts, const float *K, int K_batch, const float *R, const float *t,
+                   const float *dist, int dist_batch, float orig_size, float eps, int B, int V, float *ndc,
+                   void *stream) {
+    HM_REQUIRE(verts && K && ndc, "hm_project_fwd: null pointer");
+    HM_REQUIRE(B >= 0 && V >= 0 && (K_batch == 1 || K_batch == B), "hm_project_fwd: bad sizes B=%d V=%d K_batch=%d", B, V, K_batch);
+    if ((long)B * V == 0) return HM_OK;
+    const long n = (long)B * V;
+    project_fwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, hm_stream(stream)>>>(verts, K, K_batch, R, t, dist,
+                                                                                  dist_batch, orig_size, eps, B, V, ndc);
+    HM_CHECK_LAUNCH("hm_project_fwd");
+    return HM_OK;
+}
+
+int hm_project_bwd(const float *verts, const float *K, int K_batch, const float *R, const float *t,
+                   float orig_size, float eps, int B, int V, const float *grad_ndc, float *grad_verts,
+                   int accumulate, void *stream) {
+    HM_REQUIRE(verts && K && grad_ndc && grad_verts, "hm_project_bwd: null pointer");
+    HM_REQUIRE(B >= 0 && V >= 0 && (K_batch == 1 || K_batch == B), "hm_project_bwd: bad sizes");
+    if ((long)B * V == 0) return HM_OK;
+    const long n = (long)B * V;
+    project_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, hm_stream(stream)>>>(verts, K, K_batch, R, t, orig_size,
+                                                                                  eps, B, V, grad_ndc, grad_verts,
+                                                                                  accumulate);
+    HM_CHECK_LAUNCH("hm_project_bwd");
+    return HM_OK;
+}
+
+int hm_raster_setup(const float *ndc, const int32_t *faces, int faces_batch, int B, int V, int F,
+                    int image_size, int anti_aliasing, int fill_back, void *records, void *bboxes,
+                    void *stream) {
+    HM_REQUIRE(ndc && faces && records && bboxes, "hm_raster_setup: null pointer");
+    HM_REQUIRE(B >= 0 && V > 0 && F >= 0 && (faces_batch == 1 || faces_batch == B), "hm_raster_setup: bad sizes");
+    int is;
+    if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
+    if ((long)B * F == 0) return HM_OK;
+    const long n = (long)B * F;
+    face_setup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, hm_stream(stream)>>>(
+        ndc, faces, faces_batch, B, V, F, is, fill_back, static_cast<FaceRec *>(records),
+        static_cast<FaceBox *>(bboxes));
+    HM_CHECK_LAUNCH("hm_raster_setup");
+    return HM_OK;
+}
+
+int hm_raster_sil_fwd(const void *records, const void *bboxes, int B, int F, int image_size,
+                      int anti_aliasing, float near_, float far_, int32_t *face_index, float *alpha,
+                      uint32_t *cov_row, uint32_t *cov_col, void *stream) {
+    HM_REQUIRE(records && bboxes && face_index && alpha, "hm_raster_sil_fwd: null pointer");
+    HM_REQUIRE(B >= 0 && F >= 0 && B <= 65535, "hm_raster_sil_fwd: bad sizes (B <= 65535)");
+    int is;
+    if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
+    if (B == 0) return HM_OK;
+    dim3 grid((is / TILE) * (is / TILE), B);
+    raster_fwd_kernel<<<grid, NTHREADS, 0, hm_stream(stream)>>>(
+        static_cast<const FaceRec *>(records), static_cast<const FaceBox *>(bboxes), F, is, anti_aliasing, near_, far_,
+        face_index, alpha, cov_row, cov_col);
+    HM_CHECK_LAUNCH("hm_raster_sil_fwd");
+    return HM_OK;
+}
+
+int hm_raster_grad_prep(const float *grad_alpha, const uint32_t *cov_row, const uint32_t *cov_col, int B,
+                        int image_size, int anti_aliasing, uint32_t *m_row, uint32_t *m_col, void *stream) {
+    HM_REQUIRE(grad_alpha && cov_row && cov_col && m_row && m_col, "hm_raster_grad_prep: null pointer");
+    HM_REQUIRE(B >= 0 && B <= 65535, "hm_raster_grad_prep: bad sizes");
+    int is;
+    if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
+    if (B == 0) return HM_OK;
+    dim3 grid((is / TILE) * (is / TILE), B);
+    grad_prep_kernel<<<grid, NTHREADS, 0, hm_stream(stream)>>>(grad_alpha, cov_row, cov_col, is, anti_aliasing, m_row,
+                                                               m_col);
+    HM_CHECK_LAUNCH("hm_raster_grad_prep");
+    return HM_OK;
+}
+
+int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *face_index,
+                      const float *grad_alpha, const uint32_t *cov_row, const uint32_t *cov_col,
+                      const uint32_t *m_row, const uint32_t *m_col, int B, int V, int F, int image_size,
+                      int anti_aliasing, float eps, float *grad_ndc, void *stream) {
+    HM_REQUIRE(records && bboxes && face_index && grad_alpha && cov_row && cov_col && m_row && m_col && grad_ndc,
+               "hm_raster_sil_bwd: null pointer");
+    HM_REQUIRE(B >= 0 && F >= 0 && V > 0 && B <= 65535, "hm_raster_sil_bwd: bad sizes");
+    int is;
+    if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
+    if (B == 0 || F == 0) return HM_OK;
+    const size_t smem = (size_t)TILE * TILE * 4 + (size_t)6 * TILE * (is / 32) * 4;
+    HM_UNSUPPORTED(smem > 200 * 1024, "hm_raster_sil_bwd: raster size %d needs %zu B of shared memory", is, smem);
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(raster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) {
+            hm_set_error("hm_raster_sil_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return HM_ERR_CUDA;
+        }
+    }
+    dim3 grid((is / TILE) * (is / TILE), B);
+    raster_bwd_kernel<<<grid, NTHREADS, smem, hm_stream(stream)>>>(
+        static_cast<const FaceRec *>(records), static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps,
+        face_index, grad_alpha, cov_row, cov_col, m_row, m_col, grad_ndc);
+    HM_CHECK_LAUNCH("hm_raster_sil_bwd");
+    return HM_OK;
+}
+
+int hm_sil_loss_fwd_bwd(const float *alpha, const int8_t *target, const float *norm, float weight, int B,
+                        int image_size, float *loss_img, int loss_stride, float *iou_img, int iou_stride,
+                        float *grad_alpha, void *stream) {
+    HM_REQUIRE(alpha && target && norm, "hm_sil_loss_fwd_bwd: null pointer");
+    HM_REQUIRE(B >= 0 && image_size > 0 && (image_size * image_size) % 4 == 0, "hm_sil_loss_fwd_bwd: bad sizes");
+    if (B == 0) return HM_OK;
+    sil_loss_kernel<<<B, NTHREADS, 0, hm_stream(stream)>>>(alpha, target, norm, weight, image_size * image_size,
+                                                           loss_img, loss_stride, iou_img, iou_stride, grad_alpha);
+    HM_CHECK_LAUNCH("hm_sil_loss_fwd_bwd");
+    return HM_OK;
+}
+
+}  // extern "C"

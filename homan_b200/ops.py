@@ -1,0 +1,132 @@
+"""torch.autograd.Function wrappers over the C ABI (libhoman_b200.so). GPU only, no fallback.
+
+Each op names the reference interface it stands in for; the arithmetic lives in homan_b200/csrc/*.cu.
+"""
+import torch
+
+from . import _lib
+from ._lib import call, current_stream, ptr
+
+NEAR, FAR, RASTER_EPS = 0.1, 100.0, 1e-4
+
+
+def _check_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.HomanB200Error("homan_b200 ops need CUDA tensors (there is no CPU path)")
+
+
+def _f32(t):
+    return t.detach().contiguous().float()
+
+
+# ------------------------------------------------------------------------------------------ projection
+class _Project(torch.autograd.Function):
+    """nr.projection (neural_renderer; call sites /root/reference/homan/losses.py:34-41)."""
+
+    @staticmethod
+    def forward(ctx, verts, K, R, t, dist, orig_size, eps):
+        _check_cuda(verts, K)
+        v = _f32(verts)
+        K = _f32(K).view(-1, 3, 3)
+        B, V = v.shape[:2]
+        R = None if R is None else _f32(R).view(-1)
+        t = None if t is None else _f32(t).view(-1)
+        dist = None if dist is None else _f32(dist).view(-1, 5)
+        ndc = torch.empty_like(v)
+        call("hm_project_fwd", ptr(v), ptr(K), K.shape[0], ptr(R), ptr(t), ptr(dist),
+             0 if dist is None else dist.shape[0], float(orig_size), float(eps), B, V, ptr(ndc), current_stream())
+        ctx.save_for_backward(v, K, R, t)
+        ctx.meta = (float(orig_size), float(eps), dist is not None and bool((dist != 0).any()))
+        return ndc
+
+    @staticmethod
+    def backward(ctx, grad_ndc):
+        v, K, R, t = ctx.saved_tensors
+        orig_size, eps, has_dist = ctx.meta
+        if has_dist:
+            raise _lib.HomanB200Error("projection backward supports zero distortion only")
+        B, V = v.shape[:2]
+        g = _f32(grad_ndc)
+        out = torch.empty_like(v)
+        call("hm_project_bwd", ptr(v), ptr(K), K.shape[0], ptr(R), ptr(t), orig_size, eps, B, V, ptr(g), ptr(out), 0,
+             current_stream())
+        return out, None, None, None, None, None, None
+
+
+def project(verts, K, R=None, t=None, dist_coeffs=None, orig_size=1.0, eps=1e-9):
+    return _Project.apply(verts, K, R, t, dist_coeffs, orig_size, eps)
+
+
+# ------------------------------------------------------------------------------------------ rasteriser
+class RasterBuffers:
+    """Scratch of one silhouette render (records, bboxes, face_index, coverage / sweep bitmaps)."""
+
+    def __init__(self, B, V, F, image_size, anti_aliasing, device):
+        self.B, self.V, self.F, self.image_size, self.aa = B, V, F, image_size, bool(anti_aliasing)
+        S = image_size * 2 if anti_aliasing else image_size
+        self.S = S
+        self.records = torch.empty(B * F * 64, dtype=torch.uint8, device=device)
+        self.bboxes = torch.empty(B * F * 8, dtype=torch.uint8, device=device)
+        self.face_index = torch.empty(B, S, S, dtype=torch.int32, device=device)
+        self.alpha = torch.empty(B, image_size, image_size, dtype=torch.float32, device=device)
+        self.cov_row = torch.empty(B, S, S // 32, dtype=torch.int32, device=device)
+        self.cov_col = torch.empty(B, S, S // 32, dtype=torch.int32, device=device)
+        self.m_row = torch.empty(B, 2, S, S // 32, dtype=torch.int32, device=device)
+        self.m_col = torch.empty(B, 2, S, S // 32, dtype=torch.int32, device=device)
+
+
+def raster_forward(buf, ndc, faces, fill_back=True, near=NEAR, far=FAR):
+    """ndc [B,V,3] fp32, faces [1|B,F,3] int32 -> buf.alpha [B,R,R] (+ face_index, coverage)."""
+    s = current_stream()
+    call("hm_raster_setup", ptr(ndc), ptr(faces), faces.shape[0], buf.B, buf.V, buf.F, buf.image_size, int(buf.aa),
+         int(fill_back), ptr(buf.records), ptr(buf.bboxes), s)
+    call("hm_raster_sil_fwd", ptr(buf.records), ptr(buf.bboxes), buf.B, buf.F, buf.image_size, int(buf.aa),
+         float(near), float(far), ptr(buf.face_index), ptr(buf.alpha), ptr(buf.cov_row), ptr(buf.cov_col), s)
+    return buf.alpha
+
+
+def raster_backward(buf, grad_alpha, grad_ndc, eps=RASTER_EPS):
+    """grad_alpha [B,R,R] -> grad_ndc [B,V,3] += (approximate NMR gradient, x / y slots)."""
+    s = current_stream()
+    call("hm_raster_grad_prep", ptr(grad_alpha), ptr(buf.cov_row), ptr(buf.cov_col), buf.B, buf.image_size,
+         int(buf.aa), ptr(buf.m_row), ptr(buf.m_col), s)
+    call("hm_raster_sil_bwd", ptr(buf.records), ptr(buf.bboxes), ptr(buf.face_index), ptr(grad_alpha),
+         ptr(buf.cov_row), ptr(buf.cov_col), ptr(buf.m_row), ptr(buf.m_col), buf.B, buf.V, buf.F, buf.image_size,
+         int(buf.aa), float(eps), ptr(grad_ndc), s)
+    return grad_ndc
+
+
+class _RasterizeSilhouettes(torch.autograd.Function):
+    """fill_back + vertices_to_faces + rasterize_silhouettes of neural_renderer
+    (/root/reference/homan/losses.py:187 via Renderer.render_silhouettes)."""
+
+    @staticmethod
+    def forward(ctx, ndc, faces, image_size, anti_aliasing, fill_back, near, far, eps):
+        _check_cuda(ndc, faces)
+        ndc_c = _f32(ndc)
+        faces_c = faces.detach().contiguous().int()
+        if faces_c.dim() == 2:
+            faces_c = faces_c[None]
+        B, V = ndc_c.shape[:2]
+        F = faces_c.shape[1]
+        buf = RasterBuffers(B, V, F, image_size, anti_aliasing, ndc_c.device)
+        raster_forward(buf, ndc_c, faces_c, fill_back, near, far)
+        ctx.buf = buf
+        ctx.eps = eps
+        ctx.mark_non_differentiable(buf.face_index)
+        return buf.alpha, buf.face_index
+
+    @staticmethod
+    def backward(ctx, grad_alpha, _grad_fi):
+        buf = ctx.buf
+        g = _f32(grad_alpha)
+        grad_ndc = torch.zeros(buf.B, buf.V, 3, dtype=torch.float32, device=g.device)
+        raster_backward(buf, g, grad_ndc, ctx.eps)
+        return grad_ndc, None, None, None, None, None, None, None
+
+
+def rasterize_silhouettes(ndc, faces, image_size=256, anti_aliasing=True, fill_back=True, near=NEAR, far=FAR,
+                          eps=RASTER_EPS, return_face_index=False):
+    alpha, face_index = _RasterizeSilhouettes.apply(ndc, faces, image_size, anti_aliasing, fill_back, near, far, eps)
+    return (alpha, face_index) if return_face_index else alpha
