@@ -80,6 +80,74 @@ __device__ __forceinline__ void block_sum(float (&v)[N], float *scratch) {
     __syncthreads();
 }
 
+// Block-wide max of N values per thread (same contract as block_sum).
+template <int N>
+__device__ __forceinline__ void block_max(float (&v)[N], float *scratch) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = warp_max(v[i]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) scratch[i * 32 + warp] = v[i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            float x = lane < nwarps ? scratch[i * 32 + lane] : -3.4e38f;
+            x = warp_max(x);
+            if (lane == 0) scratch[i * 32] = x;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = scratch[i * 32];
+    __syncthreads();
+}
+
+// rot6d_to_matrix (homan/utils/geometry.py:9-27) and its backward. r6 is the [3,2] row-major parameter;
+// R is row-major with columns b1 b2 b3.
+struct Rot6d {
+    float a1[3], a2[3], b1[3], b2[3], n1, nu, R[9];
+};
+__device__ inline void rot6d_forward(const float *r6, Rot6d &o) {
+    for (int i = 0; i < 3; ++i) { o.a1[i] = r6[2 * i]; o.a2[i] = r6[2 * i + 1]; }
+    o.n1 = fmaxf(sqrtf(o.a1[0] * o.a1[0] + o.a1[1] * o.a1[1] + o.a1[2] * o.a1[2]), 1e-12f);
+    for (int i = 0; i < 3; ++i) o.b1[i] = o.a1[i] / o.n1;
+    const float dp = o.b1[0] * o.a2[0] + o.b1[1] * o.a2[1] + o.b1[2] * o.a2[2];
+    float u[3];
+    for (int i = 0; i < 3; ++i) u[i] = o.a2[i] - dp * o.b1[i];
+    o.nu = fmaxf(sqrtf(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]), 1e-12f);
+    for (int i = 0; i < 3; ++i) o.b2[i] = u[i] / o.nu;
+    const float b3[3] = {o.b1[1] * o.b2[2] - o.b1[2] * o.b2[1], o.b1[2] * o.b2[0] - o.b1[0] * o.b2[2],
+                         o.b1[0] * o.b2[1] - o.b1[1] * o.b2[0]};
+    for (int i = 0; i < 3; ++i) { o.R[i * 3] = o.b1[i]; o.R[i * 3 + 1] = o.b2[i]; o.R[i * 3 + 2] = b3[i]; }
+}
+// G = d loss / d R (row-major) -> g6 [3,2] row-major (written, not accumulated)
+__device__ inline void rot6d_backward(const Rot6d &o, const float *G, float *g6) {
+    float gb1[3] = {G[0], G[3], G[6]}, gb2[3] = {G[1], G[4], G[7]};
+    const float gb3[3] = {G[2], G[5], G[8]};
+    const float *b1 = o.b1, *b2 = o.b2, *a2 = o.a2;
+    gb1[0] += b2[1] * gb3[2] - b2[2] * gb3[1]; gb1[1] += b2[2] * gb3[0] - b2[0] * gb3[2]; gb1[2] += b2[0] * gb3[1] - b2[1] * gb3[0];
+    gb2[0] += gb3[1] * b1[2] - gb3[2] * b1[1]; gb2[1] += gb3[2] * b1[0] - gb3[0] * b1[2]; gb2[2] += gb3[0] * b1[1] - gb3[1] * b1[0];
+    const float d2 = gb2[0] * b2[0] + gb2[1] * b2[1] + gb2[2] * b2[2];
+    float gu[3];
+    for (int i = 0; i < 3; ++i) gu[i] = (gb2[i] - d2 * b2[i]) / o.nu;
+    const float dp = b1[0] * a2[0] + b1[1] * a2[1] + b1[2] * a2[2];
+    const float gub1 = gu[0] * b1[0] + gu[1] * b1[1] + gu[2] * b1[2];
+    float ga2[3];
+    for (int i = 0; i < 3; ++i) {
+        ga2[i] = gu[i] - gub1 * b1[i];
+        gb1[i] += -dp * gu[i] - gub1 * a2[i];
+    }
+    const float d1 = gb1[0] * b1[0] + gb1[1] * b1[1] + gb1[2] * b1[2];
+    for (int i = 0; i < 3; ++i) {
+        g6[2 * i] = (gb1[i] - d1 * b1[i]) / o.n1;
+        g6[2 * i + 1] = ga2[i];
+    }
+}
+
 // 1-D bulk asynchronous copy global -> shared through the TMA unit (cp.async.bulk, SASS UBLKCP),
 // completion signalled on an mbarrier. Addresses and size must be multiples of 16 bytes.
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

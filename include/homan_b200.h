@@ -84,6 +84,117 @@ int hm_sil_loss_fwd_bwd(const float *alpha, const int8_t *target, const float *n
                         int image_size, float *loss_img, int loss_stride, float *iou_img, int iou_stride,
                         float *grad_alpha, void *stream);
 
+/* ---------------------------------------------------------------- MANO + rigid placement of the hand
+ * ManoModel.forward_pca (homan/manomodel.py:84-151) -> mano layer LBS (un-vendored `mano` package,
+ * manomodel.py:119-123,136-140) -> + mano_trans -> rot6d_to_matrix (homan/utils/geometry.py:9-27) ->
+ * compute_transformation_persp (homan/utils/camera.py:108-139), i.e. HOMan.get_verts_hand
+ * (homan/homan.py:341-382), and its autograd.
+ * `model` is one fp32 blob (offsets in floats below); J_template = J_regressor @ v_template and
+ * J_shapedirs = J_regressor @ shapedirs are folded by the caller; comps holds ncomps rows of 45.
+ * pca [B,pca_stride] (first ncomps used), rot [B,3] (mano global orient), betas [B,10] (NULL = 0),
+ * mano_trans [B,3] (NULL = 0), rot6d [B,3,2] (NULL = no rigid placement: plain MANO layer output),
+ * trans [B,3], scale [1] (NULL = 1).  verts [B,778,3]; joints [B,16,3] (mano frame, may be NULL). */
+#define HM_MANO_NV 778
+#define HM_MANO_NJ 16
+#define HM_MANO_OFF_VTEMPLATE 0
+#define HM_MANO_OFF_SHAPEDIRS (HM_MANO_OFF_VTEMPLATE + 778 * 3)        /* [778,3,10] */
+#define HM_MANO_OFF_POSEDIRS (HM_MANO_OFF_SHAPEDIRS + 778 * 3 * 10)    /* [135,2334] */
+#define HM_MANO_OFF_JTEMPLATE (HM_MANO_OFF_POSEDIRS + 135 * 2334)      /* [16,3] */
+#define HM_MANO_OFF_JSHAPEDIRS (HM_MANO_OFF_JTEMPLATE + 48)            /* [16,3,10] */
+#define HM_MANO_OFF_WEIGHTS (HM_MANO_OFF_JSHAPEDIRS + 480)             /* [778,16] */
+#define HM_MANO_OFF_MEAN (HM_MANO_OFF_WEIGHTS + 778 * 16)              /* [45] (+3 pad) */
+#define HM_MANO_OFF_COMPS (HM_MANO_OFF_MEAN + 48)                      /* [ncomps,45] */
+#define HM_MANO_BLOB_FLOATS(ncomps) (HM_MANO_OFF_COMPS + (ncomps) * 45)
+int hm_mano_fwd(const float *model, int ncomps, int left, const float *pca, int pca_stride, const float *rot,
+                const float *betas, const float *mano_trans, const float *rot6d, const float *trans,
+                const float *scale, int B, float *verts, float *joints, void *stream);
+/* grad_verts [B,778,3]; grad_centroid_det [B,3] (may be NULL) is d loss / d mean_v(verts) through the
+ * mesh-detached twin of compute_transformation_persp (reaches rot6d / trans only; homan/homan.py:484-490).
+ * All outputs are accumulated (+=) and may be NULL. */
+int hm_mano_bwd(const float *model, int ncomps, int left, const float *pca, int pca_stride, const float *rot,
+                const float *betas, const float *mano_trans, const float *rot6d, const float *trans,
+                const float *scale, int B, const float *grad_verts, const float *grad_centroid_det,
+                float *grad_pca, float *grad_rot, float *grad_betas, float *grad_mano_trans, float *grad_rot6d,
+                float *grad_trans, void *stream);
+
+/* ---------------------------------------------------------------- rigid placement of the object
+ * HOMan.get_verts_object (homan/homan.py:298-307): verts = (|scale| * mesh) @ rot6d_to_matrix(rot6d) + trans.
+ * mesh [mesh_batch,V,3] (mesh_batch 1 or B), rot6d [B,3,2], trans [B,3], scale [1] (NULL = 1). */
+int hm_rigid_fwd(const float *mesh, int mesh_batch, const float *rot6d, const float *trans, const float *scale,
+                 int B, int V, float *verts, void *stream);
+/* grad_rot6d [B,6] / grad_trans [B,3] += ; the scale is a buffer on this path (optimize_object_scale=0). */
+int hm_rigid_bwd(const float *mesh, int mesh_batch, const float *rot6d, const float *scale, int B, int V,
+                 const float *grad_verts, float *grad_rot6d, float *grad_trans, void *stream);
+
+/* ---------------------------------------------------------------- vertex-space losses (fused fwd + bwd)
+ * compute_smooth_loss (homan/lossutils.py:18-36), compute_verts2d_loss_hand (homan/losses.py:141-164),
+ * compute_interaction_loss + assign_interaction_pairs + project_bbox (homan/losses.py:20-49,98-139,199-242),
+ * compute_pca_loss (homan/lossutils.py:39-40), evaluated per image b = p*T + t with per-problem normalisers.
+ * partials [B, HM_NPART] receives the unweighted per-image contributions (summed per problem by
+ * hm_finalize_losses); gradients are weighted by `w` and accumulated (+=).
+ * w = {smooth_hand, smooth_obj, v2d_hand, inter, pca} ; weight 0 with loss_on 0 skips the term. */
+#define HM_PART_SMOOTH_HAND 0
+#define HM_PART_SMOOTH_OBJ 1
+#define HM_PART_V2D 2
+#define HM_PART_V2D_PX 3      /* metric: sum of pixel distances / 778 */
+#define HM_PART_INTER 4
+#define HM_PART_PCA 5
+#define HM_PART_SIL_OBJ 6
+#define HM_PART_IOU_OBJ 7     /* metric */
+#define HM_PART_SIL_HAND 8
+#define HM_PART_IOU_HAND 9    /* metric */
+#define HM_PART_COLLISION 10
+#define HM_PART_CONTACT 11
+#define HM_PART_MINDIST 12    /* metric: min hand-object vertex distance of the image */
+#define HM_PART_INTER_FLAG 13
+#define HM_NPART 16
+int hm_vertex_losses(const float *verts_hand, const float *verts_obj, const float *camintr,
+                     const float *ref_verts2d, const float *pca, int pca_dim, int B, int T, int Vo,
+                     float image_size, float w_smooth_hand, float w_smooth_obj, float w_v2d, float w_inter,
+                     float w_pca, int flags, float *partials, float *grad_verts_hand, float *grad_verts_obj,
+                     float *grad_centroid_det, float *grad_pca, void *stream);
+#define HM_VL_SMOOTH 1
+#define HM_VL_V2D 2
+#define HM_VL_INTER 4
+#define HM_VL_PCA 8
+
+/* compute_contact_loss, default-argument path (homan/interactions/contactloss.py:149-309): nearest object
+ * vertex of every hand vertex (first minimum of |h|^2 + |o|^2 - 2 h.o), loss = mean 0.02 tanh(d / 0.02);
+ * gradient to both meshes, weighted by `weight / (T * 778)`.  partials as above (CONTACT, MINDIST). */
+int hm_contact_fwd_bwd(const float *verts_hand, const float *verts_obj, int B, int T, int Vo, float thresh,
+                       float weight, float *partials, float *grad_verts_hand, float *grad_verts_obj,
+                       void *stream);
+
+/* ---------------------------------------------------------------- SDF interpenetration
+ * SDFSceneLoss.forward for (hand, object) (homan/interactions/scenesdf.py:77-148, called from
+ * compute_collision_loss, homan/lossutils.py:43-64): phi = clamp(SDF, 0) of the grid mesh in its own
+ * normalised bbox cube, sampled trilinearly (grid_sample, zeros padding, align_corners=False) at the other
+ * mesh's vertices.  Evaluated sparsely: only the voxels that samples touch.  One call = one ordered pair:
+ * grid mesh (verts_g [B,Vg,3], faces_g [Fg,3]) sampled at verts_s [B,Vs,3].
+ * partials[b*HM_NPART + HM_PART_COLLISION] += sum of samples; grad_verts_s += weight * d/d verts_s (may be NULL).
+ * workspace: phi [B, G^3] fp32 scratch (written sparsely). */
+int hm_sdf_pair(const float *verts_g, const int32_t *faces_g, const float *verts_s, int B, int Vg, int Fg,
+                int Vs, int grid, float scale_factor, float weight, float *phi_scratch, float *partials,
+                float *grad_verts_s, void *stream);
+/* sdf.SDF()(faces, vertices) (un-vendored `sdf` package; homan/interactions/scenesdf.py:32,119): dense
+ * signed distance grid phi [B,G,G,G] (inside positive) of vertices already normalised to [-1,1]^3. */
+int hm_sdf_grid(const int32_t *faces, const float *verts, int B, int V, int F, int grid, float *phi,
+                void *stream);
+
+/* ---------------------------------------------------------------- per-problem reduction, Adam, argmin
+ * partials [B,HM_NPART] -> losses [P,HM_NPART] (sums over the T frames of each problem; metrics: mean,
+ * MINDIST -> max) and total[P] = sum_k w[k] * losses[p,k]; also advances the device step counter. */
+int hm_finalize_losses(const float *partials, const float *weights_part, int P, int T, float *losses,
+                       float *total, int *step_counter, void *stream);
+/* torch.optim.Adam step (homan/jointopt.py:138-151,192) on one flat parameter buffer:
+ * lr_per_elem [n] (0 = frozen parameter, e.g. mano_rot / mano_trans which match no optimiser group). */
+int hm_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
+                 const float *lr_per_elem, int n, float beta1, float beta2, float eps,
+                 const int *step_counter, void *stream);
+/* best init of every clip: total [C, I] -> best_index [C], best_loss [C] (first minimum). */
+int hm_argmin_over_inits(const float *total, int C, int I, int32_t *best_index, float *best_loss,
+                         void *stream);
+
 #ifdef __cplusplus
 }
 #endif

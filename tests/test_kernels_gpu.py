@@ -1,0 +1,199 @@
+"""GPU parity of the individual kernels (MANO LBS, rigid placement, SDF pair, contact, Adam) against
+the CPU oracle (torch autograd over oracle/*.py) on seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from homan_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-12))
+
+
+@pytest.mark.parametrize("side", ["right", "left"])
+def test_mano_lbs_forward_backward(side, mano_assets):
+    from homan_b200._lib import call, current_stream, ptr
+    from homan_b200.engine import mano_blob
+    from oracle import homan_ref
+    asset = mano_assets[side]
+    rng = np.random.default_rng(3)
+    B = 5
+    pca = rng.normal(size=(B, 20)).astype(np.float32) * 0.6
+    rot = rng.normal(size=(B, 3)).astype(np.float32) * 0.4
+    betas = rng.normal(size=(B, 10)).astype(np.float32) * 0.5
+    mtr = rng.normal(size=(B, 3)).astype(np.float32) * 0.02
+    r6 = rng.normal(size=(B, 3, 2)).astype(np.float32)
+    tr = rng.normal(size=(B, 1, 3)).astype(np.float32) * 0.1
+    gv = rng.normal(size=(B, 778, 3)).astype(np.float32)
+    gc = rng.normal(size=(B, 3)).astype(np.float32)
+    # oracle
+    tp = {k: torch.from_numpy(v).requires_grad_() for k, v in
+          dict(pca=pca, rot=rot, betas=betas, mtr=mtr, r6=r6, tr=tr).items()}
+    mano = homan_ref.ManoPca(mano_assets["right"], mano_assets["left"])
+    v, _ = mano(tp["pca"], tp["rot"], tp["betas"], side)
+    v = v + tp["mtr"].unsqueeze(1)
+    full, det = homan_ref.transform_persp(v, tp["tr"], homan_ref.rot6d_to_matrix(tp["r6"]), torch.ones(1))
+    ((full * torch.from_numpy(gv)).sum() + (det.mean(1) * torch.from_numpy(gc)).sum()).backward()
+    # kernel
+    d = lambda x: torch.from_numpy(x).cuda()  # noqa: E731
+    blob = mano_blob(asset, 16)
+    dp, dr, db, dm, d6, dt = d(pca), d(rot), d(betas), d(mtr), d(r6), d(tr)
+    verts = torch.empty(B, 778, 3, device="cuda")
+    s = current_stream()
+    left = 1 if side == "left" else 0
+    call("hm_mano_fwd", ptr(blob), 16, left, ptr(dp), 20, ptr(dr), ptr(db), ptr(dm), ptr(d6), ptr(dt), None, B,
+         ptr(verts), None, s)
+    assert _rel(verts.cpu(), full.detach()) < 2e-6
+    g = {k: torch.zeros_like(x) for k, x in dict(pca=dp, rot=dr, betas=db, mtr=dm, r6=d6, tr=dt).items()}
+    dgv, dgc = d(gv), d(gc)
+    call("hm_mano_bwd", ptr(blob), 16, left, ptr(dp), 20, ptr(dr), ptr(db), ptr(dm), ptr(d6), ptr(dt), None, B,
+         ptr(dgv), ptr(dgc), ptr(g["pca"]), ptr(g["rot"]), ptr(g["betas"]), ptr(g["mtr"]), ptr(g["r6"]),
+         ptr(g["tr"]), s)
+    torch.cuda.synchronize()
+    for k in g:
+        assert _rel(g[k].cpu(), tp[k].grad) < 1e-4, (k, _rel(g[k].cpu(), tp[k].grad))
+
+
+def test_mano_layer_joints_match_numpy_fp64(mano_assets):
+    from homan_b200._lib import call, current_stream, ptr
+    from homan_b200.engine import mano_blob
+    rng = np.random.default_rng(4)
+    B = 3
+    pca = rng.normal(size=(B, 16)).astype(np.float32) * 0.5
+    rot = rng.normal(size=(B, 3)).astype(np.float32) * 0.3
+    betas = rng.normal(size=(B, 10)).astype(np.float32) * 0.3
+    v_ref, j_ref = synth.mano_forward_np(mano_assets["right"], pca, rot, betas)
+    d = lambda x: torch.from_numpy(x).cuda()  # noqa: E731
+    verts, joints = torch.empty(B, 778, 3, device="cuda"), torch.empty(B, 16, 3, device="cuda")
+    blob, dp, dr, db = mano_blob(mano_assets["right"], 16), d(pca), d(rot), d(betas)
+    call("hm_mano_fwd", ptr(blob), 16, 0, ptr(dp), 16, ptr(dr), ptr(db),
+         None, None, None, None, B, ptr(verts), ptr(joints), current_stream())
+    torch.cuda.synchronize()
+    assert _rel(verts.cpu(), v_ref) < 2e-6 and _rel(joints.cpu(), j_ref) < 2e-6
+
+
+def test_rigid_object(mano_assets):
+    from homan_b200._lib import call, current_stream, ptr
+    from oracle import homan_ref
+    rng = np.random.default_rng(5)
+    B = 4
+    mesh, _ = synth.make_ellipsoid(8, 5)
+    r6 = torch.from_numpy(rng.normal(size=(B, 3, 2)).astype(np.float32)).requires_grad_()
+    tr = torch.from_numpy(rng.normal(size=(B, 1, 3)).astype(np.float32)).requires_grad_()
+    gv = torch.from_numpy(rng.normal(size=(B, mesh.shape[0], 3)).astype(np.float32))
+    m = torch.from_numpy(mesh)[None].repeat(B, 1, 1)
+    out, _ = homan_ref.transform_persp(m, tr, homan_ref.rot6d_to_matrix(r6), torch.ones(1))
+    (out * gv).sum().backward()
+    dm, d6, dt = torch.from_numpy(mesh).cuda()[None].contiguous(), r6.detach().cuda(), tr.detach().cuda()
+    verts = torch.empty(B, mesh.shape[0], 3, device="cuda")
+    g6, gt = torch.zeros(B, 3, 2, device="cuda"), torch.zeros(B, 1, 3, device="cuda")
+    s = current_stream()
+    call("hm_rigid_fwd", ptr(dm), 1, ptr(d6), ptr(dt), None, B, mesh.shape[0], ptr(verts), s)
+    dgv = gv.cuda()
+    call("hm_rigid_bwd", ptr(dm), 1, ptr(d6), None, B, mesh.shape[0], ptr(dgv), ptr(g6), ptr(gt), s)
+    torch.cuda.synchronize()
+    assert _rel(verts.cpu(), out.detach()) < 1e-6
+    assert _rel(g6.cpu(), r6.grad) < 1e-4 and _rel(gt.cpu(), tr.grad) < 1e-5
+
+
+def _grasp(T, seed, mano_assets, obj="ellipsoid80"):
+    clip = synth.make_clip(T, obj, seed=seed, mano_asset=mano_assets["right"])
+    return clip["gt"]["verts_hand"], clip["gt"]["verts_obj"], clip
+
+
+def test_sdf_pair_matches_oracle(mano_assets):
+    from homan_b200._lib import call, current_stream, ptr
+    from oracle import homan_ref
+    vh, vo, clip = _grasp(3, 21, mano_assets)
+    # push the object into the hand so that some samples are inside
+    vo = vo + (vh.mean(1, keepdims=True) - vo.mean(1, keepdims=True)) * 0.8
+    closed, fo = mano_assets["right"]["closed_faces"], clip["obj_faces"]
+    th = torch.from_numpy(vh).requires_grad_()
+    to = torch.from_numpy(vo)
+    loss, dv = homan_ref.sdf_scene([th, to], [torch.from_numpy(closed), torch.from_numpy(fo)])
+    loss.backward()
+    assert float(loss) > 0
+    B = vh.shape[0]
+    dh, do = torch.from_numpy(vh).cuda(), torch.from_numpy(vo).cuda()
+    part = torch.zeros(B, 16, device="cuda")
+    gh = torch.zeros_like(dh)
+    phi = torch.empty(B, 32 ** 3, device="cuda")
+    s = current_stream()
+    d_closed, d_fo = torch.from_numpy(closed).cuda(), torch.from_numpy(fo.astype(np.int32)).cuda()
+    call("hm_sdf_pair", ptr(dh), ptr(d_closed), ptr(do), B, 778, closed.shape[0], vo.shape[1],
+         32, 0.2, 0.0, ptr(phi), ptr(part), None, s)
+    a = part[:, 10].sum().item()
+    call("hm_sdf_pair", ptr(do), ptr(d_fo), ptr(dh), B, vo.shape[1],
+         fo.shape[0], 778, 32, 0.2, 0.5, ptr(phi), ptr(part), ptr(gh), s)
+    torch.cuda.synchronize()
+    total = part[:, 10].sum().item()
+    ref_a = float(dv[(0, 1)].sum() / 1.0)  # rescaled values; compare the normalised sums through the loss instead
+    assert abs(total - float(loss)) <= 1e-4 * float(loss), (total, float(loss), a, ref_a)
+    assert _rel(gh.cpu(), 0.5 * th.grad) < 1e-4
+
+
+def test_sdf_dense_grid_matches_oracle(mano_assets):
+    from homan_b200._lib import call, current_stream, ptr
+    from oracle import sdfmod
+    v, f = synth.make_ellipsoid(8, 5, (0.5, 0.8, 0.6))
+    verts = torch.from_numpy(np.stack([v, v * 0.7 + 0.1]).astype(np.float32))
+    faces = torch.from_numpy(f.astype(np.int32))
+    ref = sdfmod.SDF()(faces, verts, 32)
+    phi = torch.empty(2, 32, 32, 32, device="cuda")
+    d_faces, d_verts = faces.cuda(), verts.cuda()
+    call("hm_sdf_grid", ptr(d_faces), ptr(d_verts), 2, v.shape[0], f.shape[0], 32, ptr(phi), current_stream())
+    torch.cuda.synchronize()
+    assert int(((phi.cpu() > 0) != (ref > 0)).sum()) == 0
+    assert _rel(phi.cpu(), ref) < 1e-5
+
+
+def test_contact_matches_oracle(mano_assets):
+    from homan_b200._lib import call, current_stream, ptr
+    from oracle import homan_ref
+    vh, vo, clip = _grasp(4, 22, mano_assets)
+    th, to = torch.from_numpy(vh).requires_grad_(), torch.from_numpy(vo).requires_grad_()
+    model = homan_ref.ClipModel.__new__(homan_ref.ClipModel)
+    loss = homan_ref.ClipModel.contact(model, th, to)
+    loss.backward()
+    B = vh.shape[0]
+    part = torch.zeros(B, 16, device="cuda")
+    gh, go = torch.zeros(B, 778, 3, device="cuda"), torch.zeros(B, vo.shape[1], 3, device="cuda")
+    dh, do = torch.from_numpy(vh).cuda(), torch.from_numpy(vo).cuda()
+    call("hm_contact_fwd_bwd", ptr(dh), ptr(do), B, B, vo.shape[1],
+         0.02, 2.0, ptr(part), ptr(gh), ptr(go), current_stream())
+    torch.cuda.synchronize()
+    assert abs(part[:, 11].sum().item() - float(loss)) <= 1e-5 * float(loss)
+    assert _rel(gh.cpu(), 2 * th.grad) < 1e-4 and _rel(go.cpu(), 2 * to.grad) < 1e-4
+    d = torch.cdist(torch.from_numpy(vh), torch.from_numpy(vo)).flatten(1).min(1)[0]
+    # metric only: the reference's |h|^2 + |o|^2 - 2 h.o form cancels catastrophically at mm distances
+    assert _rel(part[:, 12].cpu(), d) < 5e-2
+
+
+def test_adam_matches_torch():
+    from homan_b200._lib import call, current_stream, ptr
+    rng = np.random.default_rng(6)
+    n = 1000
+    p0 = rng.normal(size=n).astype(np.float32)
+    lr = np.where(np.arange(n) < 400, 1e-2, np.where(np.arange(n) < 800, 1e-1, 0.0)).astype(np.float32)
+    ref_a = torch.from_numpy(p0[:400].copy()).requires_grad_()
+    ref_b = torch.from_numpy(p0[400:800].copy()).requires_grad_()
+    opt = torch.optim.Adam([{"params": [ref_a], "lr": 1e-2}, {"params": [ref_b], "lr": 1e-1}])
+    p, m, v = torch.from_numpy(p0).cuda(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    dlr = torch.from_numpy(lr).cuda()
+    for it in range(5):
+        g = (rng.normal(size=n) * (10.0 ** rng.integers(-4, 2))).astype(np.float32)
+        ref_a.grad, ref_b.grad = torch.from_numpy(g[:400].copy()), torch.from_numpy(g[400:800].copy())
+        opt.step()
+        step += 1
+        dg = torch.from_numpy(g).cuda()
+        call("hm_adam_step", ptr(p), ptr(dg), ptr(m), ptr(v), ptr(dlr), n, 0.9, 0.999, 1e-8,
+             ptr(step), current_stream())
+    torch.cuda.synchronize()
+    out = p.cpu().numpy()
+    assert np.allclose(out[:400], ref_a.detach().numpy(), rtol=1e-5, atol=1e-7)
+    assert np.allclose(out[400:800], ref_b.detach().numpy(), rtol=1e-5, atol=1e-7)
+    assert np.array_equal(out[800:], p0[800:])
