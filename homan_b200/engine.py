@@ -74,28 +74,23 @@ class FitEngine:
         self.ncomps = ncomps
         asset = mano_asset if mano_asset is not None else batch["mano_asset"]
         self.mano = mano_blob(asset, ncomps, dev)
-        f32 = lambda x: torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float32).to(dev)  # noqa: E731
-        i32 = lambda x: torch.as_tensor(np.ascontiguousarray(x).astype(np.int32)).to(dev)  # noqa: E731
 
-        # ---- constants
-        self.mesh_obj = f32(batch["obj_verts_can"]).view(1, -1, 3)
-        self.Vo = self.mesh_obj.shape[1]
-        self.faces_obj = i32(batch["obj_faces"]).view(1, -1, 3)
-        self.faces_hand = i32(batch["hand_faces"]).view(1, -1, 3)
-        self.faces_hand_closed = i32(asset["closed_faces"]).view(-1, 3)
-        self.camintr = f32(batch["camintr"]).view(B, 3, 3)
-        self.K_roi_obj = f32(batch["K_roi_obj"]).view(B, 3, 3)
-        self.K_roi_hand = f32(batch["K_roi_hand"]).view(B, 3, 3)
-        self.ref_verts2d = f32(batch["verts2d"]).view(B, 778, 2)
+        # ---- constants (shapes from the batch; values come in through upload())
+        self.Vo = Vo = int(np.asarray(batch["obj_verts_can"]).shape[0])
+        Fo = int(np.asarray(batch["obj_faces"]).shape[0])
         R = REND_SIZE
-        tm_o = torch.as_tensor(np.asarray(batch["target_masks_object"])).to(dev).view(self.P, self.T, R, R)
-        tm_h = torch.as_tensor(np.asarray(batch["target_masks_hand"])).to(dev).view(self.P, self.T, R, R)
-        self.target_obj = tm_o.to(torch.int8).view(B, R, R).contiguous()
-        self.target_hand = tm_h.to(torch.int8).view(B, R, R).contiguous()
-        keep_o = (tm_o >= 0).float().sum((1, 2, 3))                      # per problem (losses.py:189-190)
-        self.norm_obj = (1.0 / (keep_o * self.T)).repeat_interleave(self.T).contiguous()
-        keep_h = (tm_h >= 0).float().sum((2, 3)).view(B)                 # per image (intended sil_hand)
-        self.norm_hand = (1.0 / (keep_h * self.T)).contiguous()
+        self.mesh_obj = torch.empty(1, Vo, 3, device=dev)
+        self.faces_obj = torch.empty(1, Fo, 3, dtype=torch.int32, device=dev)
+        self.faces_hand = torch.as_tensor(np.ascontiguousarray(batch["hand_faces"]).astype(np.int32)).to(dev).view(1, -1, 3)
+        self.faces_hand_closed = torch.as_tensor(np.ascontiguousarray(asset["closed_faces"]).astype(np.int32)).to(dev).view(-1, 3)
+        self.camintr = torch.empty(B, 3, 3, device=dev)
+        self.K_roi_obj = torch.empty(B, 3, 3, device=dev)
+        self.K_roi_hand = torch.empty(B, 3, 3, device=dev)
+        self.ref_verts2d = torch.empty(B, 778, 2, device=dev)
+        self.target_obj = torch.empty(B, R, R, dtype=torch.int8, device=dev)
+        self.target_hand = torch.empty(B, R, R, dtype=torch.int8, device=dev)
+        self.norm_obj = torch.empty(B, device=dev)
+        self.norm_hand = torch.empty(B, device=dev)
         self.scale_obj = torch.ones(1, device=dev)
         self.scale_hand = torch.ones(1, device=dev)
 
@@ -115,16 +110,11 @@ class FitEngine:
         self.exp_avg_sq = torch.zeros(n, device=dev)
         self.lr_elem = torch.zeros(n, device=dev)
         self.params, self.grads, off = {}, {}, 0
-        init = {"translations_object": batch["obj_t"], "rotations_object": np.asarray(batch["obj_R"])[..., :2],
-                "translations_hand": batch["hand_t"], "rotations_hand": np.asarray(batch["hand_R"])[..., :2],
-                "mano_pca_pose": batch["pca"], "mano_betas": np.zeros((B, 10), np.float32),  # re-zeroed: homan.py:108
-                "mano_rot": batch["mano_rot"], "mano_trans": batch["mano_trans"]}
         self._segments = {}
         for k in PARAM_ORDER:
             m = int(np.prod(shapes[k]))
             self._segments[k] = (off, m, shapes[k])
             self.params[k] = self.flat[off:off + m].view(shapes[k])
-            self.params[k].copy_(f32(init[k]).reshape(shapes[k]))
             self.lr_elem[off:off + m] = lrs[k]
             off += m
 
@@ -182,6 +172,55 @@ class FitEngine:
         self.graph = None
         self.use_graph = use_graph
         self.iteration = 0
+        self.upload(self.stage_host(batch, pin=False))
+
+    # ------------------------------------------------------------------ host -> device
+    @staticmethod
+    def stage_host(batch, pin=True):
+        """Host-side staging of one problem batch: contiguous (optionally pinned) torch tensors in the
+        layouts upload() copies from. Masks travel as int8 {-1, 0, 1}."""
+        def t(x, dtype):
+            x = torch.as_tensor(np.ascontiguousarray(x)).to(dtype).contiguous()
+            return x.pin_memory() if pin and torch.cuda.is_available() else x
+        P, T = np.asarray(batch["obj_t"]).shape[:2]
+        f = torch.float32
+        return {
+            "mesh_obj": t(batch["obj_verts_can"], f), "faces_obj": t(batch["obj_faces"], torch.int32),
+            "camintr": t(batch["camintr"], f), "K_roi_obj": t(batch["K_roi_obj"], f),
+            "K_roi_hand": t(batch["K_roi_hand"], f), "ref_verts2d": t(batch["verts2d"], f),
+            "target_obj": t(batch["target_masks_object"], torch.int8),
+            "target_hand": t(batch["target_masks_hand"], torch.int8),
+            "translations_object": t(batch["obj_t"], f), "rotations_object": t(np.asarray(batch["obj_R"])[..., :2], f),
+            "translations_hand": t(batch["hand_t"], f), "rotations_hand": t(np.asarray(batch["hand_R"])[..., :2], f),
+            "mano_pca_pose": t(batch["pca"], f), "mano_rot": t(batch["mano_rot"], f),
+            "mano_trans": t(batch["mano_trans"], f),
+        }
+
+    def upload(self, host):
+        """Copies a staged batch into the engine's device buffers (async on the current stream), resets the
+        optimiser state. Returns the number of bytes copied host -> device."""
+        nbytes = 0
+        dst = {"mesh_obj": self.mesh_obj, "faces_obj": self.faces_obj, "camintr": self.camintr,
+               "K_roi_obj": self.K_roi_obj, "K_roi_hand": self.K_roi_hand, "ref_verts2d": self.ref_verts2d,
+               "target_obj": self.target_obj, "target_hand": self.target_hand}
+        dst.update({k: self.params[k] for k in PARAM_ORDER if k != "mano_betas"})
+        for k, d in dst.items():
+            src = host[k]
+            if src.numel() != d.numel():
+                raise _lib.HomanB200Error(f"upload: {k} has {src.numel()} elements, engine expects {d.numel()}")
+            d.copy_(src.view(d.shape), non_blocking=True)
+            nbytes += src.numel() * src.element_size()
+        self.params["mano_betas"].zero_()   # re-zeroed by the reference: homan/homan.py:108
+        self.exp_avg.zero_()
+        self.exp_avg_sq.zero_()
+        self.step_counter.zero_()
+        R = REND_SIZE
+        keep_o = (self.target_obj >= 0).view(self.P, -1).sum(1).float()       # per problem (losses.py:189-190)
+        self.norm_obj.copy_((1.0 / (keep_o * self.T)).repeat_interleave(self.T))
+        keep_h = (self.target_hand >= 0).view(self.B, R * R).sum(1).float()   # per image (intended sil_hand)
+        self.norm_hand.copy_(1.0 / (keep_h * self.T))
+        self.iteration = 0
+        return nbytes
 
     # ------------------------------------------------------------------ one iteration, kernel by kernel
     def _silhouette(self, verts, K_roi, faces, rb, target, norm, weight, ga, g_ndc, g_verts, slot_loss, slot_iou, s):

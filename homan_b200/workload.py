@@ -1,0 +1,48 @@
+"""Synthetic benchmark / test workloads on the GPU (BASELINE.json configs).
+
+Targets (object / hand masks) are rendered with the product rasteriser itself (anti-aliasing off ->
+binary masks), so nothing here touches the CPU oracle.
+"""
+import numpy as np
+import torch
+
+from . import ops, synth
+
+CONFIGS = {
+    # name: P inits, T frames, object mesh, loss weights
+    "cfg1": dict(P=1, T=1, obj="cube", lw="sil_obj", seed=1000),
+    "cfg2": dict(P=16, T=10, obj="ellipsoid500", lw="step1+sil_hand", seed=2000),
+    "cfg3": dict(P=16, T=30, obj="ellipsoid500", lw="step2+sil_hand", seed=3000),
+    "cfg5": dict(P=32, T=30, obj="ellipsoid20k", lw="sil_obj", seed=5000),
+    "tiny": dict(P=2, T=4, obj="ellipsoid80", lw="step2+sil_hand", seed=7000),
+}
+
+
+def loss_weights(kind):
+    if kind == "sil_obj":
+        return synth.default_loss_weights(lw_sil_obj=1.0)
+    base = synth.step2_loss_weights() if kind.startswith("step2") else synth.step1_loss_weights()
+    if kind.endswith("+sil_hand"):
+        base["lw_sil_hand"] = 1.0
+    return base
+
+
+def gpu_render_fn(device="cuda"):
+    def render(verts, faces, K):
+        v = torch.from_numpy(np.ascontiguousarray(verts, dtype=np.float32)).to(device)
+        k = torch.from_numpy(np.ascontiguousarray(K, dtype=np.float32)).to(device)
+        f = torch.from_numpy(np.ascontiguousarray(faces).astype(np.int32)).to(device)[None]
+        ndc = ops.project(v, k, orig_size=1.0)
+        out = ops.rasterize_silhouettes(ndc, f, 256, anti_aliasing=False)
+        return out.cpu().numpy()
+    return render
+
+
+def make_workload(name, clip_index=0, device="cuda", mano_asset=None):
+    """-> (batch dict of numpy arrays [P,T,...], loss weights)."""
+    cfg = CONFIGS[name]
+    asset = mano_asset if mano_asset is not None else synth.make_mano_asset(0, "right")
+    seed = cfg["seed"] + clip_index
+    clip = synth.make_clip(cfg["T"], cfg["obj"], seed=seed, mano_asset=asset, render_fn=gpu_render_fn(device))
+    inits = synth.make_inits(clip, cfg["P"], seed=seed)
+    return synth.make_batch(clip, inits), loss_weights(cfg["lw"])

