@@ -139,7 +139,6 @@ def run_reference(args):
     steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
     sec = cpu_reference_iteration_rate(args.workload, steps, warmup, batch, lw, asset)
     P = cfg["P"]
-    value = 1.0 / (sec * P) * args.gpus  # iterations/s of the whole P-init batch; x N clips for the weak-scaled job
     value = 1.0 / (sec * P)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": args.gpus,
@@ -183,8 +182,9 @@ def kernel_breakdown(eng, iters=3):
     for name, evs in rec.items():
         per_iter = len(evs) // iters
         ms = [a.elapsed_time(b) for a, b in evs[per_iter:]]  # skip the first iteration
+        each = np.asarray(ms).reshape(iters - 1, per_iter).mean(0) * 1e3
         out[name] = {"launches_per_step": per_iter, "us_per_launch": 1e3 * float(np.mean(ms)),
-                     "us_per_step": 1e3 * float(np.sum(ms)) / (iters - 1)}
+                     "us_per_step": 1e3 * float(np.sum(ms)) / (iters - 1), "us_each": [round(float(x), 1) for x in each]}
     return out
 
 

@@ -162,8 +162,10 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
     boxes[i] = bx;
 }
 
-// Collect into `list` the faces [base, base+NTHREADS) whose bbox touches the tile. Returns the count.
-__device__ __forceinline__ int collect_faces(const FaceBox *__restrict__ boxes, int base, int F, int tx0, int ty0,
+constexpr int LISTCAP = 1024;  // faces of one tile processed per batch
+
+// Appends to list[*cnt...] the faces of [base, base + NTHREADS) whose bbox touches the tile.
+__device__ __forceinline__ void append_faces(const FaceBox *__restrict__ boxes, int base, int F, int tx0, int ty0,
                                              int *list, int *cnt) {
     const int f = base + threadIdx.x;
     bool hit = false;
@@ -171,16 +173,28 @@ __device__ __forceinline__ int collect_faces(const FaceBox *__restrict__ boxes, 
         const FaceBox bx = boxes[f];
         hit = bx.x0 <= bx.x1 && bx.x0 <= tx0 + TILE - 1 && bx.x1 >= tx0 && bx.y0 <= ty0 + TILE - 1 && bx.y1 >= ty0;
     }
-    if (threadIdx.x == 0) *cnt = 0;
-    __syncthreads();
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     const int lane = threadIdx.x & 31;
     int wbase = 0;
     if (lane == 0 && m) wbase = atomicAdd(cnt, __popc(m));
     wbase = __shfl_sync(0xffffffffu, wbase, 0);
     if (hit) list[wbase + __popc(m & ((1u << lane) - 1))] = f;
+}
+
+// Fills the list with the next batch of faces touching the tile (scanning from *base). Block-uniform.
+__device__ __forceinline__ int next_batch(const FaceBox *__restrict__ boxes, int &base, int F, int tx0, int ty0,
+                                          int *list, int *cnt, int *next) {
     __syncthreads();
-    return *cnt;
+    if (threadIdx.x == 0) { *cnt = 0; *next = 0; }
+    __syncthreads();
+    int n = 0;
+    while (base < F && n <= LISTCAP - NTHREADS) {
+        append_faces(boxes, base, F, tx0, ty0, list, cnt);
+        base += NTHREADS;
+        __syncthreads();
+        n = *cnt;
+    }
+    return n;
 }
 
 // ------------------------------------------------------------------------------------------ forward
@@ -189,21 +203,26 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                   float near_, float far_, int32_t *__restrict__ face_index, float *__restrict__ alpha,
                   uint32_t *__restrict__ cov_row, uint32_t *__restrict__ cov_col) {
     __shared__ unsigned long long keys[TILE * TILE];
-    __shared__ int list[NTHREADS];
-    __shared__ int cnt;
+    __shared__ int list[LISTCAP];
+    __shared__ int cnt, next;
     __shared__ uint32_t roww[TILE][2];
     const int b = blockIdx.y;
     const int tiles_x = is / TILE;
     const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
     const unsigned long long empty = ((unsigned long long)__float_as_uint(far_) << 32) | 0xffffffffull;
     for (int i = threadIdx.x; i < TILE * TILE; i += NTHREADS) keys[i] = empty;
     recs += (long)b * F;
     boxes += (long)b * F;
 
-    for (int base = 0; base < F; base += NTHREADS) {
-        const int n = collect_faces(boxes, base, F, tx0, ty0, list, &cnt);
-        for (int li = warp; li < n; li += NWARPS) {
+    int base = 0;
+    while (base < F) {
+        const int n = next_batch(boxes, base, F, tx0, ty0, list, &cnt, &next);
+        for (;;) {  // warps pull faces off the list
+            int li = 0;
+            if (lane == 0) li = atomicAdd(&next, 1);
+            li = __shfl_sync(0xffffffffu, li, 0);
+            if (li >= n) break;
             const FaceRec *rp = recs + list[li];
             const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rp));
             const float4 q1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
@@ -228,6 +247,10 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
 #pragma unroll
             for (int k = 0; k < 9; ++k) inv[k] /= den;
             const float e0x = f3 - f0, e0y = f4 - f1, e1x = f6 - f3, e1y = f7 - f4, e2x = f0 - f6, e2y = f1 - f7;
+            // early z: the interpolated depth is a convex combination of the corner depths, so a face whose
+            // nearest corner (minus rounding slack) is behind the current winner of a pixel cannot win it
+            const float zmin = fminf(fminf(f2, f5), f8);
+            const unsigned zmin_bits = zmin > 0.f ? __float_as_uint(zmin * (1.f - 1e-5f)) : 0u;
             const int n_px = w * h;
             const float inv_w = 1.f / (float)w;
             for (int i = lane; i < n_px; i += 32) {
@@ -238,6 +261,9 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 if ((yp - f1) * e0x < (xp - f0) * e0y) continue;
                 if ((yp - f4) * e1x < (xp - f3) * e1y) continue;
                 if ((yp - f7) * e2x < (xp - f6) * e2y) continue;
+                unsigned long long *kp = &keys[(yi - ty0) * TILE + (xi - tx0)];
+                const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
+                if (zmin_bits > (unsigned)(cur >> 32)) continue;
                 float w0 = inv[0] * xi + inv[1] * yi + inv[2];
                 float w1 = inv[3] * xi + inv[4] * yi + inv[5];
                 float w2 = inv[6] * xi + inv[7] * yi + inv[8];
@@ -247,14 +273,14 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 const float ws = w0 + w1 + w2;
                 w0 /= ws; w1 /= ws; w2 /= ws;
                 const float zp = 1.f / (w0 / f2 + w1 / f5 + w2 / f8);
-                if (zp <= near_ || far_ <= zp) continue;  // also rejects NaN
+                if (zp <= near_ || far_ <= zp) continue;
                 if (!(zp == zp)) continue;
                 const unsigned long long key = ((unsigned long long)__float_as_uint(zp) << 32) | (unsigned)fn;
-                atomicMin(&keys[(yi - ty0) * TILE + (xi - tx0)], key);
+                if (key < cur) atomicMin(kp, key);
             }
         }
-        __syncthreads();
     }
+    __syncthreads();
 
     // ---- write-out: face_index rows (coalesced), coverage words
     for (int i = threadIdx.x; i < TILE * TILE; i += NTHREADS) {
@@ -349,7 +375,16 @@ grad_prep_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restric
     }
 }
 
-// ------------------------------------------------------------------------------------------ backward
+// ------------------------------------------------------------------------------------------ sweep runs
+// Run-length form of the four sweep masks: maximal stretches of consecutive set bits of one line that
+// carry the same |grad| (the silhouette loss gradient is piecewise constant: 2 * norm * (rend - ref) takes a
+// handful of values and is constant over whole missing / excess regions). A sweep then costs O(runs on the
+// line) instead of O(set pixels). Lines with more than HM_RASTER_RUN_CAP runs keep the bit-line path.
+//   runs       [B][4][is][HM_RASTER_RUN_CAP] uint2 {start | end << 16, |grad| bits}
+//   run_counts [B][4][is]  (0xffffffff = overflow);  list 0 mn_row, 1 mp_row, 2 mn_col, 3 mp_col
+constexpr int RCAP = HM_RASTER_RUN_CAP;
+constexpr unsigned RUN_OVERFLOW = 0xffffffffu;
+
 struct BwdCtx {
     const float *grad;  // grad_alpha of this image [R,R]
     int is, aa, R;
@@ -361,17 +396,64 @@ __device__ __forceinline__ float fetch_grad(const BwdCtx &c, int y, int x) {
     return __ldg(c.grad + (long)(c.is - 1 - y) * c.R + x);
 }
 
-// Visits the set bits of `line` (one raster row or column, W words) in [a, c] and accumulates the
-// two vertex contributions of backward_pixel_map for the crossing (d0, d1_cross).
-template <int AXIS>
-__device__ __forceinline__ void sweep(const uint32_t *line, int a, int c, int d0, float d1_cross, float ka,
-                                      float p0d0, float p1d0, const BwdCtx &ctx, float &acc0, float &acc1) {
+__global__ void __launch_bounds__(NTHREADS)
+build_runs_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restrict__ m_row,
+                  const uint32_t *__restrict__ m_col, int is, int aa, uint2 *__restrict__ runs,
+                  uint32_t *__restrict__ run_counts) {
+    const int b = blockIdx.y;
+    const int idx = blockIdx.x * NTHREADS + threadIdx.x;
+    if (idx >= 4 * is) return;
+    const int l4 = idx / is, line = idx % is, plane = l4 & 1, col = l4 >> 1;
+    const int W = is / 32;
+    const uint32_t *words = (col ? m_col : m_row) + (((long)b * 2 + plane) * is + line) * W;
+    BwdCtx ctx;
+    ctx.is = is; ctx.aa = aa; ctx.R = aa ? is / 2 : is; ctx.eps = 0.f;
+    ctx.grad = grad_alpha + (long)b * ctx.R * ctx.R;
+    uint2 *out = runs + (((long)b * 4 + l4) * is + line) * RCAP;
+    int n = 0, rs = -1, re = -1;
+    float rg = 0.f;
+    for (int w = 0; w < W; ++w) {
+        unsigned bits = words[w];
+        while (bits) {
+            const int bit = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int d1 = w * 32 + bit;
+            const float g = fabsf(col ? fetch_grad(ctx, d1, line) : fetch_grad(ctx, line, d1));
+            if (rs >= 0 && d1 == re + 1 && g == rg) {
+                re = d1;
+            } else {
+                if (rs >= 0) {
+                    if (n < RCAP) out[n] = make_uint2((unsigned)rs | ((unsigned)re << 16), __float_as_uint(rg));
+                    ++n;
+                }
+                rs = re = d1;
+                rg = g;
+            }
+        }
+    }
+    if (rs >= 0) {
+        if (n < RCAP) out[n] = make_uint2((unsigned)rs | ((unsigned)re << 16), __float_as_uint(rg));
+        ++n;
+    }
+    run_counts[((long)b * 4 + l4) * is + line] = n > RCAP ? RUN_OVERFLOW : (unsigned)n;
+}
+
+// ------------------------------------------------------------------------------------------ backward
+// Visits the set bits of `line` (one raster row or column, W <= 32 words, `nz` = mask of its non-zero words)
+// in [a, c] and accumulates the two vertex contributions of backward_pixel_map for the crossing (d0, d1_cross).
+__device__ __forceinline__ void sweep(const uint32_t *line, unsigned nz, int a, int c, int axis, int d0,
+                                      float d1_cross, float ka, float p0d0, float p1d0, const BwdCtx &ctx,
+                                      float &acc0, float &acc1) {
     if (a > c) return;
+    const int wa = a >> 5, wc = c >> 5;
+    unsigned wm = nz & (0xffffffffu << wa) & (0xffffffffu >> (31 - wc));
+    if (!wm) return;
     const float fd0 = (float)d0;
     const bool has0 = p1d0 != fd0, has1 = p0d0 != fd0;
     const float c0 = ka / (p1d0 - fd0), c1 = ka / (fd0 - p0d0);
-    const int wa = a >> 5, wc = c >> 5;
-    for (int w = wa; w <= wc; ++w) {
+    while (wm) {
+        const int w = __ffs(wm) - 1;
+        wm &= wm - 1;
         unsigned bits = line[w];
         if (w == wa) bits &= 0xffffffffu << (a & 31);
         if (w == wc) bits &= 0xffffffffu >> (31 - (c & 31));
@@ -379,7 +461,7 @@ __device__ __forceinline__ void sweep(const uint32_t *line, int a, int c, int d0
             const int bit = __ffs(bits) - 1;
             bits &= bits - 1;
             const int d1 = w * 32 + bit;
-            const float g = AXIS == 0 ? fetch_grad(ctx, d1, d0) : fetch_grad(ctx, d0, d1);
+            const float g = axis == 0 ? fetch_grad(ctx, d1, d0) : fetch_grad(ctx, d0, d1);
             const float diff = fabsf(g);
             const float dd = (float)d1 - d1_cross;
             if (has0) {
@@ -396,170 +478,224 @@ __device__ __forceinline__ void sweep(const uint32_t *line, int a, int c, int d0
     }
 }
 
-struct BwdSmem {
-    const int *fi;                                // [TILE*TILE] face_index tile
-    const uint32_t *a_row, *mn_row, *mp_row;      // [TILE][W] lines through the tile rows
-    const uint32_t *a_col, *mn_col, *mp_col;      // [TILE][W] lines through the tile columns
-};
+// psi(z2) - psi(z1) = sum_{k=0}^{n-1} 1 / (z1 + k) for z2 = z1 + n, z1 >= 8 (asymptotic series, error < 3e-10)
+__device__ __forceinline__ float harmonic_span(float z1, float n) {
+    const float z2 = z1 + n;
+    const float i1 = 1.f / z1, i2 = 1.f / z2;
+    const float a1 = i1 * i1, a2 = i2 * i2;
+    float r = log1pf(n * i1);
+    r += 0.5f * (i1 - i2);
+    r += (1.f / 12.f) * (a1 - a2);
+    r -= (1.f / 120.f) * (a1 * a1 - a2 * a2);
+    r += (1.f / 252.f) * (a1 * a1 * a1 - a2 * a2 * a2);
+    return r;
+}
 
-// One (edge, axis) of one face, crossings whose in-pixel lies in this tile.
-template <int AXIS>
-__device__ __forceinline__ void edge_axis(const float (&pp)[3][2], int e, int fn, int tx0, int ty0, int W,
-                                          const BwdSmem &s, const BwdCtx &ctx, float &acc0, float &acc1) {
-    const int lane = threadIdx.x & 31;
-    const int i0 = e, i1 = (e + 1) % 3, i2 = (e + 2) % 3;
-    const float p0d0 = pp[i0][AXIS], p0d1 = pp[i0][1 - AXIS];
-    const float p1d0 = pp[i1][AXIS], p1d1 = pp[i1][1 - AXIS];
-    const float p2d0 = pp[i2][AXIS], p2d1 = pp[i2][1 - AXIS];
-    const int is = ctx.is;
-    int dir;
-    if (AXIS == 0) dir = (p0d0 < p1d0) ? -1 : 1;
-    else dir = (p0d0 < p1d0) ? 1 : -1;
-    const int d0_from = __float2int_rz(fmaxf(ceilf(fminf(p0d0, p1d0)), 0.f));
-    const int d0_to = __float2int_rz(fminf(fmaxf(p0d0, p1d0), (float)(is - 1)));
-    const int t0 = AXIS == 0 ? tx0 : ty0;  // tile origin along d0
-    const int t1 = AXIS == 0 ? ty0 : tx0;  // tile origin along d1
-    const int lo = max(d0_from, t0), hi = min(d0_to, t0 + TILE - 1);
-    const float ka = p1d0 - p0d0;
-    const float slope = (p1d1 - p0d1) / ka;
-    for (int d0 = lo + lane; d0 <= hi; d0 += 32) {
-        const float d1_cross = slope * ((float)d0 - p0d0) + p0d1;
-        const int d1_in = __float2int_rz(dir > 0 ? floorf(d1_cross) : ceilf(d1_cross));
-        const int d1_out = d1_in + dir;
-        if (d1_in < 0 || is <= d1_in) continue;
-        if (d1_out < 0 || is <= d1_out) continue;
-        if (d1_in < t1 || d1_in >= t1 + TILE) continue;  // another tile owns this crossing
-        const int l0 = d0 - t0;                          // line index inside the tile
-        const uint32_t *A = (AXIS == 0 ? s.a_col : s.a_row) + l0 * W;
-        const uint32_t *Mn = (AXIS == 0 ? s.mn_col : s.mn_row) + l0 * W;
-        const uint32_t *Mp = (AXIS == 0 ? s.mp_col : s.mp_row) + l0 * W;
-        const int fi_in = AXIS == 0 ? s.fi[(d1_in - t1) * TILE + l0] : s.fi[l0 * TILE + (d1_in - t1)];
-        // out-sweep: from the out pixel to the image border, only when this face owns the in pixel
-        if (fi_in == fn) {
-            const int lim = dir > 0 ? is - 1 : 0;
-            sweep<AXIS>(Mn, min(d1_out, lim), max(d1_out, lim), d0, d1_cross, ka, p0d0, p1d0, ctx, acc0, acc1);
+// Same sum as sweep() over a run-length line. Pixels within NEAR_PX of the crossing (the large terms) are
+// evaluated one by one with the reference's own expression; the far part of a run, where every pixel has the
+// same weight G, is the harmonic sum G / K * sum 1 / (|d1 - x| + eps / |K|) in closed form.
+constexpr float NEAR_PX = 8.f;
+__device__ __forceinline__ void sweep_runs(const uint2 *runs, unsigned count, const uint32_t *line, unsigned nz, int a,
+                                           int c, int axis, int d0, float x, float ka, float p0d0, float p1d0,
+                                           const BwdCtx &ctx, float &acc0, float &acc1) {
+    if (count == RUN_OVERFLOW) {
+        sweep(line, nz, a, c, axis, d0, x, ka, p0d0, p1d0, ctx, acc0, acc1);
+        return;
+    }
+    if (a > c || count == 0u) return;
+    const float fd0 = (float)d0;
+    const bool has0 = p1d0 != fd0, has1 = p0d0 != fd0;
+    const float c0 = ka / (p1d0 - fd0), c1 = ka / (fd0 - p0d0);
+    const float K0 = c0 * 2.f / (float)ctx.is, K1 = c1 * 2.f / (float)ctx.is;
+    const float del0 = ctx.eps / fabsf(K0), del1 = ctx.eps / fabsf(K1);
+    const int near_lo = __float2int_rz(fmaxf(ceilf(x - NEAR_PX), -1.f));
+    const int near_hi = __float2int_rz(fminf(floorf(x + NEAR_PX), 65535.f));
+    for (unsigned r = 0; r < count; ++r) {
+        const uint2 run = runs[r];
+        const int s = max(a, (int)(run.x & 0xffffu)), e = min(c, (int)(run.x >> 16));
+        if (s > e) continue;
+        const float G = __uint_as_float(run.y);
+        // near zone: per pixel, as the reference
+        const int ns = max(s, near_lo), ne = min(e, near_hi);
+        for (int d1 = ns; d1 <= ne; ++d1) {
+            const float dd = (float)d1 - x;
+            if (has0) {
+                float dist = c0 * dd * 2.f / (float)ctx.is;
+                dist = (0.f < dist) ? dist + ctx.eps : dist - ctx.eps;
+                acc0 -= G / dist;
+            }
+            if (has1) {
+                float dist = c1 * dd * 2.f / (float)ctx.is;
+                dist = (0.f < dist) ? dist + ctx.eps : dist - ctx.eps;
+                acc1 -= G / dist;
+            }
         }
-        // in-sweep: from the in pixel to the opposite edge of the triangle
-        {
-            const float fd0 = (float)d0;
-            float c2;
-            if ((fd0 - p0d0) * (fd0 - p2d0) < 0.f) c2 = (p2d1 - p0d1) / (p2d0 - p0d0) * (fd0 - p0d0) + p0d1;
-            else c2 = (p1d1 - p2d1) / (p1d0 - p2d0) * (fd0 - p2d0) + p2d1;
-            const int lim = __float2int_rz(dir > 0 ? ceilf(c2) : floorf(c2));
-            int a = min(d1_in, lim), c = max(d1_in, lim);
-            a = max(a, 0);
-            c = min(c, is - 1);
-            const bool alpha_out = (A[d1_out >> 5] >> (d1_out & 31)) & 1u;
-            sweep<AXIS>(alpha_out ? Mn : Mp, a, c, d0, d1_cross, ka, p0d0, p1d0, ctx, acc0, acc1);
+        // far zone beyond the crossing (d1 - x > NEAR_PX): dist = K (dd + eps / |K|)
+        const int ps = max(s, near_hi + 1);
+        if (ps <= e) {
+            const float n = (float)(e - ps + 1), z = (float)ps - x;
+            if (has0) acc0 -= G / K0 * harmonic_span(z + del0, n);
+            if (has1) acc1 -= G / K1 * harmonic_span(z + del1, n);
+        }
+        // far zone before the crossing (x - d1 > NEAR_PX): dist = -K (|dd| + eps / |K|)
+        const int me = min(e, near_lo - 1);
+        if (s <= me) {
+            const float n = (float)(me - s + 1), z = x - (float)me;
+            if (has0) acc0 += G / K0 * harmonic_span(z + del0, n);
+            if (has1) acc1 += G / K1 * harmonic_span(z + del1, n);
         }
     }
 }
 
+// One CTA per (image, 64x64 tile); one thread per (face, edge, axis) of the faces touching the tile,
+// looping over the scan-lines d0 of that edge whose in-pixel lies in the tile.
 __global__ void __launch_bounds__(NTHREADS)
 raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
                   float eps, const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
                   const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ cov_col,
                   const uint32_t *__restrict__ m_row, const uint32_t *__restrict__ m_col,
+                  const uint2 *__restrict__ runs, const uint32_t *__restrict__ run_counts,
                   float *__restrict__ grad_ndc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ int list[NTHREADS];
-    __shared__ int cnt;
-    __shared__ float wacc[NWARPS][6];
+    __shared__ int list[LISTCAP];
+    __shared__ int cnt, next;
+    __shared__ unsigned nzw[4][TILE];  // non-zero word masks: mn_row, mp_row, mn_col, mp_col
+    __shared__ __align__(16) uint2 srun[4][TILE][RCAP];  // run lists of the same four line blocks
+    __shared__ __align__(16) unsigned scount[4][TILE];
     __shared__ __align__(8) uint64_t bar;
     const int W = is / 32;
     int *fi = reinterpret_cast<int *>(smem_raw);
     uint32_t *lines = reinterpret_cast<uint32_t *>(smem_raw + TILE * TILE * sizeof(int));
-    const int LW = TILE * W;  // words per line block
+    const int LW = TILE * W;  // words per line block: a_row mn_row mp_row a_col mn_col mp_col
     const int b = blockIdx.y;
     const int tiles_x = is / TILE;
     const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    // ---- stage the tile's face_index rows and the six bit-line blocks with TMA bulk copies
-    if (threadIdx.x == 0) {
-        mbar_init(&bar, 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    if (warp == 0) {
-        if (lane == 0) mbar_expect_tx(&bar, (uint32_t)(TILE * TILE * 4 + 6 * LW * 4));
-        __syncwarp();
-        for (int r = lane; r < TILE; r += 32)
-            tma_bulk_g2s(fi + r * TILE, face_index + ((long)b * is + ty0 + r) * is + tx0, TILE * 4, &bar);
-        if (lane < 6) {
-            const long plane = (long)is * W;
-            const uint32_t *src;
-            switch (lane) {
-                case 0: src = cov_row + ((long)b * is + ty0) * W; break;
-                case 1: src = m_row + ((long)b * 2 * is + ty0) * W; break;
-                case 2: src = m_row + ((long)b * 2 * is + ty0) * W + plane; break;
-                case 3: src = cov_col + ((long)b * is + tx0) * W; break;
-                case 4: src = m_col + ((long)b * 2 * is + tx0) * W; break;
-                default: src = m_col + ((long)b * 2 * is + tx0) * W + plane; break;
-            }
-            tma_bulk_g2s(lines + lane * LW, src, (uint32_t)(LW * 4), &bar);
-        }
-    }
-    BwdSmem s;
-    s.fi = fi;
-    s.a_row = lines; s.mn_row = lines + LW; s.mp_row = lines + 2 * LW;
-    s.a_col = lines + 3 * LW; s.mn_col = lines + 4 * LW; s.mp_col = lines + 5 * LW;
-    BwdCtx ctx;
-    ctx.is = is; ctx.aa = aa; ctx.R = aa ? is / 2 : is; ctx.eps = eps;
-    ctx.grad = grad_alpha + (long)b * ctx.R * ctx.R;
     recs += (long)b * F;
     boxes += (long)b * F;
     grad_ndc += (long)b * V * 3;
-    bool staged = false;
+    BwdCtx ctx;
+    ctx.is = is; ctx.aa = aa; ctx.R = aa ? is / 2 : is; ctx.eps = eps;
+    ctx.grad = grad_alpha + (long)b * ctx.R * ctx.R;
 
-    for (int base = 0; base < F; base += NTHREADS) {
-        const int n = collect_faces(boxes, base, F, tx0, ty0, list, &cnt);
-        if (n > 0 && !staged) {
+    int base = 0;
+    bool staged = false;
+    while (base < F) {
+        const int n = next_batch(boxes, base, F, tx0, ty0, list, &cnt, &next);
+        if (n == 0) continue;
+        if (!staged) {
+            // ---- stage the tile's face_index rows and the six bit-line blocks with TMA bulk copies
+            //      (tiles no face touches never get here: their face_index is never read)
+            if (threadIdx.x == 0) {
+                mbar_init(&bar, 1);
+                mbar_fence_init();
+            }
+            __syncthreads();
+            if (warp == 0) {
+                if (lane == 0)
+                    mbar_expect_tx(&bar, (uint32_t)(TILE * TILE * 4 + 6 * LW * 4 + 4 * TILE * RCAP * 8 + 4 * TILE * 4));
+                __syncwarp();
+                for (int r = lane; r < TILE; r += 32)
+                    tma_bulk_g2s(fi + r * TILE, face_index + ((long)b * is + ty0 + r) * is + tx0, TILE * 4, &bar);
+                if (lane < 6) {
+                    const long plane = (long)is * W;
+                    const uint32_t *src;
+                    switch (lane) {
+                        case 0: src = cov_row + ((long)b * is + ty0) * W; break;
+                        case 1: src = m_row + ((long)b * 2 * is + ty0) * W; break;
+                        case 2: src = m_row + ((long)b * 2 * is + ty0) * W + plane; break;
+                        case 3: src = cov_col + ((long)b * is + tx0) * W; break;
+                        case 4: src = m_col + ((long)b * 2 * is + tx0) * W; break;
+                        default: src = m_col + ((long)b * 2 * is + tx0) * W + plane; break;
+                    }
+                    tma_bulk_g2s(lines + lane * LW, src, (uint32_t)(LW * 4), &bar);
+                } else if (lane >= 8 && lane < 12) {
+                    const int l4 = lane - 8, t0 = (l4 >> 1) ? tx0 : ty0;
+                    tma_bulk_g2s(&srun[l4][0][0], runs + (((long)b * 4 + l4) * is + t0) * RCAP, TILE * RCAP * 8, &bar);
+                    tma_bulk_g2s(&scount[l4][0], run_counts + ((long)b * 4 + l4) * is + t0, TILE * 4, &bar);
+                }
+            }
             mbar_wait(&bar, 0);
+            {   // masks of the non-zero words of every sweep line
+                const int which = threadIdx.x >> 6, l = threadIdx.x & 63;
+                const uint32_t *blk = lines + (which == 0 ? 1 : which == 1 ? 2 : which == 2 ? 4 : 5) * LW + l * W;
+                unsigned m = 0;
+                for (int w = 0; w < W; ++w) m |= (blk[w] != 0u ? 1u : 0u) << w;
+                nzw[which][l] = m;
+            }
+            __syncthreads();
             staged = true;
         }
-        for (int li = warp; li < n; li += NWARPS) {
-            const FaceRec *rp = recs + list[li];
+        for (int task = threadIdx.x; task < 6 * n; task += NTHREADS) {
+            const int e = (task % 6) >> 1, axis = task & 1;
+            const FaceRec *rp = recs + list[task / 6];
             const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rp));
             const float4 q1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
             const float4 q2 = __ldg(reinterpret_cast<const float4 *>(rp) + 2);
             const int4 q3 = __ldg(reinterpret_cast<const int4 *>(rp) + 3);
             const int fn = __float_as_int(q2.y);
-            const int vid[3] = {__float_as_int(q2.z), __float_as_int(q2.w), q3.x};
-            float pp[3][2];
-            pp[0][0] = to_pix(q0.x, is); pp[0][1] = to_pix(q0.y, is);
-            pp[1][0] = to_pix(q0.w, is); pp[1][1] = to_pix(q1.x, is);
-            pp[2][0] = to_pix(q1.z, is); pp[2][1] = to_pix(q1.w, is);
-            if (lane < 6) wacc[warp][lane] = 0.f;
-            __syncwarp();
-#pragma unroll
-            for (int e = 0; e < 3; ++e) {
-                // axis 0: d0 = x, sweeps along y, gradient on the y slot; axis 1: the transpose
-                float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-                edge_axis<0>(pp, e, fn, tx0, ty0, W, s, ctx, a0, a1);
-                edge_axis<1>(pp, e, fn, tx0, ty0, W, s, ctx, b0, b1);
-                const bool any = (a0 != 0.f) | (a1 != 0.f) | (b0 != 0.f) | (b1 != 0.f);
-                if (__ballot_sync(0xffffffffu, any)) {
-                    a0 = warp_sum(a0); a1 = warp_sum(a1); b0 = warp_sum(b0); b1 = warp_sum(b1);
-                    if (lane == 0) {
-                        const int i0 = e, i1 = (e + 1) % 3;
-                        wacc[warp][i0 * 2 + 1] += a0;  // slot pi0*3 + (1 - axis), axis 0 -> y
-                        wacc[warp][i1 * 2 + 1] += a1;
-                        wacc[warp][i0 * 2 + 0] += b0;  // axis 1 -> x
-                        wacc[warp][i1 * 2 + 0] += b1;
-                    }
+            const int v0 = __float_as_int(q2.z), v1 = __float_as_int(q2.w), v2 = q3.x;
+            // pixel-space corners along (d0, d1) = (x, y) for axis 0, (y, x) for axis 1
+            const float ax = to_pix(q0.x, is), ay = to_pix(q0.y, is), bx = to_pix(q0.w, is), by = to_pix(q1.x, is),
+                        cx = to_pix(q1.z, is), cy = to_pix(q1.w, is);
+            const float a0 = axis ? ay : ax, a1 = axis ? ax : ay, b0 = axis ? by : bx, b1 = axis ? bx : by,
+                        c0 = axis ? cy : cx, c1 = axis ? cx : cy;
+            // vertex order of this edge: p0 = corner e, p1 = corner e+1, p2 = corner e+2
+            const float p0d0 = e == 0 ? a0 : e == 1 ? b0 : c0, p0d1 = e == 0 ? a1 : e == 1 ? b1 : c1;
+            const float p1d0 = e == 0 ? b0 : e == 1 ? c0 : a0, p1d1 = e == 0 ? b1 : e == 1 ? c1 : a1;
+            const float p2d0 = e == 0 ? c0 : e == 1 ? a0 : b0, p2d1 = e == 0 ? c1 : e == 1 ? a1 : b1;
+            const int vid0 = e == 0 ? v0 : e == 1 ? v1 : v2, vid1 = e == 0 ? v1 : e == 1 ? v2 : v0;
+            int dir;
+            if (axis == 0) dir = (p0d0 < p1d0) ? -1 : 1;
+            else dir = (p0d0 < p1d0) ? 1 : -1;
+            const int d0_from = __float2int_rz(fmaxf(ceilf(fminf(p0d0, p1d0)), 0.f));
+            const int d0_to = __float2int_rz(fminf(fmaxf(p0d0, p1d0), (float)(is - 1)));
+            const int t0 = axis == 0 ? tx0 : ty0;  // tile origin along d0
+            const int t1 = axis == 0 ? ty0 : tx0;  // tile origin along d1
+            const int lo = max(d0_from, t0), hi = min(d0_to, t0 + TILE - 1);
+            if (lo > hi) continue;
+            const float ka = p1d0 - p0d0;
+            const float slope = (p1d1 - p0d1) / ka;
+            const float slope02 = (p2d1 - p0d1) / (p2d0 - p0d0), slope21 = (p1d1 - p2d1) / (p1d0 - p2d0);
+            const uint32_t *blkA = lines + (axis == 0 ? 3 : 0) * LW;
+            const uint32_t *blkN = blkA + LW, *blkP = blkA + 2 * LW;
+            const int lN = axis == 0 ? 2 : 0, lP = lN + 1;
+            const unsigned *nzN = nzw[lN], *nzP = nzw[lP];
+            const int fs0 = axis == 0 ? 1 : TILE, fs1 = axis == 0 ? TILE : 1;  // fi strides along d0 / d1
+            float acc0 = 0.f, acc1 = 0.f;
+            for (int d0 = lo; d0 <= hi; ++d0) {
+                const float fd0 = (float)d0;
+                const float d1_cross = slope * (fd0 - p0d0) + p0d1;
+                const int d1_in = __float2int_rz(dir > 0 ? floorf(d1_cross) : ceilf(d1_cross));
+                const int d1_out = d1_in + dir;
+                if (d1_in < 0 || is <= d1_in) continue;
+                if (d1_out < 0 || is <= d1_out) continue;
+                if (d1_in < t1 || d1_in >= t1 + TILE) continue;  // another tile owns this crossing
+                const int l0 = d0 - t0;
+                // out-sweep: from the out pixel to the image border, only when this face owns the in pixel
+                if (fi[l0 * fs0 + (d1_in - t1) * fs1] == fn) {
+                    const int lim = dir > 0 ? is - 1 : 0;
+                    sweep_runs(srun[lN][l0], scount[lN][l0], blkN + l0 * W, nzN[l0], min(d1_out, lim), max(d1_out, lim),
+                               axis, d0, d1_cross, ka, p0d0, p1d0, ctx, acc0, acc1);
                 }
-                __syncwarp();
+                // in-sweep: from the in pixel to the opposite edge of the triangle
+                {
+                    float c2;
+                    if ((fd0 - p0d0) * (fd0 - p2d0) < 0.f) c2 = slope02 * (fd0 - p0d0) + p0d1;
+                    else c2 = slope21 * (fd0 - p2d0) + p2d1;
+                    const int lim = __float2int_rz(dir > 0 ? ceilf(c2) : floorf(c2));
+                    const int a = max(min(d1_in, lim), 0), c = min(max(d1_in, lim), is - 1);
+                    const bool alpha_out = (blkA[l0 * W + (d1_out >> 5)] >> (d1_out & 31)) & 1u;
+                    const int ls = alpha_out ? lN : lP;
+                    sweep_runs(srun[ls][l0], scount[ls][l0], (alpha_out ? blkN : blkP) + l0 * W, nzw[ls][l0], a, c,
+                               axis, d0, d1_cross, ka, p0d0, p1d0, ctx, acc0, acc1);
+                }
             }
-            if (lane < 6) {
-                const float g = wacc[warp][lane];
-                if (g != 0.f) atomicAdd(grad_ndc + (long)vid[lane >> 1] * 3 + (lane & 1), g);
-            }
-            __syncwarp();
+            // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
+            if (acc0 != 0.f) atomicAdd(grad_ndc + (long)vid0 * 3 + (1 - axis), acc0);
+            if (acc1 != 0.f) atomicAdd(grad_ndc + (long)vid1 * 3 + (1 - axis), acc1);
         }
-        __syncthreads();
     }
-    if (!staged) mbar_wait(&bar, 0);  // never exit with bulk copies in flight
 }
 
 // ------------------------------------------------------------------------------------------ silhouette loss
@@ -672,8 +808,10 @@ int hm_raster_sil_fwd(const void *records, const void *bboxes, int B, int F, int
 }
 
 int hm_raster_grad_prep(const float *grad_alpha, const uint32_t *cov_row, const uint32_t *cov_col, int B,
-                        int image_size, int anti_aliasing, uint32_t *m_row, uint32_t *m_col, void *stream) {
-    HM_REQUIRE(grad_alpha && cov_row && cov_col && m_row && m_col, "hm_raster_grad_prep: null pointer");
+                        int image_size, int anti_aliasing, uint32_t *m_row, uint32_t *m_col, void *runs,
+                        uint32_t *run_counts, void *stream) {
+    HM_REQUIRE(grad_alpha && cov_row && cov_col && m_row && m_col && runs && run_counts,
+               "hm_raster_grad_prep: null pointer");
     HM_REQUIRE(B >= 0 && B <= 65535, "hm_raster_grad_prep: bad sizes");
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
@@ -682,32 +820,40 @@ int hm_raster_grad_prep(const float *grad_alpha, const uint32_t *cov_row, const 
     grad_prep_kernel<<<grid, NTHREADS, 0, hm_stream(stream)>>>(grad_alpha, cov_row, cov_col, is, anti_aliasing, m_row,
                                                                m_col);
     HM_CHECK_LAUNCH("hm_raster_grad_prep");
+    dim3 grid2((4 * is + NTHREADS - 1) / NTHREADS, B);
+    build_runs_kernel<<<grid2, NTHREADS, 0, hm_stream(stream)>>>(grad_alpha, m_row, m_col, is, anti_aliasing,
+                                                                 static_cast<uint2 *>(runs), run_counts);
+    HM_CHECK_LAUNCH("hm_raster_grad_prep(runs)");
     return HM_OK;
 }
 
 int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *face_index,
                       const float *grad_alpha, const uint32_t *cov_row, const uint32_t *cov_col,
-                      const uint32_t *m_row, const uint32_t *m_col, int B, int V, int F, int image_size,
-                      int anti_aliasing, float eps, float *grad_ndc, void *stream) {
-    HM_REQUIRE(records && bboxes && face_index && grad_alpha && cov_row && cov_col && m_row && m_col && grad_ndc,
+                      const uint32_t *m_row, const uint32_t *m_col, const void *runs, const uint32_t *run_counts,
+                      int B, int V, int F, int image_size, int anti_aliasing, float eps, float *grad_ndc,
+                      void *stream) {
+    HM_REQUIRE(records && bboxes && face_index && grad_alpha && cov_row && cov_col && m_row && m_col && runs &&
+                   run_counts && grad_ndc,
                "hm_raster_sil_bwd: null pointer");
     HM_REQUIRE(B >= 0 && F >= 0 && V > 0 && B <= 65535, "hm_raster_sil_bwd: bad sizes");
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
     if (B == 0 || F == 0) return HM_OK;
     const size_t smem = (size_t)TILE * TILE * 4 + (size_t)6 * TILE * (is / 32) * 4;
-    HM_UNSUPPORTED(smem > 200 * 1024, "hm_raster_sil_bwd: raster size %d needs %zu B of shared memory", is, smem);
-    if (smem > 48 * 1024) {
+    HM_UNSUPPORTED(is > 1024, "hm_raster_sil_bwd: raster size %d > 1024 is not supported", is);
+    static size_t configured = 0;  // static + dynamic shared memory exceeds the 48 KB default: opt in once per size
+    if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(raster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             hm_set_error("hm_raster_sil_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return HM_ERR_CUDA;
         }
+        configured = smem;
     }
     dim3 grid((is / TILE) * (is / TILE), B);
     raster_bwd_kernel<<<grid, NTHREADS, smem, hm_stream(stream)>>>(
         static_cast<const FaceRec *>(records), static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps,
-        face_index, grad_alpha, cov_row, cov_col, m_row, m_col, grad_ndc);
+        face_index, grad_alpha, cov_row, cov_col, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
     HM_CHECK_LAUNCH("hm_raster_sil_bwd");
     return HM_OK;
 }

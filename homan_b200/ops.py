@@ -74,6 +74,8 @@ class RasterBuffers:
         self.cov_col = torch.empty(B, S, S // 32, dtype=torch.int32, device=device)
         self.m_row = torch.empty(B, 2, S, S // 32, dtype=torch.int32, device=device)
         self.m_col = torch.empty(B, 2, S, S // 32, dtype=torch.int32, device=device)
+        self.runs = torch.empty(B, 4, S, 8, 2, dtype=torch.int32, device=device)   # HM_RASTER_RUN_CAP = 8
+        self.run_counts = torch.empty(B, 4, S, dtype=torch.int32, device=device)
 
 
 def raster_forward(buf, ndc, faces, fill_back=True, near=NEAR, far=FAR):
@@ -90,9 +92,10 @@ def raster_backward(buf, grad_alpha, grad_ndc, eps=RASTER_EPS):
     """grad_alpha [B,R,R] -> grad_ndc [B,V,3] += (approximate NMR gradient, x / y slots)."""
     s = current_stream()
     call("hm_raster_grad_prep", ptr(grad_alpha), ptr(buf.cov_row), ptr(buf.cov_col), buf.B, buf.image_size,
-         int(buf.aa), ptr(buf.m_row), ptr(buf.m_col), s)
+         int(buf.aa), ptr(buf.m_row), ptr(buf.m_col), ptr(buf.runs), ptr(buf.run_counts), s)
     call("hm_raster_sil_bwd", ptr(buf.records), ptr(buf.bboxes), ptr(buf.face_index), ptr(grad_alpha),
-         ptr(buf.cov_row), ptr(buf.cov_col), ptr(buf.m_row), ptr(buf.m_col), buf.B, buf.V, buf.F, buf.image_size,
+         ptr(buf.cov_row), ptr(buf.cov_col), ptr(buf.m_row), ptr(buf.m_col), ptr(buf.runs), ptr(buf.run_counts),
+         buf.B, buf.V, buf.F, buf.image_size,
          int(buf.aa), float(eps), ptr(grad_ndc), s)
     return grad_ndc
 

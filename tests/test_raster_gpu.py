@@ -39,9 +39,12 @@ def _oracle_render(ndc, faces, image_size, aa, grad_alpha=None):
     return alpha.detach(), fi, g
 
 
+@pytest.mark.parametrize("noise", [True, False])
 @pytest.mark.parametrize("mesh,obj,T,aa", [("obj", "cube", 2, True), ("obj", "ellipsoid500", 3, True),
                                            ("hand", "ellipsoid80", 3, True), ("obj", "ellipsoid80", 2, False)])
-def test_forward_bit_exact_and_backward(mesh, obj, T, aa):
+def test_forward_bit_exact_and_backward(mesh, obj, T, aa, noise):
+    """noise=True: per-pixel random gradient (every sweep line overflows the run lists -> bit-line path);
+    noise=False: the piecewise-constant gradient of the silhouette loss (run-length / closed-form path)."""
     from homan_b200 import ops
     verts, faces, K = _scene(T, obj, seed=11, mesh=mesh)
     ndc = _oracle_ndc(verts, K).contiguous()
@@ -54,7 +57,8 @@ def test_forward_bit_exact_and_backward(mesh, obj, T, aa):
     keep = torch.ones_like(target)
     keep[:, :, 40:70] = 0
     grad_alpha = (2 * keep * (keep * alpha_ref - target) / keep.sum()).float()
-    grad_alpha = grad_alpha * torch.from_numpy(rng.uniform(0.5, 1.5, size=grad_alpha.shape).astype(np.float32))
+    if noise:
+        grad_alpha = grad_alpha * torch.from_numpy(rng.uniform(0.5, 1.5, size=grad_alpha.shape).astype(np.float32))
     _, _, g_ref = _oracle_render(ndc, faces, R, aa, grad_alpha)
 
     ndc_d = ndc.cuda().requires_grad_()
