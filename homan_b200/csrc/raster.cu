@@ -210,6 +210,8 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     const int tiles_x = is / TILE;
     const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
     const int lane = threadIdx.x & 31;
+    const bool pow2 = (is & (is - 1)) == 0;
+    const float inv_is = 1.f / (float)is;
     const unsigned long long empty = ((unsigned long long)__float_as_uint(far_) << 32) | 0xffffffffull;
     for (int i = threadIdx.x; i < TILE * TILE; i += NTHREADS) keys[i] = empty;
     recs += (long)b * F;
@@ -218,11 +220,14 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     int base = 0;
     while (base < F) {
         const int n = next_batch(boxes, base, F, tx0, ty0, list, &cnt, &next);
-        for (;;) {  // warps pull faces off the list
-            int li = 0;
-            if (lane == 0) li = atomicAdd(&next, 1);
-            li = __shfl_sync(0xffffffffu, li, 0);
-            if (li >= n) break;
+        // two passes: faces kept in their original winding (the outer layer of an outward-wound closed mesh)
+        // first, the reversed copies second, so that early z culls the hidden layer before its depth maths
+        for (;;) {  // warps pull (pass, face) pairs off the list
+            int li0 = 0;
+            if (lane == 0) li0 = atomicAdd(&next, 1);
+            li0 = __shfl_sync(0xffffffffu, li0, 0);
+            if (li0 >= 2 * n) break;
+            const int pass = li0 >= n ? 1 : 0, li = li0 - pass * n;
             const FaceRec *rp = recs + list[li];
             const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rp));
             const float4 q1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
@@ -231,6 +236,7 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             const float f0 = q0.x, f1 = q0.y, f2 = q0.z, f3 = q0.w, f4 = q1.x, f5 = q1.y, f6 = q1.z, f7 = q1.w,
                         f8 = q2.x;
             const int fn = __float_as_int(q2.y);
+            if ((fn >= F ? 1 : 0) != pass) continue;
             const int bx0 = (short)(q3.y & 0xffff), by0 = (short)(q3.y >> 16);
             const int bx1 = (short)(q3.z & 0xffff), by1 = (short)(q3.z >> 16);
             const int X0 = max(bx0, tx0), X1 = min(bx1, tx0 + TILE - 1);
@@ -256,8 +262,9 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             for (int i = lane; i < n_px; i += 32) {
                 const int row = __float2int_rz(((float)i + 0.5f) * inv_w);
                 const int xi = X0 + (i - row * w), yi = Y0 + row;
-                const float yp = (float)(2 * yi + 1 - is) / (float)is;
-                const float xp = (float)(2 * xi + 1 - is) / (float)is;
+                // (2i + 1 - is) / is: for a power-of-two raster the division is an exact scaling
+                const float yp = pow2 ? (float)(2 * yi + 1 - is) * inv_is : (float)(2 * yi + 1 - is) / (float)is;
+                const float xp = pow2 ? (float)(2 * xi + 1 - is) * inv_is : (float)(2 * xi + 1 - is) / (float)is;
                 if ((yp - f1) * e0x < (xp - f0) * e0y) continue;
                 if ((yp - f4) * e1x < (xp - f3) * e1y) continue;
                 if ((yp - f7) * e2x < (xp - f6) * e2y) continue;
@@ -329,11 +336,17 @@ grad_prep_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restric
                  const uint32_t *__restrict__ cov_col, int is, int aa, uint32_t *__restrict__ m_row,
                  uint32_t *__restrict__ m_col) {
     __shared__ float gs[TILE][TILE + 1];
+    __shared__ uint32_t a_row[TILE][2], a_col[TILE][2];
     const int b = blockIdx.y;
     const int tiles_x = is / TILE;
     const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int W = is / 32;
+    {   // coverage words of the tile: 64 rows x 2 words, 64 columns x 2 words (one load per thread)
+        const int l = (threadIdx.x >> 1) & 63, w = threadIdx.x & 1;
+        if (threadIdx.x < 128) a_row[l][w] = cov_row[((long)b * is + (ty0 + l)) * W + (tx0 >> 5) + w];
+        else a_col[l][w] = cov_col[((long)b * is + (tx0 + l)) * W + (ty0 >> 5) + w];
+    }
     if (aa) {
         const int R = is / 2, rtop = R - 1 - (ty0 >> 1);
         for (int i = threadIdx.x; i < (TILE / 2) * (TILE / 2); i += NTHREADS) {
@@ -356,7 +369,7 @@ grad_prep_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restric
             const unsigned neg = __ballot_sync(0xffffffffu, g < 0.f), pos = __ballot_sync(0xffffffffu, g > 0.f);
             if (lane == 0) {
                 const long o = ((long)b * 2 * is + (ty0 + yl)) * W + (tx0 >> 5) + w;
-                const unsigned A = cov_row[((long)b * is + (ty0 + yl)) * W + (tx0 >> 5) + w];
+                const unsigned A = a_row[yl][w];
                 m_row[o] = neg & ~A;
                 m_row[o + plane] = pos & A;
             }
@@ -367,7 +380,7 @@ grad_prep_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restric
             const unsigned neg = __ballot_sync(0xffffffffu, g < 0.f), pos = __ballot_sync(0xffffffffu, g > 0.f);
             if (lane == 0) {
                 const long o = ((long)b * 2 * is + (tx0 + xl)) * W + (ty0 >> 5) + w;
-                const unsigned A = cov_col[((long)b * is + (tx0 + xl)) * W + (ty0 >> 5) + w];
+                const unsigned A = a_col[xl][w];
                 m_col[o] = neg & ~A;
                 m_col[o + plane] = pos & A;
             }
@@ -520,14 +533,14 @@ __device__ __forceinline__ void sweep_runs(const uint2 *runs, unsigned count, co
         for (int d1 = ns; d1 <= ne; ++d1) {
             const float dd = (float)d1 - x;
             if (has0) {
-                float dist = c0 * dd * 2.f / (float)ctx.is;
+                float dist = K0 * dd;
                 dist = (0.f < dist) ? dist + ctx.eps : dist - ctx.eps;
-                acc0 -= G / dist;
+                acc0 -= G * __frcp_rn(dist);
             }
             if (has1) {
-                float dist = c1 * dd * 2.f / (float)ctx.is;
+                float dist = K1 * dd;
                 dist = (0.f < dist) ? dist + ctx.eps : dist - ctx.eps;
-                acc1 -= G / dist;
+                acc1 -= G * __frcp_rn(dist);
             }
         }
         // far zone beyond the crossing (d1 - x > NEAR_PX): dist = K (dd + eps / |K|)
@@ -664,6 +677,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             const int fs0 = axis == 0 ? 1 : TILE, fs1 = axis == 0 ? TILE : 1;  // fi strides along d0 / d1
             float acc0 = 0.f, acc1 = 0.f;
             for (int d0 = lo; d0 <= hi; ++d0) {
+                if ((scount[lN][d0 - t0] | scount[lP][d0 - t0]) == 0u) continue;  // nothing to sweep on this line
                 const float fd0 = (float)d0;
                 const float d1_cross = slope * (fd0 - p0d0) + p0d1;
                 const int d1_in = __float2int_rz(dir > 0 ? floorf(d1_cross) : ceilf(d1_cross));

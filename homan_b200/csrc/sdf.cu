@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(NT)
 sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ faces, const float *__restrict__ verts_s,
                 int Vg, int Fg, int Vs, float half_factor, float weight, float *__restrict__ phi_all,
                 float *__restrict__ partials, float *__restrict__ g_vs) {
-    extern __shared__ __align__(16) float lv[];  // Vg * 3 normalised mesh vertices
+    extern __shared__ __align__(16) float lv[];  // Vg * 3 normalised mesh vertices, then Fg bounding spheres
+    float4 *sph = reinterpret_cast<float4 *>(lv + ((Vg * 3 + 3) / 4) * 4);
     __shared__ unsigned needed[G * G], inside[G * G];
     __shared__ float red[6 * 32];
     __shared__ float box[4];  // centre xyz, scale
@@ -162,6 +163,18 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
             }
     }
     __syncthreads();
+    // bounding sphere of every face (centroid, radius with rounding slack): culls both loops below
+    for (int f = tid; f < Fg; f += NT) {
+        const float *a = lv + 3 * __ldg(faces + 3 * f), *bq = lv + 3 * __ldg(faces + 3 * f + 1),
+                    *c = lv + 3 * __ldg(faces + 3 * f + 2);
+        const float mx_ = (a[0] + bq[0] + c[0]) / 3.f, my_ = (a[1] + bq[1] + c[1]) / 3.f, mz_ = (a[2] + bq[2] + c[2]) / 3.f;
+        float r2 = 0.f;
+        r2 = fmaxf(r2, (a[0] - mx_) * (a[0] - mx_) + (a[1] - my_) * (a[1] - my_) + (a[2] - mz_) * (a[2] - mz_));
+        r2 = fmaxf(r2, (bq[0] - mx_) * (bq[0] - mx_) + (bq[1] - my_) * (bq[1] - my_) + (bq[2] - mz_) * (bq[2] - mz_));
+        r2 = fmaxf(r2, (c[0] - mx_) * (c[0] - mx_) + (c[1] - my_) * (c[1] - my_) + (c[2] - mz_) * (c[2] - mz_));
+        sph[f] = make_float4(mx_, my_, mz_, sqrtf(r2) * 1.0001f + 1e-6f);
+    }
+    __syncthreads();
     // ---- 3. ray parity of every touched row (warp per row, lanes over faces)
     for (int row = warp; row < G * G; row += NT / 32) {
         const unsigned need = needed[row];
@@ -169,6 +182,8 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
         const float py = voxel_centre(row % G), pz = voxel_centre(row / G);
         unsigned parity = 0u;
         for (int f = lane; f < Fg; f += 32) {
+            const float4 sp = sph[f];
+            if (fabsf(py - sp.y) > sp.w || fabsf(pz - sp.z) > sp.w) continue;  // the ray misses the face's sphere
             const int i0 = __ldg(faces + 3 * f), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
             float xs;
             if (ray_x_cross(py, pz, lv + 3 * i0, lv + 3 * i1, lv + 3 * i2, xs)) parity ^= row_mask_below(xs);
@@ -184,8 +199,19 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
             const int i = __ffs(bits) - 1;
             bits &= bits - 1;
             const float p[3] = {voxel_centre(i), voxel_centre(row % G), voxel_centre(row / G)};
+            // upper bound of the distance from the spheres, then exact tests only where the lower bound allows
+            float ub = INFINITY;
+            for (int f = lane; f < Fg; f += 32) {
+                const float4 sp = sph[f];
+                const float dx = p[0] - sp.x, dy = p[1] - sp.y, dz = p[2] - sp.z;
+                ub = fminf(ub, sqrtf(dx * dx + dy * dy + dz * dz) + sp.w);
+            }
+            ub = warp_min(ub) * 1.0001f + 1e-6f;
             float best = INFINITY;
             for (int f = lane; f < Fg; f += 32) {
+                const float4 sp = sph[f];
+                const float dx = p[0] - sp.x, dy = p[1] - sp.y, dz = p[2] - sp.z;
+                if (sqrtf(dx * dx + dy * dy + dz * dz) - sp.w > ub) continue;
                 const int i0 = __ldg(faces + 3 * f), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
                 best = fminf(best, point_tri_dist2(p, lv + 3 * i0, lv + 3 * i1, lv + 3 * i2));
             }
@@ -262,15 +288,17 @@ int hm_sdf_pair(const float *verts_g, const int32_t *faces_g, const float *verts
     HM_REQUIRE(verts_g && faces_g && verts_s && phi_scratch && partials, "hm_sdf_pair: null pointer");
     HM_REQUIRE(B >= 0 && Vg > 0 && Fg > 0 && Vs > 0, "hm_sdf_pair: bad sizes");
     HM_UNSUPPORTED(grid != G, "hm_sdf_pair: grid size %d (only %d, the reference's grid_size)", grid, G);
-    const size_t smem = (size_t)Vg * 3 * sizeof(float);
+    const size_t smem = (size_t)((Vg * 3 + 3) / 4) * 4 * sizeof(float) + (size_t)Fg * 4 * sizeof(float);
     HM_UNSUPPORTED(smem > 160 * 1024, "hm_sdf_pair: grid mesh with %d vertices does not fit shared memory", Vg);
     if (B == 0) return HM_OK;
-    if (smem > 32 * 1024) {
+    static size_t configured = 0;
+    if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(sdf_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) {
             hm_set_error("hm_sdf_pair: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             return HM_ERR_CUDA;
         }
+        configured = smem;
     }
     const float half_factor = (float)((1.0 + (double)scale_factor) * 0.5);
     sdf_pair_kernel<<<B, NT, smem, hm_stream(stream)>>>(verts_g, faces_g, verts_s, Vg, Fg, Vs, half_factor, weight,
