@@ -504,64 +504,81 @@ __device__ __forceinline__ float harmonic_span(float z1, float n) {
     return r;
 }
 
-// Same sum as sweep() over a run-length line. Pixels within NEAR_PX of the crossing (the large terms) are
-// evaluated one by one with the reference's own expression; the far part of a run, where every pixel has the
-// same weight G, is the harmonic sum G / K * sum 1 / (|d1 - x| + eps / |K|) in closed form.
+// One (crossing, run) work item: the part [s, e] of one run of one sweep line seen from the crossing at
+// x = d1_cross of scan-line d0. Pixels within NEAR_PX of the crossing (the large terms) are evaluated one by
+// one; beyond, every pixel of the run has the same weight G and the sum of 1 / dist is the harmonic sum
+// G / K * sum 1 / (|d1 - x| + eps / |K|), taken in closed form (dist = K (d1 - x) +- eps, K = c * 2 / is).
 constexpr float NEAR_PX = 8.f;
-__device__ __forceinline__ void sweep_runs(const uint2 *runs, unsigned count, const uint32_t *line, unsigned nz, int a,
-                                           int c, int axis, int d0, float x, float ka, float p0d0, float p1d0,
-                                           const BwdCtx &ctx, float &acc0, float &acc1) {
-    if (count == RUN_OVERFLOW) {
-        sweep(line, nz, a, c, axis, d0, x, ka, p0d0, p1d0, ctx, acc0, acc1);
-        return;
-    }
-    if (a > c || count == 0u) return;
-    const float fd0 = (float)d0;
-    const bool has0 = p1d0 != fd0, has1 = p0d0 != fd0;
-    const float c0 = ka / (p1d0 - fd0), c1 = ka / (fd0 - p0d0);
-    const float K0 = c0 * 2.f / (float)ctx.is, K1 = c1 * 2.f / (float)ctx.is;
-    const float del0 = ctx.eps / fabsf(K0), del1 = ctx.eps / fabsf(K1);
+__device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, int s, int e, bool has0, bool has1,
+                                          float inv_is2, float eps, float &a0, float &a1) {
+    const float K0 = c0 * inv_is2, K1 = c1 * inv_is2;
     const int near_lo = __float2int_rz(fmaxf(ceilf(x - NEAR_PX), -1.f));
     const int near_hi = __float2int_rz(fminf(floorf(x + NEAR_PX), 65535.f));
-    for (unsigned r = 0; r < count; ++r) {
-        const uint2 run = runs[r];
-        const int s = max(a, (int)(run.x & 0xffffu)), e = min(c, (int)(run.x >> 16));
-        if (s > e) continue;
-        const float G = __uint_as_float(run.y);
-        // near zone: per pixel, as the reference
-        const int ns = max(s, near_lo), ne = min(e, near_hi);
-        for (int d1 = ns; d1 <= ne; ++d1) {
-            const float dd = (float)d1 - x;
-            if (has0) {
-                float dist = K0 * dd;
-                dist = (0.f < dist) ? dist + ctx.eps : dist - ctx.eps;
-                acc0 -= G * __frcp_rn(dist);
-            }
-            if (has1) {
-                float dist = K1 * dd;
-                dist = (0.f < dist) ? dist + ctx.eps : dist - ctx.eps;
-                acc1 -= G * __frcp_rn(dist);
-            }
-        }
-        // far zone beyond the crossing (d1 - x > NEAR_PX): dist = K (dd + eps / |K|)
-        const int ps = max(s, near_hi + 1);
-        if (ps <= e) {
-            const float n = (float)(e - ps + 1), z = (float)ps - x;
-            if (has0) acc0 -= G / K0 * harmonic_span(z + del0, n);
-            if (has1) acc1 -= G / K1 * harmonic_span(z + del1, n);
-        }
-        // far zone before the crossing (x - d1 > NEAR_PX): dist = -K (|dd| + eps / |K|)
-        const int me = min(e, near_lo - 1);
-        if (s <= me) {
-            const float n = (float)(me - s + 1), z = x - (float)me;
-            if (has0) acc0 += G / K0 * harmonic_span(z + del0, n);
-            if (has1) acc1 += G / K1 * harmonic_span(z + del1, n);
-        }
+    float h0 = 0.f, h1 = 0.f;
+    const int ns = max(s, near_lo), ne = min(e, near_hi);
+    for (int d1 = ns; d1 <= ne; ++d1) {
+        const float dd = (float)d1 - x;
+        float dist0 = K0 * dd, dist1 = K1 * dd;
+        dist0 = (0.f < dist0) ? dist0 + eps : dist0 - eps;
+        dist1 = (0.f < dist1) ? dist1 + eps : dist1 - eps;
+        h0 += __frcp_rn(dist0);
+        h1 += __frcp_rn(dist1);
+    }
+    const int ps = max(s, near_hi + 1);  // far zone beyond the crossing: dist = K (dd + eps / |K|)
+    if (ps <= e) {
+        const float n = (float)(e - ps + 1), z = (float)ps - x;
+        h0 += harmonic_span(z + eps / fabsf(K0), n) / K0;
+        h1 += harmonic_span(z + eps / fabsf(K1), n) / K1;
+    }
+    const int me = min(e, near_lo - 1);  // far zone before the crossing: dist = -K (|dd| + eps / |K|)
+    if (s <= me) {
+        const float n = (float)(me - s + 1), z = x - (float)me;
+        h0 -= harmonic_span(z + eps / fabsf(K0), n) / K0;
+        h1 -= harmonic_span(z + eps / fabsf(K1), n) / K1;
+    }
+    a0 = has0 ? -G * h0 : 0.f;
+    a1 = has1 ? -G * h1 : 0.f;
+}
+
+constexpr int WQCAP = 128;  // per-warp queue of (crossing, run) items
+struct WarpQueue {
+    float x[WQCAP], c0[WQCAP], c1[WQCAP], G[WQCAP];
+    unsigned se[WQCAP], meta[WQCAP];  // s | e << 16 ; owner lane | has0 << 5 | has1 << 6
+};
+
+// Per-task accumulators live in shared memory as 64-bit fixed point (2^-40 units): integer atomics are native
+// on shared memory (float adds are CAS loops) and make the per-task sums independent of the order of arrival.
+constexpr float FIX_SCALE = 1099511627776.f;  // 2^40
+__device__ __forceinline__ void acc_add(unsigned long long *slot, float v) {
+    if (v != 0.f) atomicAdd(slot, (unsigned long long)__float2ll_rn(v * FIX_SCALE));
+}
+__device__ __forceinline__ float acc_get(unsigned long long v) { return (float)((double)(long long)v * (1.0 / 1099511627776.0)); }
+
+__device__ __forceinline__ void drain_queue(WarpQueue &q, int n, unsigned long long (*wacc)[2], float inv_is2,
+                                            float eps) {
+    const int lane = threadIdx.x & 31;
+    for (int i = lane; i < n; i += 32) {
+        const unsigned se = q.se[i], meta = q.meta[i];
+        float a0, a1;
+        eval_item(q.x[i], q.c0[i], q.c1[i], q.G[i], (int)(se & 0xffffu), (int)(se >> 16), (meta >> 5) & 1u,
+                  (meta >> 6) & 1u, inv_is2, eps, a0, a1);
+        acc_add(&wacc[meta & 31u][0], a0);
+        acc_add(&wacc[meta & 31u][1], a1);
     }
 }
 
-// One CTA per (image, 64x64 tile); one thread per (face, edge, axis) of the faces touching the tile,
-// looping over the scan-lines d0 of that edge whose in-pixel lies in the tile.
+// Parameters of the 32 tasks of a warp, readable by any lane (the crossings of a task are evaluated by
+// whichever lanes the load-balanced search hands them to).
+struct TaskTable {
+    float p0d0[32], p0d1[32], p1d0[32], p2d0[32], p2d1[32], slope[32], slope02[32], slope21[32], ka[32];
+    int packed[32], fn[32], incl[32];
+};
+
+// One CTA per (image, 64x64 tile). The (face, edge, axis) tasks of the faces touching the tile are spread
+// over the warps, 32 per warp; each warp flattens the scan-line crossings of its 32 tasks across its lanes
+// (load-balanced search over the prefix sum of the task lengths, task parameters fetched by shuffle), and the
+// (crossing, run) pairs that have something to sweep go through a per-warp queue so that the expensive part
+// runs on dense warps.
 __global__ void __launch_bounds__(NTHREADS)
 raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
                   float eps, const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
@@ -572,24 +589,33 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ int list[LISTCAP];
     __shared__ int cnt, next;
-    __shared__ unsigned nzw[4][TILE];  // non-zero word masks: mn_row, mp_row, mn_col, mp_col
-    __shared__ __align__(16) uint2 srun[4][TILE][RCAP];  // run lists of the same four line blocks
+    __shared__ __align__(16) uint2 srun[4][TILE][RCAP];  // run lists: mn_row, mp_row, mn_col, mp_col
     __shared__ __align__(16) unsigned scount[4][TILE];
+    __shared__ int wqn[NWARPS];
+    __shared__ unsigned long long wacc[NWARPS][32][2];
     __shared__ __align__(8) uint64_t bar;
     const int W = is / 32;
+    const int LW = TILE * W;  // words per coverage block: a_row, a_col
+    // dynamic shared memory: face_index tile | coverage lines | per-warp queues | per-warp task tables
     int *fi = reinterpret_cast<int *>(smem_raw);
     uint32_t *lines = reinterpret_cast<uint32_t *>(smem_raw + TILE * TILE * sizeof(int));
-    const int LW = TILE * W;  // words per line block: a_row mn_row mp_row a_col mn_col mp_col
+    WarpQueue *wq = reinterpret_cast<WarpQueue *>(smem_raw + TILE * TILE * sizeof(int) + 2 * LW * sizeof(uint32_t));
+    TaskTable *tables = reinterpret_cast<TaskTable *>(wq + NWARPS);
     const int b = blockIdx.y;
     const int tiles_x = is / TILE;
     const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
     recs += (long)b * F;
     boxes += (long)b * F;
     grad_ndc += (long)b * V * 3;
     BwdCtx ctx;
     ctx.is = is; ctx.aa = aa; ctx.R = aa ? is / 2 : is; ctx.eps = eps;
     ctx.grad = grad_alpha + (long)b * ctx.R * ctx.R;
+    const float inv_is2 = 2.f / (float)is;
+    const long plane = (long)is * W;
+    WarpQueue &q = wq[warp];
+    TaskTable &tt = tables[warp];
 
     int base = 0;
     bool staged = false;
@@ -597,7 +623,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
         const int n = next_batch(boxes, base, F, tx0, ty0, list, &cnt, &next);
         if (n == 0) continue;
         if (!staged) {
-            // ---- stage the tile's face_index rows and the six bit-line blocks with TMA bulk copies
+            // ---- stage the tile's face_index rows, coverage lines and run lists with TMA bulk copies
             //      (tiles no face touches never get here: their face_index is never read)
             if (threadIdx.x == 0) {
                 mbar_init(&bar, 1);
@@ -606,108 +632,181 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             __syncthreads();
             if (warp == 0) {
                 if (lane == 0)
-                    mbar_expect_tx(&bar, (uint32_t)(TILE * TILE * 4 + 6 * LW * 4 + 4 * TILE * RCAP * 8 + 4 * TILE * 4));
+                    mbar_expect_tx(&bar, (uint32_t)(2 * LW * 4 + 4 * TILE * RCAP * 8 + 4 * TILE * 4));
                 __syncwarp();
-                for (int r = lane; r < TILE; r += 32)
-                    tma_bulk_g2s(fi + r * TILE, face_index + ((long)b * is + ty0 + r) * is + tx0, TILE * 4, &bar);
-                if (lane < 6) {
-                    const long plane = (long)is * W;
-                    const uint32_t *src;
-                    switch (lane) {
-                        case 0: src = cov_row + ((long)b * is + ty0) * W; break;
-                        case 1: src = m_row + ((long)b * 2 * is + ty0) * W; break;
-                        case 2: src = m_row + ((long)b * 2 * is + ty0) * W + plane; break;
-                        case 3: src = cov_col + ((long)b * is + tx0) * W; break;
-                        case 4: src = m_col + ((long)b * 2 * is + tx0) * W; break;
-                        default: src = m_col + ((long)b * 2 * is + tx0) * W + plane; break;
-                    }
-                    tma_bulk_g2s(lines + lane * LW, src, (uint32_t)(LW * 4), &bar);
-                } else if (lane >= 8 && lane < 12) {
+                if (lane == 0) tma_bulk_g2s(lines, cov_row + ((long)b * is + ty0) * W, (uint32_t)(LW * 4), &bar);
+                if (lane == 1) tma_bulk_g2s(lines + LW, cov_col + ((long)b * is + tx0) * W, (uint32_t)(LW * 4), &bar);
+                if (lane >= 8 && lane < 12) {
                     const int l4 = lane - 8, t0 = (l4 >> 1) ? tx0 : ty0;
                     tma_bulk_g2s(&srun[l4][0][0], runs + (((long)b * 4 + l4) * is + t0) * RCAP, TILE * RCAP * 8, &bar);
                     tma_bulk_g2s(&scount[l4][0], run_counts + ((long)b * 4 + l4) * is + t0, TILE * 4, &bar);
                 }
             }
-            mbar_wait(&bar, 0);
-            {   // masks of the non-zero words of every sweep line
-                const int which = threadIdx.x >> 6, l = threadIdx.x & 63;
-                const uint32_t *blk = lines + (which == 0 ? 1 : which == 1 ? 2 : which == 2 ? 4 : 5) * LW + l * W;
-                unsigned m = 0;
-                for (int w = 0; w < W; ++w) m |= (blk[w] != 0u ? 1u : 0u) << w;
-                nzw[which][l] = m;
+            // the face_index tile is 64 rows of 256 B: coalesced 16-byte loads (one bulk copy per row costs more
+            // in TMA issue overhead than the bytes are worth)
+            for (int i = threadIdx.x; i < TILE * TILE / 4; i += NTHREADS) {
+                const int r = i / (TILE / 4), c4 = i % (TILE / 4);
+                const int4 v = __ldg(reinterpret_cast<const int4 *>(face_index + ((long)b * is + ty0 + r) * is + tx0) + c4);
+                reinterpret_cast<int4 *>(fi)[i] = v;
             }
+            if (warp == 0) mbar_wait(&bar, 0);
             __syncthreads();
             staged = true;
         }
-        for (int task = threadIdx.x; task < 6 * n; task += NTHREADS) {
-            const int e = (task % 6) >> 1, axis = task & 1;
-            const FaceRec *rp = recs + list[task / 6];
-            const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rp));
-            const float4 q1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
-            const float4 q2 = __ldg(reinterpret_cast<const float4 *>(rp) + 2);
-            const int4 q3 = __ldg(reinterpret_cast<const int4 *>(rp) + 3);
-            const int fn = __float_as_int(q2.y);
-            const int v0 = __float_as_int(q2.z), v1 = __float_as_int(q2.w), v2 = q3.x;
-            // pixel-space corners along (d0, d1) = (x, y) for axis 0, (y, x) for axis 1
-            const float ax = to_pix(q0.x, is), ay = to_pix(q0.y, is), bx = to_pix(q0.w, is), by = to_pix(q1.x, is),
-                        cx = to_pix(q1.z, is), cy = to_pix(q1.w, is);
-            const float a0 = axis ? ay : ax, a1 = axis ? ax : ay, b0 = axis ? by : bx, b1 = axis ? bx : by,
-                        c0 = axis ? cy : cx, c1 = axis ? cx : cy;
-            // vertex order of this edge: p0 = corner e, p1 = corner e+1, p2 = corner e+2
-            const float p0d0 = e == 0 ? a0 : e == 1 ? b0 : c0, p0d1 = e == 0 ? a1 : e == 1 ? b1 : c1;
-            const float p1d0 = e == 0 ? b0 : e == 1 ? c0 : a0, p1d1 = e == 0 ? b1 : e == 1 ? c1 : a1;
-            const float p2d0 = e == 0 ? c0 : e == 1 ? a0 : b0, p2d1 = e == 0 ? c1 : e == 1 ? a1 : b1;
-            const int vid0 = e == 0 ? v0 : e == 1 ? v1 : v2, vid1 = e == 0 ? v1 : e == 1 ? v2 : v0;
-            int dir;
-            if (axis == 0) dir = (p0d0 < p1d0) ? -1 : 1;
-            else dir = (p0d0 < p1d0) ? 1 : -1;
-            const int d0_from = __float2int_rz(fmaxf(ceilf(fminf(p0d0, p1d0)), 0.f));
-            const int d0_to = __float2int_rz(fminf(fmaxf(p0d0, p1d0), (float)(is - 1)));
-            const int t0 = axis == 0 ? tx0 : ty0;  // tile origin along d0
-            const int t1 = axis == 0 ? ty0 : tx0;  // tile origin along d1
-            const int lo = max(d0_from, t0), hi = min(d0_to, t0 + TILE - 1);
-            if (lo > hi) continue;
-            const float ka = p1d0 - p0d0;
-            const float slope = (p1d1 - p0d1) / ka;
-            const float slope02 = (p2d1 - p0d1) / (p2d0 - p0d0), slope21 = (p1d1 - p2d1) / (p1d0 - p2d0);
-            const uint32_t *blkA = lines + (axis == 0 ? 3 : 0) * LW;
-            const uint32_t *blkN = blkA + LW, *blkP = blkA + 2 * LW;
-            const int lN = axis == 0 ? 2 : 0, lP = lN + 1;
-            const unsigned *nzN = nzw[lN], *nzP = nzw[lP];
-            const int fs0 = axis == 0 ? 1 : TILE, fs1 = axis == 0 ? TILE : 1;  // fi strides along d0 / d1
-            float acc0 = 0.f, acc1 = 0.f;
-            for (int d0 = lo; d0 <= hi; ++d0) {
-                if ((scount[lN][d0 - t0] | scount[lP][d0 - t0]) == 0u) continue;  // nothing to sweep on this line
-                const float fd0 = (float)d0;
-                const float d1_cross = slope * (fd0 - p0d0) + p0d1;
-                const int d1_in = __float2int_rz(dir > 0 ? floorf(d1_cross) : ceilf(d1_cross));
-                const int d1_out = d1_in + dir;
-                if (d1_in < 0 || is <= d1_in) continue;
-                if (d1_out < 0 || is <= d1_out) continue;
-                if (d1_in < t1 || d1_in >= t1 + TILE) continue;  // another tile owns this crossing
-                const int l0 = d0 - t0;
-                // out-sweep: from the out pixel to the image border, only when this face owns the in pixel
-                if (fi[l0 * fs0 + (d1_in - t1) * fs1] == fn) {
-                    const int lim = dir > 0 ? is - 1 : 0;
-                    sweep_runs(srun[lN][l0], scount[lN][l0], blkN + l0 * W, nzN[l0], min(d1_out, lim), max(d1_out, lim),
-                               axis, d0, d1_cross, ka, p0d0, p1d0, ctx, acc0, acc1);
+        const int ntasks = 6 * n;
+        for (int g0 = warp * 32; g0 < ntasks; g0 += NWARPS * 32) {
+            // ---- one (face, edge, axis) task per lane
+            const int task = g0 + lane;
+            float p0d0 = 0.f, p0d1 = 0.f, p1d0 = 0.f, p2d0 = 0.f, p2d1 = 0.f, slope = 0.f, slope02 = 0.f, slope21 = 0.f,
+                  ka = 0.f;
+            int fn = -1, vid0 = 0, vid1 = 0, axis = 0, dir = 1, lo = 0, len = 0;
+            if (task < ntasks) {
+                const int e = (task % 6) >> 1;
+                axis = task & 1;
+                const FaceRec *rp = recs + list[task / 6];
+                const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rp));
+                const float4 q1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
+                const float4 q2 = __ldg(reinterpret_cast<const float4 *>(rp) + 2);
+                const int4 q3 = __ldg(reinterpret_cast<const int4 *>(rp) + 3);
+                fn = __float_as_int(q2.y);
+                const int v0 = __float_as_int(q2.z), v1 = __float_as_int(q2.w), v2 = q3.x;
+                // pixel-space corners along (d0, d1) = (x, y) for axis 0, (y, x) for axis 1
+                const float ax = to_pix(q0.x, is), ay = to_pix(q0.y, is), bx = to_pix(q0.w, is), by = to_pix(q1.x, is),
+                            cx = to_pix(q1.z, is), cy = to_pix(q1.w, is);
+                const float a0 = axis ? ay : ax, a1 = axis ? ax : ay, b0 = axis ? by : bx, b1 = axis ? bx : by,
+                            c0 = axis ? cy : cx, c1 = axis ? cx : cy;
+                // vertex order of this edge: p0 = corner e, p1 = corner e+1, p2 = corner e+2
+                p0d0 = e == 0 ? a0 : e == 1 ? b0 : c0; p0d1 = e == 0 ? a1 : e == 1 ? b1 : c1;
+                p1d0 = e == 0 ? b0 : e == 1 ? c0 : a0;
+                const float p1d1 = e == 0 ? b1 : e == 1 ? c1 : a1;
+                p2d0 = e == 0 ? c0 : e == 1 ? a0 : b0; p2d1 = e == 0 ? c1 : e == 1 ? a1 : b1;
+                vid0 = e == 0 ? v0 : e == 1 ? v1 : v2; vid1 = e == 0 ? v1 : e == 1 ? v2 : v0;
+                if (axis == 0) dir = (p0d0 < p1d0) ? -1 : 1;
+                else dir = (p0d0 < p1d0) ? 1 : -1;
+                const int d0_from = __float2int_rz(fmaxf(ceilf(fminf(p0d0, p1d0)), 0.f));
+                const int d0_to = __float2int_rz(fminf(fmaxf(p0d0, p1d0), (float)(is - 1)));
+                const int t0 = axis == 0 ? tx0 : ty0;
+                lo = max(d0_from, t0);
+                len = max(min(d0_to, t0 + TILE - 1) - lo + 1, 0);
+                ka = p1d0 - p0d0;
+                slope = (p1d1 - p0d1) / ka;
+                slope02 = (p2d1 - p0d1) / (p2d0 - p0d0);
+                slope21 = (p1d1 - p2d1) / (p1d0 - p2d0);
+            }
+            // inclusive prefix sum of the task lengths over the warp
+            int incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            if (total == 0) continue;
+            const int packed = (lo & 0xffff) | (axis << 16) | ((dir > 0 ? 1 : 0) << 17);
+            __syncwarp();
+            tt.p0d0[lane] = p0d0; tt.p0d1[lane] = p0d1; tt.p1d0[lane] = p1d0; tt.p2d0[lane] = p2d0; tt.p2d1[lane] = p2d1;
+            tt.slope[lane] = slope; tt.slope02[lane] = slope02; tt.slope21[lane] = slope21; tt.ka[lane] = ka;
+            tt.packed[lane] = packed; tt.fn[lane] = fn; tt.incl[lane] = incl;
+            wacc[warp][lane][0] = 0ull;
+            wacc[warp][lane][1] = 0ull;
+            if (lane == 0) wqn[warp] = 0;
+            __syncwarp();
+
+            for (int kb = 0; kb < total; kb += 32) {
+                const int kk = kb + lane;
+                const bool active = kk < total;
+                // owner task of crossing kk: number of tasks whose inclusive prefix is <= kk
+                int j = 0;
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1)
+                    if (tt.incl[j + sft - 1] <= kk) j += sft;
+                const int o = active ? j : 31;
+                const int o_excl = o > 0 ? tt.incl[o - 1] : 0, o_pack = tt.packed[o], o_fn = tt.fn[o];
+                const float o_p0d0 = tt.p0d0[o], o_p0d1 = tt.p0d1[o], o_p1d0 = tt.p1d0[o], o_p2d0 = tt.p2d0[o];
+                const float o_p2d1 = tt.p2d1[o], o_slope = tt.slope[o], o_s02 = tt.slope02[o], o_s21 = tt.slope21[o];
+                const float o_ka = tt.ka[o];
+                if (active) {
+                    const int o_axis = (o_pack >> 16) & 1, o_dir = ((o_pack >> 17) & 1) ? 1 : -1;
+                    const int d0 = (o_pack & 0xffff) + (kk - o_excl);
+                    const int t0 = o_axis == 0 ? tx0 : ty0, t1 = o_axis == 0 ? ty0 : tx0;
+                    const int l0 = d0 - t0;
+                    const int lN = o_axis == 0 ? 2 : 0, lP = lN + 1;
+                    const unsigned cN = scount[lN][l0], cP = scount[lP][l0];
+                    if ((cN | cP) != 0u) {  // something to sweep on this line
+                        const float fd0 = (float)d0;
+                        const float x = o_slope * (fd0 - o_p0d0) + o_p0d1;
+                        const int d1_in = __float2int_rz(o_dir > 0 ? floorf(x) : ceilf(x));
+                        const int d1_out = d1_in + o_dir;
+                        if (d1_in >= 0 && d1_in < is && d1_out >= 0 && d1_out < is && d1_in >= t1 && d1_in < t1 + TILE) {
+                            const bool has0 = o_p1d0 != fd0, has1 = o_p0d0 != fd0;
+                            const float c0 = o_ka / (o_p1d0 - fd0), c1 = o_ka / (fd0 - o_p0d0);
+                            const unsigned meta = (unsigned)o | (has0 ? 32u : 0u) | (has1 ? 64u : 0u);
+                            const int fs0 = o_axis == 0 ? 1 : TILE, fs1 = o_axis == 0 ? TILE : 1;
+                            // sweep 0: out-sweep (missing-coverage list, from the out pixel to the border) when this
+                            // face owns the in pixel; sweep 1: in-sweep (from the in pixel to the opposite edge)
+#pragma unroll 1
+                            for (int sw = 0; sw < 2; ++sw) {
+                                int ls, ra, rc;
+                                if (sw == 0) {
+                                    if (fi[l0 * fs0 + (d1_in - t1) * fs1] != o_fn) continue;
+                                    const int lim = o_dir > 0 ? is - 1 : 0;
+                                    ls = lN; ra = min(d1_out, lim); rc = max(d1_out, lim);
+                                } else {
+                                    float c2;
+                                    if ((fd0 - o_p0d0) * (fd0 - o_p2d0) < 0.f) c2 = o_s02 * (fd0 - o_p0d0) + o_p0d1;
+                                    else c2 = o_s21 * (fd0 - o_p2d0) + o_p2d1;
+                                    const int lim = __float2int_rz(o_dir > 0 ? ceilf(c2) : floorf(c2));
+                                    ra = max(min(d1_in, lim), 0); rc = min(max(d1_in, lim), is - 1);
+                                    const uint32_t *A = lines + (o_axis == 0 ? LW : 0) + l0 * W;
+                                    const bool alpha_out = (A[d1_out >> 5] >> (d1_out & 31)) & 1u;
+                                    ls = alpha_out ? lN : lP;
+                                }
+                                const unsigned cs = scount[ls][l0];
+                                if (cs == 0u || ra > rc) continue;
+                                if (cs == RUN_OVERFLOW) {
+                                    // more runs than the list holds: walk the bit line (global memory)
+                                    const uint32_t *line = ((ls >> 1) ? m_col : m_row) +
+                                                           ((long)b * 2 * is + (ls >> 1 ? tx0 : ty0) + l0) * W + (ls & 1) * plane;
+                                    float a0 = 0.f, a1 = 0.f;
+                                    sweep(line, FULL, ra, rc, o_axis, d0, x, o_ka, o_p0d0, o_p1d0, ctx, a0, a1);
+                                    acc_add(&wacc[warp][o][0], a0);
+                                    acc_add(&wacc[warp][o][1], a1);
+                                    continue;
+                                }
+                                for (unsigned r = 0; r < cs; ++r) {
+                                    const uint2 run = srun[ls][l0][r];
+                                    const int s = max(ra, (int)(run.x & 0xffffu)), e = min(rc, (int)(run.x >> 16));
+                                    if (s > e) continue;
+                                    const int pos = atomicAdd(&wqn[warp], 1);
+                                    if (pos < WQCAP) {
+                                        q.x[pos] = x; q.c0[pos] = c0; q.c1[pos] = c1; q.G[pos] = __uint_as_float(run.y);
+                                        q.se[pos] = (unsigned)s | ((unsigned)e << 16);
+                                        q.meta[pos] = meta;
+                                    } else {  // queue full: evaluate in place
+                                        float a0, a1;
+                                        eval_item(x, c0, c1, __uint_as_float(run.y), s, e, has0, has1, inv_is2, eps, a0, a1);
+                                        acc_add(&wacc[warp][o][0], a0);
+                                        acc_add(&wacc[warp][o][1], a1);
+                                    }
+                                }
+                            }
+                        }
+                    }
                 }
-                // in-sweep: from the in pixel to the opposite edge of the triangle
-                {
-                    float c2;
-                    if ((fd0 - p0d0) * (fd0 - p2d0) < 0.f) c2 = slope02 * (fd0 - p0d0) + p0d1;
-                    else c2 = slope21 * (fd0 - p2d0) + p2d1;
-                    const int lim = __float2int_rz(dir > 0 ? ceilf(c2) : floorf(c2));
-                    const int a = max(min(d1_in, lim), 0), c = min(max(d1_in, lim), is - 1);
-                    const bool alpha_out = (blkA[l0 * W + (d1_out >> 5)] >> (d1_out & 31)) & 1u;
-                    const int ls = alpha_out ? lN : lP;
-                    sweep_runs(srun[ls][l0], scount[ls][l0], (alpha_out ? blkN : blkP) + l0 * W, nzw[ls][l0], a, c,
-                               axis, d0, d1_cross, ka, p0d0, p1d0, ctx, acc0, acc1);
+                __syncwarp();
+                const int nq = min(wqn[warp], WQCAP);
+                if (nq > WQCAP - 48 || kb + 32 >= total) {
+                    drain_queue(q, nq, wacc[warp], inv_is2, eps);
+                    __syncwarp();
+                    if (lane == 0) wqn[warp] = 0;
+                    __syncwarp();
                 }
             }
             // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
+            const float acc0 = acc_get(wacc[warp][lane][0]), acc1 = acc_get(wacc[warp][lane][1]);
             if (acc0 != 0.f) atomicAdd(grad_ndc + (long)vid0 * 3 + (1 - axis), acc0);
             if (acc1 != 0.f) atomicAdd(grad_ndc + (long)vid1 * 3 + (1 - axis), acc1);
+            __syncwarp();
         }
     }
 }
@@ -853,7 +952,8 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
     if (B == 0 || F == 0) return HM_OK;
-    const size_t smem = (size_t)TILE * TILE * 4 + (size_t)6 * TILE * (is / 32) * 4;
+    const size_t smem = (size_t)TILE * TILE * 4 + (size_t)2 * TILE * (is / 32) * 4 + NWARPS * sizeof(WarpQueue) +
+                        NWARPS * sizeof(TaskTable);
     HM_UNSUPPORTED(is > 1024, "hm_raster_sil_bwd: raster size %d > 1024 is not supported", is);
     static size_t configured = 0;  // static + dynamic shared memory exceeds the 48 KB default: opt in once per size
     if (smem > configured) {
