@@ -546,24 +546,43 @@ struct WarpQueue {
     unsigned se[WQCAP], meta[WQCAP];  // s | e << 16 ; owner lane | has0 << 5 | has1 << 6
 };
 
-// Per-task accumulators live in shared memory as 64-bit fixed point (2^-40 units): integer atomics are native
-// on shared memory (float adds are CAS loops) and make the per-task sums independent of the order of arrival.
-constexpr float FIX_SCALE = 1099511627776.f;  // 2^40
-__device__ __forceinline__ void acc_add(unsigned long long *slot, float v) {
-    if (v != 0.f) atomicAdd(slot, (unsigned long long)__float2ll_rn(v * FIX_SCALE));
+// Per-task accumulators live in shared memory (float; atomics there are CAS loops, so contention must be
+// avoided): a drain pass evaluates 32 items, sums the results of the items that belong to the same task inside
+// the warp (match_any + shuffles), and one lane per task does a plain read-modify-write.
+__device__ __forceinline__ void acc_add(float *slot, float v) {
+    if (v != 0.f) atomicAdd(slot, v);
 }
-__device__ __forceinline__ float acc_get(unsigned long long v) { return (float)((double)(long long)v * (1.0 / 1099511627776.0)); }
 
-__device__ __forceinline__ void drain_queue(WarpQueue &q, int n, unsigned long long (*wacc)[2], float inv_is2,
-                                            float eps) {
+__device__ __forceinline__ void drain_queue(WarpQueue &q, int n, float (*wacc)[2], float inv_is2, float eps) {
     const int lane = threadIdx.x & 31;
-    for (int i = lane; i < n; i += 32) {
-        const unsigned se = q.se[i], meta = q.meta[i];
-        float a0, a1;
-        eval_item(q.x[i], q.c0[i], q.c1[i], q.G[i], (int)(se & 0xffffu), (int)(se >> 16), (meta >> 5) & 1u,
-                  (meta >> 6) & 1u, inv_is2, eps, a0, a1);
-        acc_add(&wacc[meta & 31u][0], a0);
-        acc_add(&wacc[meta & 31u][1], a1);
+    const unsigned FULL = 0xffffffffu;
+    for (int base = 0; base < n; base += 32) {
+        const int i = base + lane;
+        float a0 = 0.f, a1 = 0.f;
+        unsigned key = 32u + (unsigned)lane;  // lanes without an item form singleton groups
+        if (i < n) {
+            const unsigned se = q.se[i], meta = q.meta[i];
+            eval_item(q.x[i], q.c0[i], q.c1[i], q.G[i], (int)(se & 0xffffu), (int)(se >> 16), (meta >> 5) & 1u,
+                      (meta >> 6) & 1u, inv_is2, eps, a0, a1);
+            key = meta & 31u;
+        }
+        unsigned peers = __match_any_sync(FULL, key);
+        const bool leader = (__ffs(peers) - 1) == lane;
+        int cnt = __popc(peers);
+        int mx = cnt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
+        float s0 = 0.f, s1 = 0.f;
+        for (int it = 0; it < mx; ++it) {
+            const int src = peers ? __ffs(peers) - 1 : lane;
+            const float v0 = __shfl_sync(FULL, a0, src), v1 = __shfl_sync(FULL, a1, src);
+            if (peers) { s0 += v0; s1 += v1; peers &= peers - 1; }
+        }
+        if (leader && key < 32u) {
+            if (s0 != 0.f) wacc[key][0] += s0;
+            if (s1 != 0.f) wacc[key][1] += s1;
+        }
+        __syncwarp();
     }
 }
 
@@ -592,7 +611,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     __shared__ __align__(16) uint2 srun[4][TILE][RCAP];  // run lists: mn_row, mp_row, mn_col, mp_col
     __shared__ __align__(16) unsigned scount[4][TILE];
     __shared__ int wqn[NWARPS];
-    __shared__ unsigned long long wacc[NWARPS][32][2];
+    __shared__ float wacc[NWARPS][32][2];
     __shared__ __align__(8) uint64_t bar;
     const int W = is / 32;
     const int LW = TILE * W;  // words per coverage block: a_row, a_col
@@ -707,8 +726,8 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             tt.p0d0[lane] = p0d0; tt.p0d1[lane] = p0d1; tt.p1d0[lane] = p1d0; tt.p2d0[lane] = p2d0; tt.p2d1[lane] = p2d1;
             tt.slope[lane] = slope; tt.slope02[lane] = slope02; tt.slope21[lane] = slope21; tt.ka[lane] = ka;
             tt.packed[lane] = packed; tt.fn[lane] = fn; tt.incl[lane] = incl;
-            wacc[warp][lane][0] = 0ull;
-            wacc[warp][lane][1] = 0ull;
+            wacc[warp][lane][0] = 0.f;
+            wacc[warp][lane][1] = 0.f;
             if (lane == 0) wqn[warp] = 0;
             __syncwarp();
 
@@ -803,7 +822,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 }
             }
             // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
-            const float acc0 = acc_get(wacc[warp][lane][0]), acc1 = acc_get(wacc[warp][lane][1]);
+            const float acc0 = wacc[warp][lane][0], acc1 = wacc[warp][lane][1];
             if (acc0 != 0.f) atomicAdd(grad_ndc + (long)vid0 * 3 + (1 - axis), acc0);
             if (acc1 != 0.f) atomicAdd(grad_ndc + (long)vid1 * 3 + (1 - axis), acc1);
             __syncwarp();
