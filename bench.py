@@ -219,10 +219,10 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         eng.step()
-    if world > 1:  # final best-init reduction (the only collective of the job)
-        bi, bl = eng.best_init(clips=1)
-        gathered = [torch.empty_like(bl) for _ in range(world)]
-        dist.all_gather(gathered, bl)
+    # final best-init reduction (the only collective of the job): per-clip argmin, then one all_gather
+    from homan_b200 import distributed as hd
+    bi, bl = eng.best_init(clips=1)
+    hd.gather_best([rank], bi.long(), bl, world)
     e1.record()
     barrier()
     clocks = sampler.stop()

@@ -145,18 +145,31 @@ class FitEngine:
         self.total = torch.zeros(self.P, device=dev)
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
 
+        self.configure(loss_weights)
+        self.gpu_launches_per_step = 0
+        self.graph = None
+        self.use_graph = use_graph
+        self.iteration = 0
+        self.upload(self.stage_host(batch, pin=False))
+
+
+    def configure(self, loss_weights):
+        """(Re)selects the active loss terms (gating of /root/reference/homan/homan.py:433-506: a term runs iff its
+        weight is > 0) without touching parameters or optimiser state. Invalidates the captured graph."""
+        self.lw = {k: float(v) for k, v in loss_weights.items()}
+        B, Vo, R, dev = self.B, self.Vo, REND_SIZE, self.device
         on = lambda k: self.lw.get(k, 0.0) > 0  # noqa: E731  (gating of homan.py:433-506)
         self.on_sil_obj, self.on_sil_hand = on("lw_sil_obj"), on("lw_sil_hand")
         self.on_smooth = on("lw_smooth_hand") or on("lw_smooth_obj")
         self.on_v2d, self.on_inter, self.on_pca = on("lw_v2d_hand"), on("lw_inter"), on("lw_pca")
         self.on_contact, self.on_collision = on("lw_contact"), on("lw_collision")
-        if self.on_sil_obj:
+        if self.on_sil_obj and not hasattr(self, "rb_obj"):
             self.rb_obj = ops.RasterBuffers(B, Vo, self.faces_obj.shape[1], R, True, dev)
             self.ga_obj = torch.empty(B, R, R, device=dev)
-        if self.on_sil_hand:
+        if self.on_sil_hand and not hasattr(self, "rb_hand"):
             self.rb_hand = ops.RasterBuffers(B, 778, self.faces_hand.shape[1], R, True, dev)
             self.ga_hand = torch.empty(B, R, R, device=dev)
-        if self.on_collision:
+        if self.on_collision and not hasattr(self, "phi_scratch"):
             self.phi_scratch = torch.empty(B, SDF_GRID ** 3, device=dev)
         w = torch.zeros(NPART)
         for name, slot in LOSS_SLOTS.items():
@@ -168,11 +181,7 @@ class FitEngine:
             self.const_losses["loss_scale_obj"] = 0.0
         if on("lw_scale_hand"):
             self.const_losses["loss_scale_hand"] = 0.0
-        self.gpu_launches_per_step = 0
         self.graph = None
-        self.use_graph = use_graph
-        self.iteration = 0
-        self.upload(self.stage_host(batch, pin=False))
 
     # ------------------------------------------------------------------ host -> device
     @staticmethod

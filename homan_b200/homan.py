@@ -1,0 +1,197 @@
+"""Drop-in for /root/reference/homan/homan.py::HOMan on the fitting hot path.
+
+Same constructor keywords (homan.py:27-60), same parameter / buffer names (checkpoint compatible,
+SURVEY.md §5), `forward(loss_weights) -> (loss_dict, metric_dict)` with the reference's loss names, and the
+accessors the driver uses (`get_verts_object()`, `get_verts_hand()`, `verts_object_init`, `verts_hand_init`,
+`faces_hand`, `faces_object`, `state_dict()`; fit_vid_dataset.py:365-379,489-493). All arithmetic runs in the
+fused CUDA engine (engine.py); the nn.Parameters are views of the engine's flat parameter buffer.
+
+Extension: `frames_per_problem=T` batches P = B / T independent problems (clips x inits) in front of the
+reference's frame axis; the default (T = B) is the reference's single-clip semantics.
+Supported configuration (README.md:207-238 of the reference): one hand per frame, hand_proj_mode="persp",
+optimize_mano=True, optimize_mano_beta=True, optimize_object_scale=False. Anything else raises.
+"""
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib
+from .engine import LOSS_SLOTS, PARAM_ORDER, FitEngine
+from .shims.mano_layer import load_asset
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else np.asarray(x)
+
+
+class _FusedLosses(torch.autograd.Function):
+    """Bridges the fused forward+backward to autograd: outputs the unweighted losses (summed over problems);
+    backward hands out the parameter gradients the engine already accumulated for sum_k lw_k * loss_k, and
+    therefore requires the upstream gradient of loss k to be lw_k (what jointopt.py:180-183,191 produces)."""
+
+    @staticmethod
+    def forward(ctx, model, weights, *params):
+        eng = model.engine
+        eng._iteration(adam=False)
+        eng.step_counter.zero_()
+        ctx.model, ctx.weights = model, weights
+        names = model._loss_names
+        vals = torch.stack([eng.losses[:, model._slot_of[n]].sum() for n in names]) if names else eng.losses.new_zeros(0)
+        return vals
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        model = ctx.model
+        expect = torch.tensor([ctx.weights[n] for n in model._loss_names], device=grad_out.device)
+        if grad_out.numel() and not torch.allclose(grad_out, expect, rtol=1e-5, atol=0):
+            raise _lib.HomanB200Error(
+                "homan_b200.HOMan: losses must be combined as sum(loss_k * loss_weights['lw_k']) with the "
+                "loss_weights passed to forward() (the fused kernels already applied them)")
+        return (None, None) + tuple(model.engine.grads[k].clone() for k in PARAM_ORDER)
+
+
+class HOMan(nn.Module):
+    def __init__(self, translations_object, rotations_object, verts_object_og, faces_object, translations_hand,
+                 rotations_hand, verts_hand_og, ref_verts2d_hand, hand_sides, mano_trans, mano_rot, mano_betas,
+                 mano_pca_pose, faces_hand, masks_object, masks_hand, camintr_rois_object, camintr_rois_hand,
+                 target_masks_object, target_masks_hand, class_name, cams_hand=None, int_scale_init=1.0,
+                 camintr=None, optimize_object_scale=False, optimize_ortho_cam=True, hand_proj_mode="persp",
+                 optimize_mano=True, optimize_mano_beta=True, inter_type="centroid", image_size=640,
+                 frames_per_problem=None, mano_asset=None, mano_root="extra_data/mano", loss_weights=None, lr=1e-2):
+        super().__init__()
+        if len(hand_sides) != 1:
+            raise NotImplementedError("homan_b200.HOMan: one hand per frame")
+        if hand_proj_mode != "persp" or not optimize_mano or not optimize_mano_beta or optimize_object_scale:
+            raise NotImplementedError("homan_b200.HOMan: persp projection, optimize_mano, optimize_mano_beta, "
+                                      "fixed object scale (the reference's README configuration)")
+        if inter_type != "centroid" or int_scale_init != 1:
+            raise NotImplementedError("homan_b200.HOMan: inter_type='centroid', int_scale_init=1")
+        self.hand_sides, self.hand_nb, self.hand_proj_mode = hand_sides, 1, hand_proj_mode
+        self.optimize_mano, self.optimize_object_scale, self.image_size = optimize_mano, optimize_object_scale, image_size
+        self.class_name, self.lr = class_name, lr
+        B = int(translations_object.shape[0])
+        T = B if frames_per_problem is None else int(frames_per_problem)
+        if B % T:
+            raise ValueError("batch size must be a multiple of frames_per_problem")
+        P = B // T
+        side = hand_sides[0]
+        asset = mano_asset if mano_asset is not None else load_asset(mano_root, is_right=(side == "right"))
+        if "closed_faces" not in asset:
+            closed = np.load("local_data/closed_fmano.npy")  # /root/reference/homan/lossutils.py:15
+            asset = dict(asset, closed_faces=closed if side == "right" else closed[:, ::-1].copy())
+        rot_o, rot_h = _np(rotations_object), _np(rotations_hand)
+        verts_og = _np(verts_object_og)
+        faces_o = _np(faces_object)
+        cam = np.array([[[1, 0, 0.5], [0, 1, 0.5], [0, 0, 1]]], np.float32) if camintr is None else _np(camintr)
+        if cam.ndim == 2:
+            cam = cam[None]
+        cam = np.broadcast_to(cam, (T,) + cam.shape[1:]) if cam.shape[0] == 1 else cam
+        rs = lambda x, *tail: np.ascontiguousarray(_np(x), dtype=np.float32).reshape((P, T) + tail)  # noqa: E731
+        batch = {
+            "side": side, "image_size": image_size, "mano_asset": asset,
+            "obj_verts_can": np.ascontiguousarray(verts_og[0] if verts_og.ndim == 3 else verts_og, np.float32),
+            "obj_faces": np.ascontiguousarray(faces_o[0] if faces_o.ndim == 3 else faces_o),
+            "hand_faces": np.ascontiguousarray(_np(faces_hand).reshape(-1, 3)[:1538]),
+            "obj_t": rs(translations_object, 3), "obj_R": rs(rot_o, 3, rot_o.shape[-1]),
+            "hand_t": rs(translations_hand, 3), "hand_R": rs(rot_h, 3, rot_h.shape[-1]),
+            "pca": rs(mano_pca_pose, _np(mano_pca_pose).shape[-1]), "mano_rot": rs(mano_rot, 3),
+            "mano_trans": rs(mano_trans, 3), "betas": rs(mano_betas, 10),
+            "camintr": np.ascontiguousarray(np.tile(cam, (P, 1, 1)) if cam.shape[0] == T else cam, np.float32).reshape(P, T, 3, 3),
+            "K_roi_obj": rs(camintr_rois_object, 3, 3), "K_roi_hand": rs(camintr_rois_hand, 3, 3),
+            "verts2d": rs(ref_verts2d_hand, 778, 2),
+            "target_masks_object": rs(target_masks_object, 256, 256), "target_masks_hand": rs(target_masks_hand, 256, 256),
+        }
+        self._batch, self._asset = batch, asset
+        self.P, self.T = P, T
+        self._build_engine(loss_weights or {})
+        dev = self.engine.device
+        buf = lambda x: torch.as_tensor(_np(x)).to(dev)  # noqa: E731
+        self.register_buffer("verts_object_og", buf(verts_object_og).float())
+        self.register_buffer("verts_hand_og", buf(verts_hand_og).float())
+        self.register_buffer("ref_verts2d_hand", buf(ref_verts2d_hand).float())
+        self.register_buffer("int_scales_hand", torch.ones(1, device=dev))
+        self.register_buffer("int_scales_object", torch.ones(1, device=dev))
+        self.register_buffer("int_scale_object_mean", torch.ones(1, device=dev))
+        self.register_buffer("int_scale_hand_mean", torch.ones(1, device=dev))
+        tmo, tmh = buf(target_masks_object).float(), buf(target_masks_hand).float()
+        self.register_buffer("ref_mask_object", (tmo > 0).float())
+        self.register_buffer("keep_mask_object", (tmo >= 0).float())
+        self.register_buffer("ref_mask_hand", (tmh > 0).float())
+        self.register_buffer("keep_mask_hand", (tmh >= 0).float())
+        self.register_buffer("camintr_rois_object", buf(camintr_rois_object).float())
+        self.register_buffer("camintr_rois_hand", buf(camintr_rois_hand).float())
+        self.register_buffer("faces_object", buf(faces_object))
+        self.register_buffer("faces_hand", buf(faces_hand))
+        self.register_buffer("textures_object", torch.ones(faces_o.shape[0], faces_o.shape[-2], 1, 1, 1, 3, device=dev))
+        fh = _np(faces_hand)
+        self.register_buffer("textures_hand", torch.ones(fh.shape[0], fh.shape[-2], 1, 1, 1, 3, device=dev))
+        self.register_buffer("camintr", buf(cam).float())
+        if cams_hand is not None:
+            self.cams_hand = nn.Parameter(buf(cams_hand).float(), requires_grad=True)
+        if masks_hand is not None:
+            self.register_buffer("masks_human", buf(masks_hand))
+        mo = buf(masks_object)
+        self.register_buffer("masks_object", mo[None] if mo.dim() == 2 else mo)
+        with torch.no_grad():
+            self.verts_object_init, _ = self.get_verts_object()
+            self.verts_hand_init, _ = self.get_verts_hand()
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _build_engine(self, loss_weights):
+        self.engine = FitEngine(self._batch, loss_weights, lr=self.lr, mano_asset=self._asset, use_graph=True)
+        for k in PARAM_ORDER:
+            # nn.Parameters that alias the engine's flat buffer (fused Adam updates them in place)
+            setattr(self, k, nn.Parameter(self.engine.params[k], requires_grad=True))
+        self._weights = {k: float(v) for k, v in loss_weights.items()}
+
+    def _sync_weights(self, loss_weights):
+        lw = {k: float(v) for k, v in loss_weights.items()}
+        if lw != self._weights:
+            self.engine.configure(lw)   # parameters (and any optimiser holding them) stay in place
+            self._weights = lw
+
+    def load_state_dict(self, state_dict, strict=True):
+        out = super().load_state_dict(state_dict, strict=strict)
+        for k in PARAM_ORDER:  # keep aliasing the engine buffer after a load
+            self.engine.params[k].copy_(getattr(self, k).data.reshape(self.engine.params[k].shape))
+            getattr(self, k).data = self.engine.params[k]
+        return out
+
+    # ------------------------------------------------------------------ reference API
+    def get_verts_object(self, **kwargs):
+        s = _lib.current_stream()
+        self.engine._forward_vertices(s)
+        v = self.engine.verts_obj.clone()
+        return v, v
+
+    def get_verts_hand(self, detach_scale=False, **kwargs):
+        s = _lib.current_stream()
+        self.engine._forward_vertices(s)
+        v = self.engine.verts_hand.clone()
+        return v, v
+
+    def forward(self, loss_weights=None):
+        if loss_weights is None:
+            loss_weights = self._weights
+        self._sync_weights(loss_weights)
+        eng = self.engine
+        names = [n for n in LOSS_SLOTS if eng.lw.get(n.replace("loss_", "lw_"), 0.0) > 0]
+        if eng.on_smooth:
+            names += [n for n in ("loss_smooth_obj", "loss_smooth_hand") if n not in names]
+        from .engine import PART
+        self._loss_names = names
+        self._slot_of = {n: PART[LOSS_SLOTS[n]] for n in names}
+        weights = {n: eng.lw.get(n.replace("loss_", "lw_"), 0.0) for n in names}
+        vals = _FusedLosses.apply(self, weights, *[getattr(self, k) for k in PARAM_ORDER])
+        loss_dict = {n: vals[i] for i, n in enumerate(names)}
+        for k, v in eng.const_losses.items():
+            loss_dict[k] = vals.new_tensor(v)
+        metric_dict = {}
+        m = eng.metric_dict()
+        for k, v in m.items():
+            metric_dict[k] = float(v.max() if k == "handobj_maxdist" else v.mean())
+        return loss_dict, metric_dict
+
+    def per_problem_losses(self):
+        """{loss name: [P]} of the last forward / step (the problem-axis extension)."""
+        return self.engine.loss_dict()

@@ -1,0 +1,105 @@
+"""GPU: the reference-facing surfaces (optimize_hand_object, HOMan, and the neural_renderer / sdf / mano
+drop-ins) against the golden vectors of the unmodified reference and against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from golden_utils import PARAMS, load, reference_inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["ref_cfg1_cube", "ref_small_step2"])
+def test_optimize_hand_object_matches_reference(name, mano_assets, tmp_path):
+    from homan_b200.jointopt import optimize_hand_object
+    z, batch, lw, iters = load(name, mano_assets["right"])
+    inp = reference_inputs(batch, 0, mano_assets["right"])
+    model, ev, imgs = optimize_hand_object(loss_weights=lw, num_iterations=iters, lr=1e-2, viz_folder=str(tmp_path),
+                                           optimize_mano=True, optimize_mano_beta=True, image_size=640,
+                                           mano_asset=mano_assets["right"], **inp)
+    ref = z["ev_loss_p0"]
+    got = np.asarray(ev["loss"])
+    assert len(got) == iters and len(imgs) == 0
+    assert np.all(np.abs(got[:2] - ref[:2]) <= 1e-4 * np.abs(ref[:2])), (got, ref)
+    assert np.all(np.abs(got - ref) <= 1e-1 * np.abs(ref)), (got, ref)
+    for k in ev:
+        if k.startswith("loss_") and f"ev_{k}_p0" in z.files:
+            r = z[f"ev_{k}_p0"][0]
+            assert abs(ev[k][0] - r) <= 1e-4 * max(abs(r), 1e-7) + 1e-9, (k, ev[k][0], r)
+    sd = model.state_dict()
+    for k in PARAMS + ("verts_object_og", "ref_mask_object", "keep_mask_hand", "camintr_rois_object", "faces_hand",
+                       "int_scales_object", "camintr"):
+        assert k in sd, k
+    assert model.get_verts_object()[0].shape == (batch["T"], batch["obj_verts_can"].shape[0], 3)
+    assert model.get_verts_hand()[0].shape == (batch["T"], 778, 3)
+
+
+def test_homan_module_with_torch_adam_loop(mano_assets):
+    """The reference's own loop shape: forward -> weighted sum -> backward -> torch.optim.Adam.step()."""
+    from homan_b200.homan import HOMan
+    from homan_b200.jointopt import optimize_hand_object  # noqa: F401
+    z, batch, lw, iters = load("ref_small_step2", mano_assets["right"])
+    inp = reference_inputs(batch, 0, mano_assets["right"])
+    cat = lambda seq, key: torch.cat([p[key] for p in seq])  # noqa: E731
+    pp, op = inp["person_parameters"], inp["object_parameters"]
+    model = HOMan(
+        hand_sides=["right"], translations_object=cat(op, "translations"), rotations_object=cat(op, "rotations"),
+        verts_object_og=torch.from_numpy(inp["objvertices"]), faces_object=torch.from_numpy(inp["objfaces"]),
+        target_masks_object=cat(op, "target_masks"), target_masks_hand=cat(pp, "target_masks"),
+        verts_hand_og=cat(pp, "verts"), ref_verts2d_hand=cat(pp, "verts2d"), mano_trans=cat(pp, "mano_trans"),
+        mano_rot=cat(pp, "mano_rot"), mano_pca_pose=cat(pp, "mano_pca_pose"), mano_betas=cat(pp, "mano_betas"),
+        translations_hand=cat(pp, "translations"), rotations_hand=cat(pp, "rotations"), faces_hand=pp[0]["faces"],
+        masks_object=torch.zeros(1, 8, 8), masks_hand=cat(pp, "masks"), cams_hand=cat(pp, "cams"),
+        camintr_rois_object=torch.cat([o["K_roi"][:, 0] for o in op]), camintr_rois_hand=cat(pp, "K_roi"),
+        camintr=inp["camintr"], class_name="default", int_scale_init=1, mano_asset=mano_assets["right"])
+    named = dict(model.named_parameters())
+    rigid = [v for k, v in named.items() if "mano" not in k and "rotation" not in k]
+    rots = [v for k, v in named.items() if "rotation" in k and "mano" not in k]
+    opt = torch.optim.Adam([{"params": rigid, "lr": 1e-2}, {"params": [model.mano_pca_pose, model.mano_betas], "lr": 1e-1},
+                            {"params": rots, "lr": 1e-1}])
+    totals = []
+    for _ in range(2):
+        opt.zero_grad()
+        loss_dict, metric_dict = model(loss_weights=lw)
+        loss = sum(loss_dict[k] * lw[k.replace("loss", "lw")] for k in loss_dict)
+        totals.append(loss.item())
+        loss.backward()
+        opt.step()
+    ref = z["ev_loss_p0"]
+    assert abs(totals[0] - ref[0]) <= 1e-4 * abs(ref[0]) and abs(totals[1] - ref[1]) <= 1e-3 * abs(ref[1]), (totals, ref[:2])
+    g = model.rotations_object.grad
+    assert g is not None and torch.isfinite(g).all()
+    with pytest.raises(Exception):
+        l2, _ = model(loss_weights=lw)
+        sum(l2.values()).backward()   # un-weighted combination: refused, the kernels already applied lw
+
+
+def test_shims_match_oracle(mano_assets):
+    from homan_b200 import synth
+    from homan_b200.shims import mano_layer, neural_renderer
+    from oracle import mano_layer as o_mano, nmr
+    clip = synth.make_clip(2, "ellipsoid80", seed=5, mano_asset=mano_assets["right"])
+    v, f, K = clip["gt"]["verts_obj"], clip["obj_faces"], clip["K_roi_obj"]
+    ro = nmr.Renderer(image_size=256, K=torch.from_numpy(K), R=torch.eye(3)[None], t=torch.zeros(1, 3), orig_size=1)
+    ref = ro(torch.from_numpy(v), torch.from_numpy(f)[None].repeat(2, 1, 1), mode="silhouettes")
+    rg = neural_renderer.Renderer(image_size=256, K=torch.from_numpy(K).cuda(), R=torch.eye(3)[None].cuda(),
+                                  t=torch.zeros(1, 3).cuda(), orig_size=1)
+    got = rg(torch.from_numpy(v).cuda(), torch.from_numpy(f.astype(np.int32)).cuda()[None].repeat(2, 1, 1), mode="silhouettes")
+    assert int((got.cpu() != ref).sum()) <= 4   # one-ulp projection differences may move a boundary sub-pixel
+    # MANO layer
+    rng = np.random.default_rng(0)
+    B = 3
+    betas, rot, pose = (torch.from_numpy(rng.normal(size=s).astype(np.float32) * 0.3) for s in ((B, 10), (B, 3), (B, 45)))
+    lo = o_mano.load(mano_assets["right"], num_pca_comps=16, use_pca=False, flat_hand_mean=True)
+    lg = mano_layer.load(mano_assets["right"], num_pca_comps=16, use_pca=False, flat_hand_mean=True)
+    vo, jo, *_ = lo(betas=betas, global_orient=rot, hand_pose=pose, transl=torch.zeros(B, 3))
+    pg = pose.cuda().requires_grad_()
+    vg, jg, *_ = lg(betas=betas.cuda(), global_orient=rot.cuda(), hand_pose=pg, transl=torch.zeros(B, 3).cuda())
+    assert (vg.detach().cpu() - vo).abs().max() < 1e-6 and (jg.cpu() - jo).abs().max() < 1e-6
+    po = pose.clone().requires_grad_()
+    vo2, *_ = lo(betas=betas, global_orient=rot, hand_pose=po, transl=torch.zeros(B, 3))
+    w = torch.from_numpy(rng.normal(size=(B, 778, 3)).astype(np.float32))
+    (vo2 * w).sum().backward()
+    (vg * w.cuda()).sum().backward()
+    assert (pg.grad.cpu() - po.grad).abs().max() <= 1e-4 * po.grad.abs().max()
+    assert lg.hand_components.shape == (16, 45) and lg.hand_mean.shape == (45,)
