@@ -183,12 +183,12 @@ __device__ __forceinline__ void append_faces(const FaceBox *__restrict__ boxes, 
 
 // Fills the list with the next batch of faces touching the tile (scanning from *base). Block-uniform.
 __device__ __forceinline__ int next_batch(const FaceBox *__restrict__ boxes, int &base, int F, int tx0, int ty0,
-                                          int *list, int *cnt, int *next) {
+                                          int *list, int *cnt, int *next, int cap = LISTCAP) {
     __syncthreads();
     if (threadIdx.x == 0) { *cnt = 0; *next = 0; }
     __syncthreads();
     int n = 0;
-    while (base < F && n <= LISTCAP - NTHREADS) {
+    while (base < F && n <= cap - NTHREADS) {
         append_faces(boxes, base, F, tx0, ty0, list, cnt);
         base += NTHREADS;
         __syncthreads();
@@ -206,6 +206,7 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     __shared__ int list[LISTCAP];
     __shared__ int cnt, next;
     __shared__ uint32_t roww[TILE][2];
+    __shared__ unsigned short pixq[NWARPS][64];
     const int b = blockIdx.y;
     const int tiles_x = is / TILE;
     const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
@@ -259,31 +260,59 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             const unsigned zmin_bits = zmin > 0.f ? __float_as_uint(zmin * (1.f - 1e-5f)) : 0u;
             const int n_px = w * h;
             const float inv_w = 1.f / (float)w;
-            for (int i = lane; i < n_px; i += 32) {
-                const int row = __float2int_rz(((float)i + 0.5f) * inv_w);
-                const int xi = X0 + (i - row * w), yi = Y0 + row;
-                // (2i + 1 - is) / is: for a power-of-two raster the division is an exact scaling
-                const float yp = pow2 ? (float)(2 * yi + 1 - is) * inv_is : (float)(2 * yi + 1 - is) / (float)is;
-                const float xp = pow2 ? (float)(2 * xi + 1 - is) * inv_is : (float)(2 * xi + 1 - is) / (float)is;
-                if ((yp - f1) * e0x < (xp - f0) * e0y) continue;
-                if ((yp - f4) * e1x < (xp - f3) * e1y) continue;
-                if ((yp - f7) * e2x < (xp - f6) * e2y) continue;
-                unsigned long long *kp = &keys[(yi - ty0) * TILE + (xi - tx0)];
-                const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
-                if (zmin_bits > (unsigned)(cur >> 32)) continue;
-                float w0 = inv[0] * xi + inv[1] * yi + inv[2];
-                float w1 = inv[3] * xi + inv[4] * yi + inv[5];
-                float w2 = inv[6] * xi + inv[7] * yi + inv[8];
-                w0 = fminf(fmaxf(w0, 0.f), 1.f);
-                w1 = fminf(fmaxf(w1, 0.f), 1.f);
-                w2 = fminf(fmaxf(w2, 0.f), 1.f);
-                const float ws = w0 + w1 + w2;
-                w0 /= ws; w1 /= ws; w2 /= ws;
-                const float zp = 1.f / (w0 / f2 + w1 / f5 + w2 / f8);
-                if (zp <= near_ || far_ <= zp) continue;
-                if (!(zp == zp)) continue;
-                const unsigned long long key = ((unsigned long long)__float_as_uint(zp) << 32) | (unsigned)fn;
-                if (key < cur) atomicMin(kp, key);
+            // Inside pixels are compacted into a per-warp queue so that the depth maths (7 IEEE divisions) runs
+            // on full warps: slivers put only a few of the 32 candidate pixels of an iteration inside.
+            unsigned short *pq = pixq[threadIdx.x >> 5];
+            int qn = 0;
+            for (int i0 = 0; i0 < n_px || qn > 0; i0 += 32) {
+                bool in = false;
+                unsigned packed = 0;
+                const int i = i0 + lane;
+                if (i < n_px) {
+                    const int row = __float2int_rz(((float)i + 0.5f) * inv_w);
+                    const int xi = X0 + (i - row * w), yi = Y0 + row;
+                    // (2i + 1 - is) / is: for a power-of-two raster the division is an exact scaling
+                    const float yp = pow2 ? (float)(2 * yi + 1 - is) * inv_is : (float)(2 * yi + 1 - is) / (float)is;
+                    const float xp = pow2 ? (float)(2 * xi + 1 - is) * inv_is : (float)(2 * xi + 1 - is) / (float)is;
+                    in = !((yp - f1) * e0x < (xp - f0) * e0y) && !((yp - f4) * e1x < (xp - f3) * e1y) &&
+                         !((yp - f7) * e2x < (xp - f6) * e2y);
+                    packed = (unsigned)(xi - tx0) | ((unsigned)(yi - ty0) << 6);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, in);
+                if (in) pq[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)packed;
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32 || (i0 + 32 >= n_px && qn > 0)) {
+                    const int take = min(qn, 32);
+                    if (lane < take) {
+                        const unsigned e = pq[lane];
+                        const int xl = e & 63u, yl = e >> 6;
+                        const int xi = tx0 + xl, yi = ty0 + yl;
+                        unsigned long long *kp = &keys[yl * TILE + xl];
+                        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
+                        if (!(zmin_bits > (unsigned)(cur >> 32))) {
+                            float w0 = inv[0] * xi + inv[1] * yi + inv[2];
+                            float w1 = inv[3] * xi + inv[4] * yi + inv[5];
+                            float w2 = inv[6] * xi + inv[7] * yi + inv[8];
+                            w0 = fminf(fmaxf(w0, 0.f), 1.f);
+                            w1 = fminf(fmaxf(w1, 0.f), 1.f);
+                            w2 = fminf(fmaxf(w2, 0.f), 1.f);
+                            const float ws = w0 + w1 + w2;
+                            w0 /= ws; w1 /= ws; w2 /= ws;
+                            const float zp = 1.f / (w0 / f2 + w1 / f5 + w2 / f8);
+                            if (zp > near_ && zp < far_) {  // also rejects NaN
+                                const unsigned long long key = ((unsigned long long)__float_as_uint(zp) << 32) | (unsigned)fn;
+                                if (key < cur) atomicMin(kp, key);
+                            }
+                        }
+                    }
+                    const int rem = qn - take;
+                    const unsigned short carry = (lane < rem) ? pq[32 + lane] : (unsigned short)0;
+                    __syncwarp();
+                    if (lane < rem) pq[lane] = carry;
+                    qn = rem;
+                    __syncwarp();
+                }
             }
         }
     }
@@ -540,11 +569,28 @@ __device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, 
     a1 = has1 ? -G * h1 : 0.f;
 }
 
-constexpr int WQCAP = 128;  // per-warp queue of (crossing, run) items
+constexpr int WQCAP = 96;   // per-warp queue of (crossing, run) items
+constexpr int BWD_LISTCAP = 512;
 struct WarpQueue {
-    float x[WQCAP], c0[WQCAP], c1[WQCAP], G[WQCAP];
-    unsigned se[WQCAP], meta[WQCAP];  // s | e << 16 ; owner lane | has0 << 5 | has1 << 6
+    float x[WQCAP], G[WQCAP];
+    unsigned se[WQCAP], meta[WQCAP];  // s | e << 16 ; owner lane | d0 << 5
 };
+
+// Parameters of the 32 tasks of a warp, readable by any lane (the crossings of a task are evaluated by
+// whichever lanes the load-balanced search hands them to).
+struct TaskTable {
+    float p0d0[32], p0d1[32], p1d0[32], p2d0[32], p2d1[32], slope[32], slope02[32], slope21[32], ka[32];
+    int packed[32], fn[32], incl[32];
+};
+
+__device__ __forceinline__ void eval_queued(const TaskTable &tt, float x, float G, unsigned se, unsigned meta,
+                                            float inv_is2, float eps, float &a0, float &a1) {
+    const int o = meta & 31u;
+    const float fd0 = (float)(meta >> 5);
+    const float p0d0 = tt.p0d0[o], p1d0 = tt.p1d0[o], ka = tt.ka[o];
+    eval_item(x, ka / (p1d0 - fd0), ka / (fd0 - p0d0), G, (int)(se & 0xffffu), (int)(se >> 16), p1d0 != fd0,
+              p0d0 != fd0, inv_is2, eps, a0, a1);
+}
 
 // Per-task accumulators live in shared memory (float; atomics there are CAS loops, so contention must be
 // avoided): a drain pass evaluates 32 items, sums the results of the items that belong to the same task inside
@@ -553,7 +599,8 @@ __device__ __forceinline__ void acc_add(float *slot, float v) {
     if (v != 0.f) atomicAdd(slot, v);
 }
 
-__device__ __forceinline__ void drain_queue(WarpQueue &q, int n, float (*wacc)[2], float inv_is2, float eps) {
+__device__ __forceinline__ void drain_queue(WarpQueue &q, const TaskTable &tt, int n, float (*wacc)[2], float inv_is2,
+                                            float eps) {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     for (int base = 0; base < n; base += 32) {
@@ -561,9 +608,8 @@ __device__ __forceinline__ void drain_queue(WarpQueue &q, int n, float (*wacc)[2
         float a0 = 0.f, a1 = 0.f;
         unsigned key = 32u + (unsigned)lane;  // lanes without an item form singleton groups
         if (i < n) {
-            const unsigned se = q.se[i], meta = q.meta[i];
-            eval_item(q.x[i], q.c0[i], q.c1[i], q.G[i], (int)(se & 0xffffu), (int)(se >> 16), (meta >> 5) & 1u,
-                      (meta >> 6) & 1u, inv_is2, eps, a0, a1);
+            const unsigned meta = q.meta[i];
+            eval_queued(tt, q.x[i], q.G[i], q.se[i], meta, inv_is2, eps, a0, a1);
             key = meta & 31u;
         }
         unsigned peers = __match_any_sync(FULL, key);
@@ -586,13 +632,6 @@ __device__ __forceinline__ void drain_queue(WarpQueue &q, int n, float (*wacc)[2
     }
 }
 
-// Parameters of the 32 tasks of a warp, readable by any lane (the crossings of a task are evaluated by
-// whichever lanes the load-balanced search hands them to).
-struct TaskTable {
-    float p0d0[32], p0d1[32], p1d0[32], p2d0[32], p2d1[32], slope[32], slope02[32], slope21[32], ka[32];
-    int packed[32], fn[32], incl[32];
-};
-
 // One CTA per (image, 64x64 tile). The (face, edge, axis) tasks of the faces touching the tile are spread
 // over the warps, 32 per warp; each warp flattens the scan-line crossings of its 32 tasks across its lanes
 // (load-balanced search over the prefix sum of the task lengths, task parameters fetched by shuffle), and the
@@ -606,7 +645,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                   const uint2 *__restrict__ runs, const uint32_t *__restrict__ run_counts,
                   float *__restrict__ grad_ndc) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ int list[LISTCAP];
+    __shared__ int list[BWD_LISTCAP];
     __shared__ int cnt, next;
     __shared__ __align__(16) uint2 srun[4][TILE][RCAP];  // run lists: mn_row, mp_row, mn_col, mp_col
     __shared__ __align__(16) unsigned scount[4][TILE];
@@ -639,7 +678,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     int base = 0;
     bool staged = false;
     while (base < F) {
-        const int n = next_batch(boxes, base, F, tx0, ty0, list, &cnt, &next);
+        const int n = next_batch(boxes, base, F, tx0, ty0, list, &cnt, &next, BWD_LISTCAP);
         if (n == 0) continue;
         if (!staged) {
             // ---- stage the tile's face_index rows, coverage lines and run lists with TMA bulk copies
@@ -757,9 +796,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                         const int d1_in = __float2int_rz(o_dir > 0 ? floorf(x) : ceilf(x));
                         const int d1_out = d1_in + o_dir;
                         if (d1_in >= 0 && d1_in < is && d1_out >= 0 && d1_out < is && d1_in >= t1 && d1_in < t1 + TILE) {
-                            const bool has0 = o_p1d0 != fd0, has1 = o_p0d0 != fd0;
-                            const float c0 = o_ka / (o_p1d0 - fd0), c1 = o_ka / (fd0 - o_p0d0);
-                            const unsigned meta = (unsigned)o | (has0 ? 32u : 0u) | (has1 ? 64u : 0u);
+                            const unsigned meta = (unsigned)o | ((unsigned)d0 << 5);
                             const int fs0 = o_axis == 0 ? 1 : TILE, fs1 = o_axis == 0 ? TILE : 1;
                             // sweep 0: out-sweep (missing-coverage list, from the out pixel to the border) when this
                             // face owns the in pixel; sweep 1: in-sweep (from the in pixel to the opposite edge)
@@ -767,21 +804,22 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                             for (int sw = 0; sw < 2; ++sw) {
                                 int ls, ra, rc;
                                 if (sw == 0) {
-                                    if (fi[l0 * fs0 + (d1_in - t1) * fs1] != o_fn) continue;
+                                    if (cN == 0u || fi[l0 * fs0 + (d1_in - t1) * fs1] != o_fn) continue;
                                     const int lim = o_dir > 0 ? is - 1 : 0;
                                     ls = lN; ra = min(d1_out, lim); rc = max(d1_out, lim);
                                 } else {
+                                    const uint32_t *A = lines + (o_axis == 0 ? LW : 0) + l0 * W;
+                                    const bool alpha_out = (A[d1_out >> 5] >> (d1_out & 31)) & 1u;
+                                    ls = alpha_out ? lN : lP;
+                                    if ((alpha_out ? cN : cP) == 0u) continue;
                                     float c2;
                                     if ((fd0 - o_p0d0) * (fd0 - o_p2d0) < 0.f) c2 = o_s02 * (fd0 - o_p0d0) + o_p0d1;
                                     else c2 = o_s21 * (fd0 - o_p2d0) + o_p2d1;
                                     const int lim = __float2int_rz(o_dir > 0 ? ceilf(c2) : floorf(c2));
                                     ra = max(min(d1_in, lim), 0); rc = min(max(d1_in, lim), is - 1);
-                                    const uint32_t *A = lines + (o_axis == 0 ? LW : 0) + l0 * W;
-                                    const bool alpha_out = (A[d1_out >> 5] >> (d1_out & 31)) & 1u;
-                                    ls = alpha_out ? lN : lP;
                                 }
-                                const unsigned cs = scount[ls][l0];
-                                if (cs == 0u || ra > rc) continue;
+                                const unsigned cs = ls == lN ? cN : cP;
+                                if (ra > rc) continue;
                                 if (cs == RUN_OVERFLOW) {
                                     // more runs than the list holds: walk the bit line (global memory)
                                     const uint32_t *line = ((ls >> 1) ? m_col : m_row) +
@@ -796,14 +834,13 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                                     const uint2 run = srun[ls][l0][r];
                                     const int s = max(ra, (int)(run.x & 0xffffu)), e = min(rc, (int)(run.x >> 16));
                                     if (s > e) continue;
+                                    const unsigned se = (unsigned)s | ((unsigned)e << 16);
                                     const int pos = atomicAdd(&wqn[warp], 1);
                                     if (pos < WQCAP) {
-                                        q.x[pos] = x; q.c0[pos] = c0; q.c1[pos] = c1; q.G[pos] = __uint_as_float(run.y);
-                                        q.se[pos] = (unsigned)s | ((unsigned)e << 16);
-                                        q.meta[pos] = meta;
+                                        q.x[pos] = x; q.G[pos] = __uint_as_float(run.y); q.se[pos] = se; q.meta[pos] = meta;
                                     } else {  // queue full: evaluate in place
                                         float a0, a1;
-                                        eval_item(x, c0, c1, __uint_as_float(run.y), s, e, has0, has1, inv_is2, eps, a0, a1);
+                                        eval_queued(tt, x, __uint_as_float(run.y), se, meta, inv_is2, eps, a0, a1);
                                         acc_add(&wacc[warp][o][0], a0);
                                         acc_add(&wacc[warp][o][1], a1);
                                     }
@@ -815,7 +852,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 __syncwarp();
                 const int nq = min(wqn[warp], WQCAP);
                 if (nq > WQCAP - 48 || kb + 32 >= total) {
-                    drain_queue(q, nq, wacc[warp], inv_is2, eps);
+                    drain_queue(q, tt, nq, wacc[warp], inv_is2, eps);
                     __syncwarp();
                     if (lane == 0) wqn[warp] = 0;
                     __syncwarp();
