@@ -207,6 +207,7 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     __shared__ int cnt, next;
     __shared__ uint32_t roww[TILE][2];
     __shared__ unsigned short pixq[NWARPS][64];
+    __shared__ short spanx[NWARPS][64], spanpre[NWARPS][64];
     const int b = blockIdx.y;
     const int tiles_x = is / TILE;
     const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
@@ -258,10 +259,50 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             // nearest corner (minus rounding slack) is behind the current winner of a pixel cannot win it
             const float zmin = fminf(fminf(f2, f5), f8);
             const unsigned zmin_bits = zmin > 0.f ? __float_as_uint(zmin * (1.f - 1e-5f)) : 0u;
-            const int n_px = w * h;
-            const float inv_w = 1.f / (float)w;
+            // Candidate pixels: per row of the bbox, the conservative x-span of the triangle (each edge bounds x
+            // from one side), flattened over the lanes through a prefix sum of the span lengths - slivers and
+            // diagonal faces cost their area, not their bounding box. The exact test below decides coverage.
+            short *rowx = spanx[threadIdx.x >> 5], *rowpre = spanpre[threadIdx.x >> 5];
+            int n_px;
+            {
+                int len[2], xlo[2];
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    const int r = lane + 32 * half;
+                    len[half] = 0; xlo[half] = X0;
+                    if (r < h) {
+                        const int yi = Y0 + r;
+                        const float yp = pow2 ? (float)(2 * yi + 1 - is) * inv_is : (float)(2 * yi + 1 - is) / (float)is;
+                        float lo = -3.0e38f, hi = 3.0e38f;
+                        bool empty = false;
+                        const float c0 = (yp - f1) * e0x, c1 = (yp - f4) * e1x, c2 = (yp - f7) * e2x;
+                        if (e0y > 0.f) hi = fminf(hi, f0 + __fdividef(c0, e0y)); else if (e0y < 0.f) lo = fmaxf(lo, f0 + __fdividef(c0, e0y)); else empty |= c0 < -1e-6f;
+                        if (e1y > 0.f) hi = fminf(hi, f3 + __fdividef(c1, e1y)); else if (e1y < 0.f) lo = fmaxf(lo, f3 + __fdividef(c1, e1y)); else empty |= c1 < -1e-6f;
+                        if (e2y > 0.f) hi = fminf(hi, f6 + __fdividef(c2, e2y)); else if (e2y < 0.f) lo = fmaxf(lo, f6 + __fdividef(c2, e2y)); else empty |= c2 < -1e-6f;
+                        // NaN bounds (degenerate edges) fall back to the whole row
+                        int a = X0, c = X1;
+                        const float plo = to_pix(lo, is), phi = to_pix(hi, is);
+                        if (plo == plo) a = max(X0, __float2int_rz(fminf(fmaxf(ceilf(plo) - 1.f, -1.f), 70000.f)));
+                        if (phi == phi) c = min(X1, __float2int_rz(fminf(fmaxf(floorf(phi) + 1.f, -1.f), 70000.f)));
+                        xlo[half] = a;
+                        len[half] = empty ? 0 : max(c - a + 1, 0);
+                    }
+                }
+                int inc0 = len[0], inc1 = len[1];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v0 = __shfl_up_sync(0xffffffffu, inc0, o), v1 = __shfl_up_sync(0xffffffffu, inc1, o);
+                    if (lane >= o) { inc0 += v0; inc1 += v1; }
+                }
+                const int tot0 = __shfl_sync(0xffffffffu, inc0, 31), tot1 = __shfl_sync(0xffffffffu, inc1, 31);
+                __syncwarp();
+                rowx[lane] = (short)xlo[0]; rowpre[lane] = (short)(inc0 - len[0]);
+                rowx[lane + 32] = (short)xlo[1]; rowpre[lane + 32] = (short)(tot0 + inc1 - len[1]);
+                n_px = tot0 + tot1;
+                __syncwarp();
+            }
             // Inside pixels are compacted into a per-warp queue so that the depth maths (7 IEEE divisions) runs
-            // on full warps: slivers put only a few of the 32 candidate pixels of an iteration inside.
+            // on full warps.
             unsigned short *pq = pixq[threadIdx.x >> 5];
             int qn = 0;
             for (int i0 = 0; i0 < n_px || qn > 0; i0 += 32) {
@@ -269,8 +310,11 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 unsigned packed = 0;
                 const int i = i0 + lane;
                 if (i < n_px) {
-                    const int row = __float2int_rz(((float)i + 0.5f) * inv_w);
-                    const int xi = X0 + (i - row * w), yi = Y0 + row;
+                    int row = 0;
+#pragma unroll
+                    for (int sft = 32; sft > 0; sft >>= 1)
+                        if (row + sft < h && rowpre[row + sft] <= i) row += sft;
+                    const int xi = rowx[row] + (i - rowpre[row]), yi = Y0 + row;
                     // (2i + 1 - is) / is: for a power-of-two raster the division is an exact scaling
                     const float yp = pow2 ? (float)(2 * yi + 1 - is) * inv_is : (float)(2 * yi + 1 - is) / (float)is;
                     const float xp = pow2 ? (float)(2 * xi + 1 - is) * inv_is : (float)(2 * xi + 1 - is) / (float)is;
