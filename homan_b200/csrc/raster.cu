@@ -617,20 +617,21 @@ constexpr int WQCAP = 96;   // per-warp queue of (crossing, run) items
 constexpr int BWD_LISTCAP = 512;
 struct WarpQueue {
     float x[WQCAP], G[WQCAP];
-    unsigned se[WQCAP], meta[WQCAP];  // s | e << 16 ; owner lane | d0 << 5
+    unsigned se[WQCAP], meta[WQCAP];  // s | e << 16 ; owner task (0..255) | d0 << 8
 };
 
-// Parameters of the 32 tasks of a warp, readable by any lane (the crossings of a task are evaluated by
-// whichever lanes the load-balanced search hands them to).
+// Parameters of the (up to) 256 tasks of a chunk, one per thread, readable by every thread of the CTA (the
+// crossings of a task are evaluated by whichever lanes the load-balanced search hands them to).
 struct TaskTable {
-    float p0d0[32], p0d1[32], p1d0[32], p2d0[32], p2d1[32], slope[32], slope02[32], slope21[32], ka[32];
-    int packed[32], fn[32], incl[32];
+    float p0d0[NTHREADS], p0d1[NTHREADS], p1d0[NTHREADS], p2d0[NTHREADS], p2d1[NTHREADS], slope[NTHREADS],
+        slope02[NTHREADS], slope21[NTHREADS], ka[NTHREADS];
+    int packed[NTHREADS], fn[NTHREADS], incl[NTHREADS];
 };
 
 __device__ __forceinline__ void eval_queued(const TaskTable &tt, float x, float G, unsigned se, unsigned meta,
                                             float inv_is2, float eps, float &a0, float &a1) {
-    const int o = meta & 31u;
-    const float fd0 = (float)(meta >> 5);
+    const int o = meta & 255u;
+    const float fd0 = (float)(meta >> 8);
     const float p0d0 = tt.p0d0[o], p1d0 = tt.p1d0[o], ka = tt.ka[o];
     eval_item(x, ka / (p1d0 - fd0), ka / (fd0 - p0d0), G, (int)(se & 0xffffu), (int)(se >> 16), p1d0 != fd0,
               p0d0 != fd0, inv_is2, eps, a0, a1);
@@ -650,16 +651,15 @@ __device__ __forceinline__ void drain_queue(WarpQueue &q, const TaskTable &tt, i
     for (int base = 0; base < n; base += 32) {
         const int i = base + lane;
         float a0 = 0.f, a1 = 0.f;
-        unsigned key = 32u + (unsigned)lane;  // lanes without an item form singleton groups
+        unsigned key = 256u + (unsigned)lane;  // lanes without an item form singleton groups
         if (i < n) {
             const unsigned meta = q.meta[i];
             eval_queued(tt, q.x[i], q.G[i], q.se[i], meta, inv_is2, eps, a0, a1);
-            key = meta & 31u;
+            key = meta & 255u;
         }
         unsigned peers = __match_any_sync(FULL, key);
         const bool leader = (__ffs(peers) - 1) == lane;
-        int cnt = __popc(peers);
-        int mx = cnt;
+        int mx = __popc(peers);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
         float s0 = 0.f, s1 = 0.f;
@@ -668,17 +668,17 @@ __device__ __forceinline__ void drain_queue(WarpQueue &q, const TaskTable &tt, i
             const float v0 = __shfl_sync(FULL, a0, src), v1 = __shfl_sync(FULL, a1, src);
             if (peers) { s0 += v0; s1 += v1; peers &= peers - 1; }
         }
-        if (leader && key < 32u) {
-            if (s0 != 0.f) wacc[key][0] += s0;
-            if (s1 != 0.f) wacc[key][1] += s1;
+        if (leader && key < 256u) {
+            acc_add(&wacc[key][0], s0);
+            acc_add(&wacc[key][1], s1);
         }
         __syncwarp();
     }
 }
 
-// One CTA per (image, 64x64 tile). The (face, edge, axis) tasks of the faces touching the tile are spread
-// over the warps, 32 per warp; each warp flattens the scan-line crossings of its 32 tasks across its lanes
-// (load-balanced search over the prefix sum of the task lengths, task parameters fetched by shuffle), and the
+// One CTA per (image, 64x64 tile). The (face, edge, axis) tasks of the faces touching the tile are taken 256
+// at a time, one per thread; their scan-line crossings are flattened over ALL lanes of the CTA (load-balanced
+// search over the CTA-wide prefix sum of the task lengths, task parameters read from a shared table), and the
 // (crossing, run) pairs that have something to sweep go through a per-warp queue so that the expensive part
 // runs on dense warps.
 __global__ void __launch_bounds__(NTHREADS)
@@ -693,16 +693,16 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     __shared__ int cnt, next;
     __shared__ __align__(16) uint2 srun[4][TILE][RCAP];  // run lists: mn_row, mp_row, mn_col, mp_col
     __shared__ __align__(16) unsigned scount[4][TILE];
-    __shared__ int wqn[NWARPS];
-    __shared__ float wacc[NWARPS][32][2];
+    __shared__ int wqn[NWARPS], wsum[NWARPS];
+    __shared__ float wacc[NTHREADS][2];
     __shared__ __align__(8) uint64_t bar;
     const int W = is / 32;
     const int LW = TILE * W;  // words per coverage block: a_row, a_col
-    // dynamic shared memory: face_index tile | coverage lines | per-warp queues | per-warp task tables
+    // dynamic shared memory: face_index tile | coverage lines | per-warp queues | task table of the chunk
     int *fi = reinterpret_cast<int *>(smem_raw);
     uint32_t *lines = reinterpret_cast<uint32_t *>(smem_raw + TILE * TILE * sizeof(int));
     WarpQueue *wq = reinterpret_cast<WarpQueue *>(smem_raw + TILE * TILE * sizeof(int) + 2 * LW * sizeof(uint32_t));
-    TaskTable *tables = reinterpret_cast<TaskTable *>(wq + NWARPS);
+    TaskTable &tt = *reinterpret_cast<TaskTable *>(wq + NWARPS);
     const int b = blockIdx.y;
     const int tiles_x = is / TILE;
     const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
@@ -717,7 +717,6 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     const float inv_is2 = 2.f / (float)is;
     const long plane = (long)is * W;
     WarpQueue &q = wq[warp];
-    TaskTable &tt = tables[warp];
 
     int base = 0;
     bool staged = false;
@@ -756,73 +755,83 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             staged = true;
         }
         const int ntasks = 6 * n;
-        for (int g0 = warp * 32; g0 < ntasks; g0 += NWARPS * 32) {
-            // ---- one (face, edge, axis) task per lane
-            const int task = g0 + lane;
-            float p0d0 = 0.f, p0d1 = 0.f, p1d0 = 0.f, p2d0 = 0.f, p2d1 = 0.f, slope = 0.f, slope02 = 0.f, slope21 = 0.f,
-                  ka = 0.f;
-            int fn = -1, vid0 = 0, vid1 = 0, axis = 0, dir = 1, lo = 0, len = 0;
-            if (task < ntasks) {
-                const int e = (task % 6) >> 1;
-                axis = task & 1;
-                const FaceRec *rp = recs + list[task / 6];
-                const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rp));
-                const float4 q1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
-                const float4 q2 = __ldg(reinterpret_cast<const float4 *>(rp) + 2);
-                const int4 q3 = __ldg(reinterpret_cast<const int4 *>(rp) + 3);
-                fn = __float_as_int(q2.y);
-                const int v0 = __float_as_int(q2.z), v1 = __float_as_int(q2.w), v2 = q3.x;
-                // pixel-space corners along (d0, d1) = (x, y) for axis 0, (y, x) for axis 1
-                const float ax = to_pix(q0.x, is), ay = to_pix(q0.y, is), bx = to_pix(q0.w, is), by = to_pix(q1.x, is),
-                            cx = to_pix(q1.z, is), cy = to_pix(q1.w, is);
-                const float a0 = axis ? ay : ax, a1 = axis ? ax : ay, b0 = axis ? by : bx, b1 = axis ? bx : by,
-                            c0 = axis ? cy : cx, c1 = axis ? cx : cy;
-                // vertex order of this edge: p0 = corner e, p1 = corner e+1, p2 = corner e+2
-                p0d0 = e == 0 ? a0 : e == 1 ? b0 : c0; p0d1 = e == 0 ? a1 : e == 1 ? b1 : c1;
-                p1d0 = e == 0 ? b0 : e == 1 ? c0 : a0;
-                const float p1d1 = e == 0 ? b1 : e == 1 ? c1 : a1;
-                p2d0 = e == 0 ? c0 : e == 1 ? a0 : b0; p2d1 = e == 0 ? c1 : e == 1 ? a1 : b1;
-                vid0 = e == 0 ? v0 : e == 1 ? v1 : v2; vid1 = e == 0 ? v1 : e == 1 ? v2 : v0;
-                if (axis == 0) dir = (p0d0 < p1d0) ? -1 : 1;
-                else dir = (p0d0 < p1d0) ? 1 : -1;
-                const int d0_from = __float2int_rz(fmaxf(ceilf(fminf(p0d0, p1d0)), 0.f));
-                const int d0_to = __float2int_rz(fminf(fmaxf(p0d0, p1d0), (float)(is - 1)));
-                const int t0 = axis == 0 ? tx0 : ty0;
-                lo = max(d0_from, t0);
-                len = max(min(d0_to, t0 + TILE - 1) - lo + 1, 0);
-                ka = p1d0 - p0d0;
-                slope = (p1d1 - p0d1) / ka;
-                slope02 = (p2d1 - p0d1) / (p2d0 - p0d0);
-                slope21 = (p1d1 - p2d1) / (p1d0 - p2d0);
-            }
-            // inclusive prefix sum of the task lengths over the warp
-            int incl = len;
+        for (int chunk = 0; chunk < ntasks; chunk += NTHREADS) {
+            // ---- one (face, edge, axis) task per thread; its parameters go to the CTA-wide table
+            const int task = chunk + threadIdx.x;
+            int vid0 = 0, vid1 = 0, axis = 0, len = 0;
+            {
+                float p0d0 = 0.f, p0d1 = 0.f, p1d0 = 0.f, p2d0 = 0.f, p2d1 = 0.f, slope = 0.f, slope02 = 0.f,
+                      slope21 = 0.f, ka = 0.f;
+                int fn = -1, dir = 1, lo = 0;
+                if (task < ntasks) {
+                    const int e = (task % 6) >> 1;
+                    axis = task & 1;
+                    const FaceRec *rp = recs + list[task / 6];
+                    const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rp));
+                    const float4 q1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
+                    const float4 q2 = __ldg(reinterpret_cast<const float4 *>(rp) + 2);
+                    const int4 q3 = __ldg(reinterpret_cast<const int4 *>(rp) + 3);
+                    fn = __float_as_int(q2.y);
+                    const int v0 = __float_as_int(q2.z), v1 = __float_as_int(q2.w), v2 = q3.x;
+                    // pixel-space corners along (d0, d1) = (x, y) for axis 0, (y, x) for axis 1
+                    const float ax = to_pix(q0.x, is), ay = to_pix(q0.y, is), bx = to_pix(q0.w, is), by = to_pix(q1.x, is),
+                                cx = to_pix(q1.z, is), cy = to_pix(q1.w, is);
+                    const float a0 = axis ? ay : ax, a1 = axis ? ax : ay, b0 = axis ? by : bx, b1 = axis ? bx : by,
+                                c0 = axis ? cy : cx, c1 = axis ? cx : cy;
+                    // vertex order of this edge: p0 = corner e, p1 = corner e+1, p2 = corner e+2
+                    p0d0 = e == 0 ? a0 : e == 1 ? b0 : c0; p0d1 = e == 0 ? a1 : e == 1 ? b1 : c1;
+                    p1d0 = e == 0 ? b0 : e == 1 ? c0 : a0;
+                    const float p1d1 = e == 0 ? b1 : e == 1 ? c1 : a1;
+                    p2d0 = e == 0 ? c0 : e == 1 ? a0 : b0; p2d1 = e == 0 ? c1 : e == 1 ? a1 : b1;
+                    vid0 = e == 0 ? v0 : e == 1 ? v1 : v2; vid1 = e == 0 ? v1 : e == 1 ? v2 : v0;
+                    if (axis == 0) dir = (p0d0 < p1d0) ? -1 : 1;
+                    else dir = (p0d0 < p1d0) ? 1 : -1;
+                    const int d0_from = __float2int_rz(fmaxf(ceilf(fminf(p0d0, p1d0)), 0.f));
+                    const int d0_to = __float2int_rz(fminf(fmaxf(p0d0, p1d0), (float)(is - 1)));
+                    const int t0 = axis == 0 ? tx0 : ty0;
+                    lo = max(d0_from, t0);
+                    len = max(min(d0_to, t0 + TILE - 1) - lo + 1, 0);
+                    ka = p1d0 - p0d0;
+                    slope = (p1d1 - p0d1) / ka;
+                    slope02 = (p2d1 - p0d1) / (p2d0 - p0d0);
+                    slope21 = (p1d1 - p2d1) / (p1d0 - p2d0);
+                }
+                // inclusive prefix sum of the task lengths over the CTA (warp scans + warp totals)
+                int incl = len;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += v;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                __syncthreads();  // previous chunk fully consumed (table, accumulators, wsum)
+                if (lane == 31) wsum[warp] = incl;
+                const int t = threadIdx.x;
+                tt.p0d0[t] = p0d0; tt.p0d1[t] = p0d1; tt.p1d0[t] = p1d0; tt.p2d0[t] = p2d0; tt.p2d1[t] = p2d1;
+                tt.slope[t] = slope; tt.slope02[t] = slope02; tt.slope21[t] = slope21; tt.ka[t] = ka;
+                tt.packed[t] = (lo & 0xffff) | (axis << 16) | ((dir > 0 ? 1 : 0) << 17);
+                tt.fn[t] = fn;
+                wacc[t][0] = 0.f;
+                wacc[t][1] = 0.f;
+                if (lane == 0) wqn[warp] = 0;
+                __syncthreads();
+                int offset = 0;
+#pragma unroll
+                for (int w = 0; w < NWARPS; ++w) offset += (w < warp) ? wsum[w] : 0;
+                tt.incl[t] = incl + offset;
+                __syncthreads();
             }
-            const int total = __shfl_sync(FULL, incl, 31);
-            if (total == 0) continue;
-            const int packed = (lo & 0xffff) | (axis << 16) | ((dir > 0 ? 1 : 0) << 17);
-            __syncwarp();
-            tt.p0d0[lane] = p0d0; tt.p0d1[lane] = p0d1; tt.p1d0[lane] = p1d0; tt.p2d0[lane] = p2d0; tt.p2d1[lane] = p2d1;
-            tt.slope[lane] = slope; tt.slope02[lane] = slope02; tt.slope21[lane] = slope21; tt.ka[lane] = ka;
-            tt.packed[lane] = packed; tt.fn[lane] = fn; tt.incl[lane] = incl;
-            wacc[warp][lane][0] = 0.f;
-            wacc[warp][lane][1] = 0.f;
-            if (lane == 0) wqn[warp] = 0;
-            __syncwarp();
+            const int total = tt.incl[NTHREADS - 1];
 
-            for (int kb = 0; kb < total; kb += 32) {
+            // ---- crossings of the whole chunk, 32 per warp per round, dealt round-robin to the warps
+            for (int kb = warp * 32; kb < total; kb += NTHREADS) {
                 const int kk = kb + lane;
                 const bool active = kk < total;
                 // owner task of crossing kk: number of tasks whose inclusive prefix is <= kk
                 int j = 0;
 #pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1)
+                for (int sft = NTHREADS / 2; sft > 0; sft >>= 1)
                     if (tt.incl[j + sft - 1] <= kk) j += sft;
-                const int o = active ? j : 31;
+                const int o = active ? j : NTHREADS - 1;
                 const int o_excl = o > 0 ? tt.incl[o - 1] : 0, o_pack = tt.packed[o], o_fn = tt.fn[o];
                 const float o_p0d0 = tt.p0d0[o], o_p0d1 = tt.p0d1[o], o_p1d0 = tt.p1d0[o], o_p2d0 = tt.p2d0[o];
                 const float o_p2d1 = tt.p2d1[o], o_slope = tt.slope[o], o_s02 = tt.slope02[o], o_s21 = tt.slope21[o];
@@ -840,7 +849,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                         const int d1_in = __float2int_rz(o_dir > 0 ? floorf(x) : ceilf(x));
                         const int d1_out = d1_in + o_dir;
                         if (d1_in >= 0 && d1_in < is && d1_out >= 0 && d1_out < is && d1_in >= t1 && d1_in < t1 + TILE) {
-                            const unsigned meta = (unsigned)o | ((unsigned)d0 << 5);
+                            const unsigned meta = (unsigned)o | ((unsigned)d0 << 8);
                             const int fs0 = o_axis == 0 ? 1 : TILE, fs1 = o_axis == 0 ? TILE : 1;
                             // sweep 0: out-sweep (missing-coverage list, from the out pixel to the border) when this
                             // face owns the in pixel; sweep 1: in-sweep (from the in pixel to the opposite edge)
@@ -870,8 +879,8 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                                                            ((long)b * 2 * is + (ls >> 1 ? tx0 : ty0) + l0) * W + (ls & 1) * plane;
                                     float a0 = 0.f, a1 = 0.f;
                                     sweep(line, FULL, ra, rc, o_axis, d0, x, o_ka, o_p0d0, o_p1d0, ctx, a0, a1);
-                                    acc_add(&wacc[warp][o][0], a0);
-                                    acc_add(&wacc[warp][o][1], a1);
+                                    acc_add(&wacc[o][0], a0);
+                                    acc_add(&wacc[o][1], a1);
                                     continue;
                                 }
                                 for (unsigned r = 0; r < cs; ++r) {
@@ -885,8 +894,8 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                                     } else {  // queue full: evaluate in place
                                         float a0, a1;
                                         eval_queued(tt, x, __uint_as_float(run.y), se, meta, inv_is2, eps, a0, a1);
-                                        acc_add(&wacc[warp][o][0], a0);
-                                        acc_add(&wacc[warp][o][1], a1);
+                                        acc_add(&wacc[o][0], a0);
+                                        acc_add(&wacc[o][1], a1);
                                     }
                                 }
                             }
@@ -895,18 +904,18 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 }
                 __syncwarp();
                 const int nq = min(wqn[warp], WQCAP);
-                if (nq > WQCAP - 48 || kb + 32 >= total) {
-                    drain_queue(q, tt, nq, wacc[warp], inv_is2, eps);
+                if (nq > WQCAP - 48 || kb + NTHREADS >= total) {
+                    drain_queue(q, tt, nq, wacc, inv_is2, eps);
                     __syncwarp();
                     if (lane == 0) wqn[warp] = 0;
                     __syncwarp();
                 }
             }
+            __syncthreads();
             // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
-            const float acc0 = wacc[warp][lane][0], acc1 = wacc[warp][lane][1];
+            const float acc0 = wacc[threadIdx.x][0], acc1 = wacc[threadIdx.x][1];
             if (acc0 != 0.f) atomicAdd(grad_ndc + (long)vid0 * 3 + (1 - axis), acc0);
             if (acc1 != 0.f) atomicAdd(grad_ndc + (long)vid1 * 3 + (1 - axis), acc1);
-            __syncwarp();
         }
     }
 }
@@ -1053,7 +1062,7 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
     if (B == 0 || F == 0) return HM_OK;
     const size_t smem = (size_t)TILE * TILE * 4 + (size_t)2 * TILE * (is / 32) * 4 + NWARPS * sizeof(WarpQueue) +
-                        NWARPS * sizeof(TaskTable);
+                        sizeof(TaskTable);
     HM_UNSUPPORTED(is > 1024, "hm_raster_sil_bwd: raster size %d > 1024 is not supported", is);
     static size_t configured = 0;  // static + dynamic shared memory exceeds the 48 KB default: opt in once per size
     if (smem > configured) {
