@@ -409,7 +409,7 @@ grad_prep_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restric
                  const uint32_t *__restrict__ cov_col, int is, int aa, uint32_t *__restrict__ m_row,
                  uint32_t *__restrict__ m_col) {
     __shared__ float gs[TILE][TILE + 1];
-    __shared__ uint32_t a_row[TILE][2], a_col[TILE][2];
+    __shared__ uint32_t a_row[TILE][2], a_col[TILE][2], out_w[4][TILE][2];
     const int b = blockIdx.y;
     const int tiles_x = is / TILE;
     const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
@@ -441,10 +441,9 @@ grad_prep_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restric
             const float g = gs[yl >> sh][xl >> sh];
             const unsigned neg = __ballot_sync(0xffffffffu, g < 0.f), pos = __ballot_sync(0xffffffffu, g > 0.f);
             if (lane == 0) {
-                const long o = ((long)b * 2 * is + (ty0 + yl)) * W + (tx0 >> 5) + w;
                 const unsigned A = a_row[yl][w];
-                m_row[o] = neg & ~A;
-                m_row[o + plane] = pos & A;
+                out_w[0][yl][w] = neg & ~A;
+                out_w[1][yl][w] = pos & A;
             }
         }
         {   // column words: line = raster column, bit = y
@@ -452,11 +451,23 @@ grad_prep_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restric
             const float g = gs[yl >> sh][xl >> sh];
             const unsigned neg = __ballot_sync(0xffffffffu, g < 0.f), pos = __ballot_sync(0xffffffffu, g > 0.f);
             if (lane == 0) {
-                const long o = ((long)b * 2 * is + (tx0 + xl)) * W + (ty0 >> 5) + w;
                 const unsigned A = a_col[xl][w];
-                m_col[o] = neg & ~A;
-                m_col[o + plane] = pos & A;
+                out_w[2][xl][w] = neg & ~A;
+                out_w[3][xl][w] = pos & A;
             }
+        }
+    }
+    __syncthreads();
+    {   // one store per thread and plane
+        const int l = (threadIdx.x >> 1) & 63, w = threadIdx.x & 1;
+        if (threadIdx.x < 128) {
+            const long o = ((long)b * 2 * is + (ty0 + l)) * W + (tx0 >> 5) + w;
+            m_row[o] = out_w[0][l][w];
+            m_row[o + plane] = out_w[1][l][w];
+        } else {
+            const long o = ((long)b * 2 * is + (tx0 + l)) * W + (ty0 >> 5) + w;
+            m_col[o] = out_w[2][l][w];
+            m_col[o + plane] = out_w[3][l][w];
         }
     }
 }
@@ -567,7 +578,7 @@ __device__ __forceinline__ void sweep(const uint32_t *line, unsigned nz, int a, 
 // psi(z2) - psi(z1) = sum_{k=0}^{n-1} 1 / (z1 + k) for z2 = z1 + n, z1 >= 8 (asymptotic series, error < 3e-10)
 __device__ __forceinline__ float harmonic_span(float z1, float n) {
     const float z2 = z1 + n;
-    const float i1 = 1.f / z1, i2 = 1.f / z2;
+    const float i1 = __frcp_rn(z1), i2 = __frcp_rn(z2);
     const float a1 = i1 * i1, a2 = i2 * i2;
     float r = log1pf(n * i1);
     r += 0.5f * (i1 - i2);
@@ -585,6 +596,8 @@ constexpr float NEAR_PX = 8.f;
 __device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, int s, int e, bool has0, bool has1,
                                           float inv_is2, float eps, float &a0, float &a1) {
     const float K0 = c0 * inv_is2, K1 = c1 * inv_is2;
+    const float rK0 = __frcp_rn(K0), rK1 = __frcp_rn(K1);
+    const float del0 = eps * fabsf(rK0), del1 = eps * fabsf(rK1);
     const int near_lo = __float2int_rz(fmaxf(ceilf(x - NEAR_PX), -1.f));
     const int near_hi = __float2int_rz(fminf(floorf(x + NEAR_PX), 65535.f));
     float h0 = 0.f, h1 = 0.f;
@@ -600,14 +613,14 @@ __device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, 
     const int ps = max(s, near_hi + 1);  // far zone beyond the crossing: dist = K (dd + eps / |K|)
     if (ps <= e) {
         const float n = (float)(e - ps + 1), z = (float)ps - x;
-        h0 += harmonic_span(z + eps / fabsf(K0), n) / K0;
-        h1 += harmonic_span(z + eps / fabsf(K1), n) / K1;
+        h0 += harmonic_span(z + del0, n) * rK0;
+        h1 += harmonic_span(z + del1, n) * rK1;
     }
     const int me = min(e, near_lo - 1);  // far zone before the crossing: dist = -K (|dd| + eps / |K|)
     if (s <= me) {
         const float n = (float)(me - s + 1), z = x - (float)me;
-        h0 -= harmonic_span(z + eps / fabsf(K0), n) / K0;
-        h1 -= harmonic_span(z + eps / fabsf(K1), n) / K1;
+        h0 -= harmonic_span(z + del0, n) * rK0;
+        h1 -= harmonic_span(z + del1, n) * rK1;
     }
     a0 = has0 ? -G * h0 : 0.f;
     a1 = has1 ? -G * h1 : 0.f;
@@ -693,7 +706,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     __shared__ int cnt, next;
     __shared__ __align__(16) uint2 srun[4][TILE][RCAP];  // run lists: mn_row, mp_row, mn_col, mp_col
     __shared__ __align__(16) unsigned scount[4][TILE];
-    __shared__ int wqn[NWARPS], wsum[NWARPS];
+    __shared__ int wqn[NWARPS], wsum[NWARPS], wend[NWARPS];
     __shared__ float wacc[NTHREADS][2];
     __shared__ __align__(8) uint64_t bar;
     const int W = is / 32;
@@ -818,6 +831,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
 #pragma unroll
                 for (int w = 0; w < NWARPS; ++w) offset += (w < warp) ? wsum[w] : 0;
                 tt.incl[t] = incl + offset;
+                if (lane == 31) wend[warp] = incl + offset;  // inclusive prefix at the end of each warp block
                 __syncthreads();
             }
             const int total = tt.incl[NTHREADS - 1];
@@ -826,12 +840,15 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             for (int kb = warp * 32; kb < total; kb += NTHREADS) {
                 const int kk = kb + lane;
                 const bool active = kk < total;
-                // owner task of crossing kk: number of tasks whose inclusive prefix is <= kk
+                // owner task of crossing kk = number of tasks whose inclusive prefix is <= kk: first the warp
+                // block (8 independent compares against the block ends), then 5 dependent steps inside it
                 int j = 0;
 #pragma unroll
-                for (int sft = NTHREADS / 2; sft > 0; sft >>= 1)
+                for (int w = 0; w < NWARPS - 1; ++w) j += (wend[w] <= kk) ? 32 : 0;
+#pragma unroll
+                for (int sft = 16; sft > 0; sft >>= 1)
                     if (tt.incl[j + sft - 1] <= kk) j += sft;
-                const int o = active ? j : NTHREADS - 1;
+                const int o = active ? min(j, NTHREADS - 1) : NTHREADS - 1;
                 const int o_excl = o > 0 ? tt.incl[o - 1] : 0, o_pack = tt.packed[o], o_fn = tt.fn[o];
                 const float o_p0d0 = tt.p0d0[o], o_p0d1 = tt.p0d1[o], o_p1d0 = tt.p1d0[o], o_p2d0 = tt.p2d0[o];
                 const float o_p2d1 = tt.p2d1[o], o_slope = tt.slope[o], o_s02 = tt.slope02[o], o_s21 = tt.slope21[o];

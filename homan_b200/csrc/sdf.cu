@@ -18,7 +18,9 @@
 
 namespace {
 
-constexpr int NT = 256;
+constexpr int NT = 256;   // dense grid kernel
+constexpr int PNT = 512;  // pair kernel: one CTA per image, long serial phases -> more warps per CTA
+constexpr int VLIST = 8192;  // compacted inside voxels per pass
 constexpr int G = 32;  // grid size of the reference (scenesdf.py:14)
 
 __device__ __forceinline__ float dot3(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
@@ -109,7 +111,7 @@ __device__ __forceinline__ Corner unnormalise(float x, float y, float z) {
     return c;
 }
 
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(PNT)
 sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ faces, const float *__restrict__ verts_s,
                 int Vg, int Fg, int Vs, float half_factor, float weight, float *__restrict__ phi_all,
                 float *__restrict__ partials, float *__restrict__ g_vs) {
@@ -118,13 +120,15 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
     __shared__ unsigned needed[G * G], inside[G * G];
     __shared__ float red[6 * 32];
     __shared__ float box[4];  // centre xyz, scale
+    __shared__ unsigned short vlist[VLIST];
+    __shared__ int wtot[PNT / 32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *vg = verts_g + (long)b * Vg * 3;
     const float *vs = verts_s + (long)b * Vs * 3;
     float *phi = phi_all + (long)b * G * G * G;
     // ---- 1. bbox cube of the grid mesh
     float mx[6] = {-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
-    for (int i = tid; i < Vg; i += NT) {
+    for (int i = tid; i < Vg; i += PNT) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             const float v = vg[3 * i + k];
@@ -132,7 +136,7 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
             mx[3 + k] = fmaxf(mx[3 + k], v);
         }
     }
-    for (int i = tid; i < G * G; i += NT) { needed[i] = 0u; inside[i] = 0u; }
+    for (int i = tid; i < G * G; i += PNT) { needed[i] = 0u; inside[i] = 0u; }
     block_max<6>(mx, red);
     if (tid == 0) {
         float s = 0.f;
@@ -146,9 +150,9 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
     }
     __syncthreads();
     const float cx = box[0], cy = box[1], cz = box[2], sc = box[3];
-    for (int i = tid; i < Vg * 3; i += NT) lv[i] = (vg[i] - box[i % 3]) / sc;
+    for (int i = tid; i < Vg * 3; i += PNT) lv[i] = (vg[i] - box[i % 3]) / sc;
     // ---- 2. voxels touched by the samples
-    for (int i = tid; i < Vs; i += NT) {
+    for (int i = tid; i < Vs; i += PNT) {
         const Corner c = unnormalise((vs[3 * i] - cx) / sc, (vs[3 * i + 1] - cy) / sc, (vs[3 * i + 2] - cz) / sc);
 #pragma unroll
         for (int dz = 0; dz < 2; ++dz)
@@ -164,7 +168,7 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
     }
     __syncthreads();
     // bounding sphere of every face (centroid, radius with rounding slack): culls both loops below
-    for (int f = tid; f < Fg; f += NT) {
+    for (int f = tid; f < Fg; f += PNT) {
         const float *a = lv + 3 * __ldg(faces + 3 * f), *bq = lv + 3 * __ldg(faces + 3 * f + 1),
                     *c = lv + 3 * __ldg(faces + 3 * f + 2);
         const float mx_ = (a[0] + bq[0] + c[0]) / 3.f, my_ = (a[1] + bq[1] + c[1]) / 3.f, mz_ = (a[2] + bq[2] + c[2]) / 3.f;
@@ -176,7 +180,7 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
     }
     __syncthreads();
     // ---- 3. ray parity of every touched row (warp per row, lanes over faces)
-    for (int row = warp; row < G * G; row += NT / 32) {
+    for (int row = warp; row < G * G; row += PNT / 32) {
         const unsigned need = needed[row];
         if (!need) continue;
         const float py = voxel_centre(row % G), pz = voxel_centre(row / G);
@@ -192,13 +196,47 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
         if (lane == 0) inside[row] = parity & need;
     }
     __syncthreads();
-    // ---- 4. distance of the touched inside voxels (warp per voxel, lanes over faces)
-    for (int row = warp; row < G * G; row += NT / 32) {
-        unsigned bits = inside[row];
-        while (bits) {
-            const int i = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const float p[3] = {voxel_centre(i), voxel_centre(row % G), voxel_centre(row / G)};
+    // ---- 4. distance of the touched inside voxels: compact them (deterministic prefix sum over the rows),
+    //         then one warp per voxel, lanes over faces
+    static_assert(G * G == 2 * PNT, "two voxel rows per thread");
+    const unsigned bits0 = inside[2 * tid], bits1 = inside[2 * tid + 1];
+    const int c0 = __popc(bits0), c1 = __popc(bits1);
+    int incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wtot[warp] = incl;
+    __syncthreads();
+    int excl = incl - (c0 + c1);
+    for (int w = 0; w < warp; ++w) excl += wtot[w];
+    int total = 0;
+    for (int w = 0; w < PNT / 32; ++w) total += wtot[w];
+    for (int base = 0; base < total; base += VLIST) {
+        {
+            int g = excl;
+            unsigned m = bits0;
+            while (m) {
+                const int ix = __ffs(m) - 1;
+                m &= m - 1;
+                if (g >= base && g < base + VLIST) vlist[g - base] = (unsigned short)((2 * tid) * G + ix);
+                ++g;
+            }
+            m = bits1;
+            while (m) {
+                const int ix = __ffs(m) - 1;
+                m &= m - 1;
+                if (g >= base && g < base + VLIST) vlist[g - base] = (unsigned short)((2 * tid + 1) * G + ix);
+                ++g;
+            }
+        }
+        __syncthreads();
+        const int nv = min(total - base, VLIST);
+        for (int i = warp; i < nv; i += PNT / 32) {
+            const int vox = vlist[i];
+            const int row = vox / G, ix = vox % G;
+            const float p[3] = {voxel_centre(ix), voxel_centre(row % G), voxel_centre(row / G)};
             // upper bound of the distance from the spheres, then exact tests only where the lower bound allows
             float ub = INFINITY;
             for (int f = lane; f < Fg; f += 32) {
@@ -216,13 +254,13 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
                 best = fminf(best, point_tri_dist2(p, lv + 3 * i0, lv + 3 * i1, lv + 3 * i2));
             }
             best = warp_min(best);
-            if (lane == 0) phi[row * G + i] = sqrtf(best);
+            if (lane == 0) phi[vox] = sqrtf(best);
         }
+        __syncthreads();
     }
-    __syncthreads();
     // ---- 5. trilinear samples (grid_sample, zeros padding) + gradient w.r.t. the sampled vertices
     float acc[1] = {0.f};
-    for (int i = tid; i < Vs; i += NT) {
+    for (int i = tid; i < Vs; i += PNT) {
         const Corner c = unnormalise((vs[3 * i] - cx) / sc, (vs[3 * i + 1] - cy) / sc, (vs[3 * i + 2] - cz) / sc);
         float out = 0.f, gx = 0.f, gy = 0.f, gz = 0.f;
 #pragma unroll
@@ -301,7 +339,7 @@ int hm_sdf_pair(const float *verts_g, const int32_t *faces_g, const float *verts
         configured = smem;
     }
     const float half_factor = (float)((1.0 + (double)scale_factor) * 0.5);
-    sdf_pair_kernel<<<B, NT, smem, hm_stream(stream)>>>(verts_g, faces_g, verts_s, Vg, Fg, Vs, half_factor, weight,
+    sdf_pair_kernel<<<B, PNT, smem, hm_stream(stream)>>>(verts_g, faces_g, verts_s, Vg, Fg, Vs, half_factor, weight,
                                                         phi_scratch, partials, grad_verts_s);
     HM_CHECK_LAUNCH("hm_sdf_pair");
     return HM_OK;
