@@ -162,23 +162,54 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
     boxes[i] = bx;
 }
 
-constexpr int LISTCAP = 1024;  // faces of one tile processed per batch
+constexpr int LISTCAP = 2048;  // faces of one tile processed per batch
 
-// Appends to list[*cnt...] the faces of [base, base + NTHREADS) whose bbox touches the tile.
+constexpr int SCAN = 4 * NTHREADS;  // faces tested per scan step (four 8-byte boxes per thread)
+
+// Appends to list[*cnt...] the faces of [base, base + SCAN) whose bbox touches the tile.
 __device__ __forceinline__ void append_faces(const FaceBox *__restrict__ boxes, int base, int F, int tx0, int ty0,
                                              int *list, int *cnt) {
-    const int f = base + threadIdx.x;
-    bool hit = false;
-    if (f < F) {
-        const FaceBox bx = boxes[f];
-        hit = bx.x0 <= bx.x1 && bx.x0 <= tx0 + TILE - 1 && bx.x1 >= tx0 && bx.y0 <= ty0 + TILE - 1 && bx.y1 >= ty0;
+    const int f0 = base + 4 * threadIdx.x;
+    FaceBox bx[4];
+    if (f0 + 3 < F && (reinterpret_cast<uintptr_t>(boxes + f0) & 15u) == 0) {  // two 16-byte loads of 4 boxes
+        const uint4 u0 = __ldg(reinterpret_cast<const uint4 *>(boxes + f0));
+        const uint4 u1 = __ldg(reinterpret_cast<const uint4 *>(boxes + f0) + 1);
+        const unsigned w[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            bx[k].x0 = (short)(w[2 * k] & 0xffff); bx[k].y0 = (short)(w[2 * k] >> 16);
+            bx[k].x1 = (short)(w[2 * k + 1] & 0xffff); bx[k].y1 = (short)(w[2 * k + 1] >> 16);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (f0 + k < F) bx[k] = boxes[f0 + k];
+            else { bx[k].x0 = 1; bx[k].x1 = 0; bx[k].y0 = 1; bx[k].y1 = 0; }
+        }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, hit);
     const int lane = threadIdx.x & 31;
+    unsigned hits = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const bool hit = bx[k].x0 <= bx[k].x1 && bx[k].x0 <= tx0 + TILE - 1 && bx[k].x1 >= tx0 &&
+                         bx[k].y0 <= ty0 + TILE - 1 && bx[k].y1 >= ty0;
+        hits |= (hit ? 1u : 0u) << k;
+    }
+    const int mine = __popc(hits);
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
     int wbase = 0;
-    if (lane == 0 && m) wbase = atomicAdd(cnt, __popc(m));
-    wbase = __shfl_sync(0xffffffffu, wbase, 0);
-    if (hit) list[wbase + __popc(m & ((1u << lane) - 1))] = f;
+    if (lane == 31 && total) wbase = atomicAdd(cnt, total);
+    wbase = __shfl_sync(0xffffffffu, wbase, 31);
+    int pos = wbase + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if ((hits >> k) & 1u) list[pos++] = f0 + k;
 }
 
 // Fills the list with the next batch of faces touching the tile (scanning from *base). Block-uniform.
@@ -188,9 +219,9 @@ __device__ __forceinline__ int next_batch(const FaceBox *__restrict__ boxes, int
     if (threadIdx.x == 0) { *cnt = 0; *next = 0; }
     __syncthreads();
     int n = 0;
-    while (base < F && n <= cap - NTHREADS) {
+    while (base < F && n <= cap - SCAN) {
         append_faces(boxes, base, F, tx0, ty0, list, cnt);
-        base += NTHREADS;
+        base += SCAN;
         __syncthreads();
         n = *cnt;
     }
@@ -627,7 +658,7 @@ __device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, 
 }
 
 constexpr int WQCAP = 96;   // per-warp queue of (crossing, run) items
-constexpr int BWD_LISTCAP = 512;
+constexpr int BWD_LISTCAP = 1024;
 struct WarpQueue {
     float x[WQCAP], G[WQCAP];
     unsigned se[WQCAP], meta[WQCAP];  // s | e << 16 ; owner task (0..255) | d0 << 8
