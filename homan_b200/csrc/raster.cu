@@ -276,15 +276,6 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             const int Y0 = max(by0, ty0), Y1 = min(by1, ty0 + TILE - 1);
             const int w = X1 - X0 + 1, h = Y1 - Y0 + 1;
             if (w <= 0 || h <= 0) continue;
-            // barycentric matrix in pixel coordinates (same expressions as the oracle)
-            const float p00 = to_pix(f0, is), p01 = to_pix(f1, is), p10 = to_pix(f3, is), p11 = to_pix(f4, is),
-                        p20 = to_pix(f6, is), p21 = to_pix(f7, is);
-            float inv[9] = {p11 - p21, p20 - p10, p10 * p21 - p20 * p11,
-                            p21 - p01, p00 - p20, p20 * p01 - p00 * p21,
-                            p01 - p11, p10 - p00, p00 * p11 - p10 * p01};
-            const float den = p20 * (p01 - p11) + p00 * (p11 - p21) + p10 * (p21 - p01);
-#pragma unroll
-            for (int k = 0; k < 9; ++k) inv[k] /= den;
             const float e0x = f3 - f0, e0y = f4 - f1, e1x = f6 - f3, e1y = f7 - f4, e2x = f0 - f6, e2y = f1 - f7;
             // early z: the interpolated depth is a convex combination of the corner depths, so a face whose
             // nearest corner (minus rounding slack) is behind the current winner of a pixel cannot win it
@@ -332,6 +323,16 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 n_px = tot0 + tot1;
                 __syncwarp();
             }
+            if (n_px == 0) continue;  // the bounding box touches the tile, the triangle does not
+            // barycentric matrix in pixel coordinates (same expressions as the oracle)
+            const float p00 = to_pix(f0, is), p01 = to_pix(f1, is), p10 = to_pix(f3, is), p11 = to_pix(f4, is),
+                        p20 = to_pix(f6, is), p21 = to_pix(f7, is);
+            float inv[9] = {p11 - p21, p20 - p10, p10 * p21 - p20 * p11,
+                            p21 - p01, p00 - p20, p20 * p01 - p00 * p21,
+                            p01 - p11, p10 - p00, p00 * p11 - p10 * p01};
+            const float den = p20 * (p01 - p11) + p00 * (p11 - p21) + p10 * (p21 - p01);
+#pragma unroll
+            for (int k = 0; k < 9; ++k) inv[k] /= den;
             // Inside pixels are compacted into a per-warp queue so that the depth maths (7 IEEE divisions) runs
             // on full warps.
             unsigned short *pq = pixq[threadIdx.x >> 5];
@@ -701,20 +702,21 @@ __device__ __forceinline__ void drain_queue(WarpQueue &q, const TaskTable &tt, i
             eval_queued(tt, q.x[i], q.G[i], q.se[i], meta, inv_is2, eps, a0, a1);
             key = meta & 255u;
         }
-        unsigned peers = __match_any_sync(FULL, key);
-        const bool leader = (__ffs(peers) - 1) == lane;
-        int mx = __popc(peers);
+        // segmented sum over runs of equal keys (items of one task sit next to each other in the queue almost
+        // always); the head of every run adds to the task's accumulator, so the CAS loop of a shared-memory
+        // float add rarely finds contention
+        const unsigned knext = __shfl_down_sync(FULL, key, 1);
+        const unsigned bnd = __ballot_sync(FULL, lane == 31 || knext != key);  // last lane of every run
+        const int end = lane + __ffs(bnd >> lane) - 1;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(FULL, mx, o));
-        float s0 = 0.f, s1 = 0.f;
-        for (int it = 0; it < mx; ++it) {
-            const int src = peers ? __ffs(peers) - 1 : lane;
-            const float v0 = __shfl_sync(FULL, a0, src), v1 = __shfl_sync(FULL, a1, src);
-            if (peers) { s0 += v0; s1 += v1; peers &= peers - 1; }
+        for (int d = 1; d < 32; d <<= 1) {
+            const float v0 = __shfl_down_sync(FULL, a0, d), v1 = __shfl_down_sync(FULL, a1, d);
+            if (lane + d <= end) { a0 += v0; a1 += v1; }
         }
-        if (leader && key < 256u) {
-            acc_add(&wacc[key][0], s0);
-            acc_add(&wacc[key][1], s1);
+        const unsigned kprev = __shfl_up_sync(FULL, key, 1);
+        if ((lane == 0 || kprev != key) && key < 256u) {
+            acc_add(&wacc[key][0], a0);
+            acc_add(&wacc[key][1], a1);
         }
         __syncwarp();
     }
