@@ -264,10 +264,15 @@ def run_ours(args):
            raster_bwd_algorithmic_bytes(eng.B, eng.faces_obj.shape[1])) / 2 if eng.on_sil_hand else \
         raster_bwd_algorithmic_bytes(eng.B, eng.faces_obj.shape[1])
     roofline = None
+    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+    tpath = os.path.join(ROOT, "profiles", "raster_bwd_traffic.json")
+    if os.path.exists(tpath) and args.workload == "cfg3":
+        with open(tpath) as fh:
+            traffic = json.load(fh)["traffic_bytes_per_launch"]
     if bwd:
         achieved = alg / (bwd["us_per_launch"] * 1e-6) / 1e9
         roofline = {"kernel": "raster_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                    "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
+                    "frac": achieved / hbm, "traffic": traffic, "peak_source": hbm_src,
                     "algorithmic_bytes_per_launch": alg, "us_per_launch": bwd["us_per_launch"]}
     # ---- CPU baseline (oracle port), bounded sample: one init, one timed iteration
     cpu = None
