@@ -24,6 +24,8 @@ struct __align__(16) FaceRec {
     int v[3];     // vertex indices in that winding
     short bb[4];  // pixel bbox x0 y0 x1 y1 (clamped), empty when x0 > x1
     int pad;
+    float inv[9];  // barycentric matrix in pixel coordinates, already divided by its determinant
+    float pad2[7];
 };
 static_assert(sizeof(FaceRec) == HM_FACE_RECORD_BYTES, "record size");
 
@@ -156,6 +158,18 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
     r.fn = fn;
     r.bb[0] = (short)x0; r.bb[1] = (short)y0; r.bb[2] = (short)x1; r.bb[3] = (short)y1;
     r.pad = 0;
+    {   // barycentric matrix of the stored winding (same expressions as the oracle's per-face setup)
+        const float p00 = to_pix(r.c[0], is), p01 = to_pix(r.c[1], is), p10 = to_pix(r.c[3], is), p11 = to_pix(r.c[4], is),
+                    p20 = to_pix(r.c[6], is), p21 = to_pix(r.c[7], is);
+        const float m[9] = {p11 - p21, p20 - p10, p10 * p21 - p20 * p11,
+                            p21 - p01, p00 - p20, p20 * p01 - p00 * p21,
+                            p01 - p11, p10 - p00, p00 * p11 - p10 * p01};
+        const float den = p20 * (p01 - p11) + p00 * (p11 - p21) + p10 * (p21 - p01);
+#pragma unroll
+        for (int k = 0; k < 9; ++k) r.inv[k] = m[k] / den;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) r.pad2[k] = 0.f;
+    }
     recs[i] = r;
     FaceBox bx;
     bx.x0 = (short)x0; bx.y0 = (short)y0; bx.x1 = (short)x1; bx.y1 = (short)y1;
@@ -324,15 +338,15 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 __syncwarp();
             }
             if (n_px == 0) continue;  // the bounding box touches the tile, the triangle does not
-            // barycentric matrix in pixel coordinates (same expressions as the oracle)
-            const float p00 = to_pix(f0, is), p01 = to_pix(f1, is), p10 = to_pix(f3, is), p11 = to_pix(f4, is),
-                        p20 = to_pix(f6, is), p21 = to_pix(f7, is);
-            float inv[9] = {p11 - p21, p20 - p10, p10 * p21 - p20 * p11,
-                            p21 - p01, p00 - p20, p20 * p01 - p00 * p21,
-                            p01 - p11, p10 - p00, p00 * p11 - p10 * p01};
-            const float den = p20 * (p01 - p11) + p00 * (p11 - p21) + p10 * (p21 - p01);
-#pragma unroll
-            for (int k = 0; k < 9; ++k) inv[k] /= den;
+            // barycentric matrix in pixel coordinates, prepared once per face by the setup kernel
+            float inv[9];
+            {
+                const float4 i0 = __ldg(reinterpret_cast<const float4 *>(rp) + 4);
+                const float4 i1 = __ldg(reinterpret_cast<const float4 *>(rp) + 5);
+                inv[0] = i0.x; inv[1] = i0.y; inv[2] = i0.z; inv[3] = i0.w;
+                inv[4] = i1.x; inv[5] = i1.y; inv[6] = i1.z; inv[7] = i1.w;
+                inv[8] = __ldg(reinterpret_cast<const float *>(rp) + 24);
+            }
             // Inside pixels are compacted into a per-warp queue so that the depth maths (7 IEEE divisions) runs
             // on full warps.
             unsigned short *pq = pixq[threadIdx.x >> 5];
