@@ -582,21 +582,125 @@ build_runs_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restri
 }
 
 // ------------------------------------------------------------------------------------------ backward
-// Visits the set bits of `line` (one raster row or column, W <= 32 words, `nz` = mask of its non-zero words)
-// in [a, c] and accumulates the two vertex contributions of backward_pixel_map for the crossing (d0, d1_cross).
-__device__ __forceinline__ void sweep(const uint32_t *line, unsigned nz, int a, int c, int axis, int d0,
-                                      float d1_cross, float ka, float p0d0, float p1d0, const BwdCtx &ctx,
-                                      float &acc0, float &acc1) {
+// psi(z2) - psi(z1) = sum_{k=0}^{n-1} 1 / (z1 + k) for z2 = z1 + n, z1 >= 4 (asymptotic series, error < 1e-7)
+__device__ __forceinline__ float harmonic_span(float z1, float n) {
+    const float z2 = z1 + n;
+    const float i1 = __frcp_rn(z1), i2 = __frcp_rn(z2);
+    const float a1 = i1 * i1, a2 = i2 * i2;
+    float r = log1pf(n * i1);
+    r += 0.5f * (i1 - i2);
+    r += (1.f / 12.f) * (a1 - a2);
+    r -= (1.f / 120.f) * (a1 * a1 - a2 * a2);
+    r += (1.f / 252.f) * (a1 * a1 * a1 - a2 * a2 * a2);
+    return r;
+}
+
+// One (crossing, run) work item: the part [s, e] of one run of one sweep line seen from the crossing at
+// x = d1_cross of scan-line d0. A sweep runs away from the crossing, so the whole item lies on one side of it:
+// pixel k of the item (counted from the crossing) sits at distance z + k. The first NEAR_N pixels (the large terms)
+// are evaluated with the reference's expression; beyond, every pixel has the same weight G and the sum of
+// 1 / dist is the harmonic sum G / K * sum 1 / (z + k + eps / |K|), taken in closed form (dist = K (d1 - x) +- eps,
+// K = c * 2 / is). Straight-line code: every lane of a warp does the same work whatever its item looks like.
+constexpr int NEAR_N = 4;
+__device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, int s, int e, bool has0, bool has1,
+                                          float inv_is2, float eps, float &a0, float &a1) {
+    const float K0 = c0 * inv_is2, K1 = c1 * inv_is2;
+    const float rK0 = __frcp_rn(K0), rK1 = __frcp_rn(K1);
+    const float del0 = eps * fabsf(rK0), del1 = eps * fabsf(rK1);
+    const bool left = (float)e <= x;
+    const float sgn = left ? -1.f : 1.f;
+    const float z = left ? x - (float)e : (float)s - x;  // distance of the item's nearest pixel (>= 0)
+    const int n = e - s + 1;
+    float h0 = 0.f, h1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < NEAR_N; ++k) {
+        const float dd = sgn * (z + (float)k);
+        float dist0 = K0 * dd, dist1 = K1 * dd;
+        dist0 = (0.f < dist0) ? dist0 + eps : dist0 - eps;
+        dist1 = (0.f < dist1) ? dist1 + eps : dist1 - eps;
+        const float t0 = __frcp_rn(dist0), t1 = __frcp_rn(dist1);
+        if (k < n) { h0 += t0; h1 += t1; }
+    }
+    const float nf = (float)max(n - NEAR_N, 0), zf = z + (float)NEAR_N;
+    h0 += sgn * harmonic_span(zf + del0, nf) * rK0;
+    h1 += sgn * harmonic_span(zf + del1, nf) * rK1;
+    a0 = has0 ? -G * h0 : 0.f;
+    a1 = has1 ? -G * h1 : 0.f;
+}
+
+constexpr int BWD_LISTCAP = 1024;
+constexpr int BWD_SUB = 128;  // faces whose tasks are sorted and processed together
+constexpr int SEG = 8;        // scan-lines one thread walks
+constexpr int SQCAP = 64;  // per-warp queue of (crossing, run) items
+
+// A queued (crossing, run) item: crossing position x on its scan-line, the two distance coefficients of the
+// reference (ka / (p1.d0 - d0) and ka / (d0 - p0.d0)), the run's weight and its pixels inside the sweep.
+struct SweepQueue {
+    float x[SQCAP], c0[SQCAP], c1[SQCAP], G[SQCAP];
+    unsigned range[SQCAP];  // s | e << 16
+    unsigned meta[SQCAP];   // list (2 bits) | line << 2 (6 bits) | has0 << 8 | has1 << 9 | bit-line walk << 10
+    float r0[32], r1[32];   // results of the 32 items evaluated by one drain
+};
+
+// One (face, edge, axis) task of backward_pixel_map: the scan-lines d0 = lo .. lo + len - 1 of one edge inside
+// the tile, swept along d1 (axis 0: d0 = x, d1 = y; axis 1 swapped).
+struct TaskParams {
+    float p0d0, p0d1, p1d0, p2d0, p2d1, slope, slope02, slope21, ka;
+    int fn, dir, lo, len, axis, vid0, vid1;
+};
+__device__ __forceinline__ TaskParams task_params(const FaceRec *__restrict__ recs, const int *list, int task, int is,
+                                                  int tx0, int ty0) {
+    TaskParams p;
+    const int e = (task % 6) >> 1;
+    p.axis = task & 1;
+    const FaceRec *rp = recs + list[task / 6];
+    const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rp));
+    const float4 q1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
+    const float4 q2 = __ldg(reinterpret_cast<const float4 *>(rp) + 2);
+    const int4 q3 = __ldg(reinterpret_cast<const int4 *>(rp) + 3);
+    p.fn = __float_as_int(q2.y);
+    const int v0 = __float_as_int(q2.z), v1 = __float_as_int(q2.w), v2 = q3.x;
+    // pixel-space corners along (d0, d1) = (x, y) for axis 0, (y, x) for axis 1
+    const float ax = to_pix(q0.x, is), ay = to_pix(q0.y, is), bx = to_pix(q0.w, is), by = to_pix(q1.x, is),
+                cx = to_pix(q1.z, is), cy = to_pix(q1.w, is);
+    const float a0 = p.axis ? ay : ax, a1 = p.axis ? ax : ay, b0 = p.axis ? by : bx, b1 = p.axis ? bx : by,
+                c0 = p.axis ? cy : cx, c1 = p.axis ? cx : cy;
+    // vertex order of this edge: p0 = corner e, p1 = corner e+1, p2 = corner e+2
+    p.p0d0 = e == 0 ? a0 : e == 1 ? b0 : c0; p.p0d1 = e == 0 ? a1 : e == 1 ? b1 : c1;
+    p.p1d0 = e == 0 ? b0 : e == 1 ? c0 : a0;
+    const float p1d1 = e == 0 ? b1 : e == 1 ? c1 : a1;
+    p.p2d0 = e == 0 ? c0 : e == 1 ? a0 : b0; p.p2d1 = e == 0 ? c1 : e == 1 ? a1 : b1;
+    p.vid0 = e == 0 ? v0 : e == 1 ? v1 : v2; p.vid1 = e == 0 ? v1 : e == 1 ? v2 : v0;
+    if (p.axis == 0) p.dir = (p.p0d0 < p.p1d0) ? -1 : 1;
+    else p.dir = (p.p0d0 < p.p1d0) ? 1 : -1;
+    const int d0_from = __float2int_rz(fmaxf(ceilf(fminf(p.p0d0, p.p1d0)), 0.f));
+    const int d0_to = __float2int_rz(fminf(fmaxf(p.p0d0, p.p1d0), (float)(is - 1)));
+    const int t0 = p.axis == 0 ? tx0 : ty0, t1 = p.axis == 0 ? ty0 : tx0;
+    p.lo = max(d0_from, t0);
+    int hi = min(d0_to, t0 + TILE - 1);
+    p.ka = p.p1d0 - p.p0d0;
+    p.slope = (p1d1 - p.p0d1) / p.ka;
+    p.slope02 = (p.p2d1 - p.p0d1) / (p.p2d0 - p.p0d0);
+    p.slope21 = (p1d1 - p.p2d1) / (p.p1d0 - p.p2d0);
+    // only crossings whose in-pixel lies in this tile are handled here: restrict the scan-lines to where the
+    // edge passes the tile's d1 range (slack of a pixel; steep enough edges only, so the bound is accurate)
+    const float as = fabsf(p.slope);
+    if (as > 1e-2f && as < 1e6f) {
+        const float u0 = p.p0d0 + ((float)(t1 - 2) - p.p0d1) / p.slope, u1 = p.p0d0 + ((float)(t1 + TILE + 1) - p.p0d1) / p.slope;
+        p.lo = max(p.lo, __float2int_rz(fmaxf(floorf(fminf(u0, u1)) - 1.f, -1.f)));
+        hi = min(hi, __float2int_rz(fminf(ceilf(fmaxf(u0, u1)) + 1.f, 70000.f)));
+    }
+    p.len = p.fn >= 0 ? max(hi - p.lo + 1, 0) : 0;
+    return p;
+}
+
+// Bit-line walk for lines whose run list overflowed: visits the set bits of `line` in [a, c].
+__device__ __forceinline__ void sweep_bits(const uint32_t *line, int a, int c, int axis, int d0, float d1_cross,
+                                           float c0, float c1, bool has0, bool has1, const BwdCtx &ctx, float &acc0,
+                                           float &acc1) {
     if (a > c) return;
     const int wa = a >> 5, wc = c >> 5;
-    unsigned wm = nz & (0xffffffffu << wa) & (0xffffffffu >> (31 - wc));
-    if (!wm) return;
-    const float fd0 = (float)d0;
-    const bool has0 = p1d0 != fd0, has1 = p0d0 != fd0;
-    const float c0 = ka / (p1d0 - fd0), c1 = ka / (fd0 - p0d0);
-    while (wm) {
-        const int w = __ffs(wm) - 1;
-        wm &= wm - 1;
+    for (int w = wa; w <= wc; ++w) {
         unsigned bits = line[w];
         if (w == wa) bits &= 0xffffffffu << (a & 31);
         if (w == wc) bits &= 0xffffffffu >> (31 - (c & 31));
@@ -621,127 +725,13 @@ __device__ __forceinline__ void sweep(const uint32_t *line, unsigned nz, int a, 
     }
 }
 
-// psi(z2) - psi(z1) = sum_{k=0}^{n-1} 1 / (z1 + k) for z2 = z1 + n, z1 >= 8 (asymptotic series, error < 3e-10)
-__device__ __forceinline__ float harmonic_span(float z1, float n) {
-    const float z2 = z1 + n;
-    const float i1 = __frcp_rn(z1), i2 = __frcp_rn(z2);
-    const float a1 = i1 * i1, a2 = i2 * i2;
-    float r = log1pf(n * i1);
-    r += 0.5f * (i1 - i2);
-    r += (1.f / 12.f) * (a1 - a2);
-    r -= (1.f / 120.f) * (a1 * a1 - a2 * a2);
-    r += (1.f / 252.f) * (a1 * a1 * a1 - a2 * a2 * a2);
-    return r;
-}
-
-// One (crossing, run) work item: the part [s, e] of one run of one sweep line seen from the crossing at
-// x = d1_cross of scan-line d0. Pixels within NEAR_PX of the crossing (the large terms) are evaluated one by
-// one; beyond, every pixel of the run has the same weight G and the sum of 1 / dist is the harmonic sum
-// G / K * sum 1 / (|d1 - x| + eps / |K|), taken in closed form (dist = K (d1 - x) +- eps, K = c * 2 / is).
-constexpr float NEAR_PX = 8.f;
-__device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, int s, int e, bool has0, bool has1,
-                                          float inv_is2, float eps, float &a0, float &a1) {
-    const float K0 = c0 * inv_is2, K1 = c1 * inv_is2;
-    const float rK0 = __frcp_rn(K0), rK1 = __frcp_rn(K1);
-    const float del0 = eps * fabsf(rK0), del1 = eps * fabsf(rK1);
-    const int near_lo = __float2int_rz(fmaxf(ceilf(x - NEAR_PX), -1.f));
-    const int near_hi = __float2int_rz(fminf(floorf(x + NEAR_PX), 65535.f));
-    float h0 = 0.f, h1 = 0.f;
-    const int ns = max(s, near_lo), ne = min(e, near_hi);
-    for (int d1 = ns; d1 <= ne; ++d1) {
-        const float dd = (float)d1 - x;
-        float dist0 = K0 * dd, dist1 = K1 * dd;
-        dist0 = (0.f < dist0) ? dist0 + eps : dist0 - eps;
-        dist1 = (0.f < dist1) ? dist1 + eps : dist1 - eps;
-        h0 += __frcp_rn(dist0);
-        h1 += __frcp_rn(dist1);
-    }
-    const int ps = max(s, near_hi + 1);  // far zone beyond the crossing: dist = K (dd + eps / |K|)
-    if (ps <= e) {
-        const float n = (float)(e - ps + 1), z = (float)ps - x;
-        h0 += harmonic_span(z + del0, n) * rK0;
-        h1 += harmonic_span(z + del1, n) * rK1;
-    }
-    const int me = min(e, near_lo - 1);  // far zone before the crossing: dist = -K (|dd| + eps / |K|)
-    if (s <= me) {
-        const float n = (float)(me - s + 1), z = x - (float)me;
-        h0 -= harmonic_span(z + del0, n) * rK0;
-        h1 -= harmonic_span(z + del1, n) * rK1;
-    }
-    a0 = has0 ? -G * h0 : 0.f;
-    a1 = has1 ? -G * h1 : 0.f;
-}
-
-constexpr int WQCAP = 96;   // per-warp queue of (crossing, run) items
-constexpr int BWD_LISTCAP = 1024;
-struct WarpQueue {
-    float x[WQCAP], G[WQCAP];
-    unsigned se[WQCAP], meta[WQCAP];  // s | e << 16 ; owner task (0..255) | d0 << 8
-};
-
-// Parameters of the (up to) 256 tasks of a chunk, one per thread, readable by every thread of the CTA (the
-// crossings of a task are evaluated by whichever lanes the load-balanced search hands them to).
-struct TaskTable {
-    float p0d0[NTHREADS], p0d1[NTHREADS], p1d0[NTHREADS], p2d0[NTHREADS], p2d1[NTHREADS], slope[NTHREADS],
-        slope02[NTHREADS], slope21[NTHREADS], ka[NTHREADS];
-    int packed[NTHREADS], fn[NTHREADS], incl[NTHREADS];
-};
-
-__device__ __forceinline__ void eval_queued(const TaskTable &tt, float x, float G, unsigned se, unsigned meta,
-                                            float inv_is2, float eps, float &a0, float &a1) {
-    const int o = meta & 255u;
-    const float fd0 = (float)(meta >> 8);
-    const float p0d0 = tt.p0d0[o], p1d0 = tt.p1d0[o], ka = tt.ka[o];
-    eval_item(x, ka / (p1d0 - fd0), ka / (fd0 - p0d0), G, (int)(se & 0xffffu), (int)(se >> 16), p1d0 != fd0,
-              p0d0 != fd0, inv_is2, eps, a0, a1);
-}
-
-// Per-task accumulators live in shared memory (float; atomics there are CAS loops, so contention must be
-// avoided): a drain pass evaluates 32 items, sums the results of the items that belong to the same task inside
-// the warp (match_any + shuffles), and one lane per task does a plain read-modify-write.
-__device__ __forceinline__ void acc_add(float *slot, float v) {
-    if (v != 0.f) atomicAdd(slot, v);
-}
-
-__device__ __forceinline__ void drain_queue(WarpQueue &q, const TaskTable &tt, int n, float (*wacc)[2], float inv_is2,
-                                            float eps) {
-    const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    for (int base = 0; base < n; base += 32) {
-        const int i = base + lane;
-        float a0 = 0.f, a1 = 0.f;
-        unsigned key = 256u + (unsigned)lane;  // lanes without an item form singleton groups
-        if (i < n) {
-            const unsigned meta = q.meta[i];
-            eval_queued(tt, q.x[i], q.G[i], q.se[i], meta, inv_is2, eps, a0, a1);
-            key = meta & 255u;
-        }
-        // segmented sum over runs of equal keys (items of one task sit next to each other in the queue almost
-        // always); the head of every run adds to the task's accumulator, so the CAS loop of a shared-memory
-        // float add rarely finds contention
-        const unsigned knext = __shfl_down_sync(FULL, key, 1);
-        const unsigned bnd = __ballot_sync(FULL, lane == 31 || knext != key);  // last lane of every run
-        const int end = lane + __ffs(bnd >> lane) - 1;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const float v0 = __shfl_down_sync(FULL, a0, d), v1 = __shfl_down_sync(FULL, a1, d);
-            if (lane + d <= end) { a0 += v0; a1 += v1; }
-        }
-        const unsigned kprev = __shfl_up_sync(FULL, key, 1);
-        if ((lane == 0 || kprev != key) && key < 256u) {
-            acc_add(&wacc[key][0], a0);
-            acc_add(&wacc[key][1], a1);
-        }
-        __syncwarp();
-    }
-}
-
-// One CTA per (image, 64x64 tile). The (face, edge, axis) tasks of the faces touching the tile are taken 256
-// at a time, one per thread; their scan-line crossings are flattened over ALL lanes of the CTA (load-balanced
-// search over the CTA-wide prefix sum of the task lengths, task parameters read from a shared table), and the
-// (crossing, run) pairs that have something to sweep go through a per-warp queue so that the expensive part
-// runs on dense warps.
-__global__ void __launch_bounds__(NTHREADS)
+// One CTA per (image, 64x64 tile). The (face, edge, axis) tasks of the faces touching the tile are sorted by
+// length (counting sort in shared memory); warps pull groups of 32 tasks of similar length off the sorted list
+// and every thread walks the scan-line crossings of ONE task with the task's parameters in registers. A crossing whose out-sweep / in-sweep has runs to visit queues the sweep in
+// a per-warp shared queue (ballot compaction); 32 queued sweeps are evaluated at a time on a full warp, and every
+// thread collects the results of the sweeps it queued itself (it remembers their slots in a bit mask), so the
+// per-task sums stay in registers: no shared-memory float atomics, one global atomicAdd per face-vertex component.
+__global__ void __launch_bounds__(NTHREADS, 3)
 raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
                   float eps, const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
                   const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ cov_col,
@@ -753,21 +743,21 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     __shared__ int cnt, next;
     __shared__ __align__(16) uint2 srun[4][TILE][RCAP];  // run lists: mn_row, mp_row, mn_col, mp_col
     __shared__ __align__(16) unsigned scount[4][TILE];
-    __shared__ int wqn[NWARPS], wsum[NWARPS], wend[NWARPS];
-    __shared__ float wacc[NTHREADS][2];
+    __shared__ int hist[TILE + 2], hpos[TILE + 2];
+    __shared__ unsigned char slen[6 * BWD_SUB];                 // scan-lines of every task of the sub-batch
+    __shared__ unsigned short sorted[6 * BWD_SUB * (TILE / SEG)];  // segments (task | index << 12), longest first
+    __shared__ float wacc[6 * BWD_SUB][2];                       // per-task sums of the sub-batch
     __shared__ __align__(8) uint64_t bar;
     const int W = is / 32;
-    const int LW = TILE * W;  // words per coverage block: a_row, a_col
-    // dynamic shared memory: face_index tile | coverage lines | per-warp queues | task table of the chunk
+    // dynamic shared memory: face_index tile | per-warp queues
     int *fi = reinterpret_cast<int *>(smem_raw);
-    uint32_t *lines = reinterpret_cast<uint32_t *>(smem_raw + TILE * TILE * sizeof(int));
-    WarpQueue *wq = reinterpret_cast<WarpQueue *>(smem_raw + TILE * TILE * sizeof(int) + 2 * LW * sizeof(uint32_t));
-    TaskTable &tt = *reinterpret_cast<TaskTable *>(wq + NWARPS);
+    SweepQueue *sq = reinterpret_cast<SweepQueue *>(smem_raw + TILE * TILE * sizeof(int));
     const int b = blockIdx.y;
     const int tiles_x = is / TILE;
     const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
+    const unsigned lt_mask = (1u << lane) - 1u;
     recs += (long)b * F;
     boxes += (long)b * F;
     grad_ndc += (long)b * V * 3;
@@ -776,7 +766,30 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     ctx.grad = grad_alpha + (long)b * ctx.R * ctx.R;
     const float inv_is2 = 2.f / (float)is;
     const long plane = (long)is * W;
-    WarpQueue &q = wq[warp];
+    SweepQueue &q = sq[warp];
+
+    // Evaluates the first `nq` (<= 32) queued items, one per lane, and leaves the results in q.r0 / q.r1.
+    auto evaluate = [&](int nq) {
+        float a0 = 0.f, a1 = 0.f;
+        if (lane < nq) {
+            const float x = q.x[lane], c0 = q.c0[lane], c1 = q.c1[lane];
+            const unsigned rng = q.range[lane], meta = q.meta[lane];
+            const int ra = (int)(rng & 0xffffu), rc = (int)(rng >> 16);
+            const bool has0 = (meta >> 8) & 1u, has1 = (meta >> 9) & 1u;
+            if ((meta >> 10) & 1u) {
+                // more runs than the list holds: walk the bit line (global memory)
+                const int ls = meta & 3u, l0 = (meta >> 2) & 63u;
+                const int col = ls >> 1;
+                const uint32_t *line = (col ? m_col : m_row) + ((long)b * 2 * is + (col ? tx0 : ty0) + l0) * W + (ls & 1) * plane;
+                sweep_bits(line, ra, rc, col ? 0 : 1, (col ? tx0 : ty0) + l0, x, c0, c1, has0, has1, ctx, a0, a1);
+            } else {
+                eval_item(x, c0, c1, q.G[lane], ra, rc, has0, has1, inv_is2, eps, a0, a1);
+            }
+        }
+        q.r0[lane] = a0;
+        q.r1[lane] = a1;
+        __syncwarp();
+    };
 
     int base = 0;
     bool staged = false;
@@ -784,7 +797,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
         const int n = next_batch(boxes, base, F, tx0, ty0, list, &cnt, &next, BWD_LISTCAP);
         if (n == 0) continue;
         if (!staged) {
-            // ---- stage the tile's face_index rows, coverage lines and run lists with TMA bulk copies
+            // ---- stage the tile's face_index rows and run lists (TMA bulk copies)
             //      (tiles no face touches never get here: their face_index is never read)
             if (threadIdx.x == 0) {
                 mbar_init(&bar, 1);
@@ -793,10 +806,8 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             __syncthreads();
             if (warp == 0) {
                 if (lane == 0)
-                    mbar_expect_tx(&bar, (uint32_t)(2 * LW * 4 + 4 * TILE * RCAP * 8 + 4 * TILE * 4));
+                    mbar_expect_tx(&bar, (uint32_t)(4 * TILE * RCAP * 8 + 4 * TILE * 4));
                 __syncwarp();
-                if (lane == 0) tma_bulk_g2s(lines, cov_row + ((long)b * is + ty0) * W, (uint32_t)(LW * 4), &bar);
-                if (lane == 1) tma_bulk_g2s(lines + LW, cov_col + ((long)b * is + tx0) * W, (uint32_t)(LW * 4), &bar);
                 if (lane >= 8 && lane < 12) {
                     const int l4 = lane - 8, t0 = (l4 >> 1) ? tx0 : ty0;
                     tma_bulk_g2s(&srun[l4][0][0], runs + (((long)b * 4 + l4) * is + t0) * RCAP, TILE * RCAP * 8, &bar);
@@ -814,172 +825,193 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             __syncthreads();
             staged = true;
         }
-        const int ntasks = 6 * n;
-        for (int chunk = 0; chunk < ntasks; chunk += NTHREADS) {
-            // ---- one (face, edge, axis) task per thread; its parameters go to the CTA-wide table
-            const int task = chunk + threadIdx.x;
-            int vid0 = 0, vid1 = 0, axis = 0, len = 0;
-            {
-                float p0d0 = 0.f, p0d1 = 0.f, p1d0 = 0.f, p2d0 = 0.f, p2d1 = 0.f, slope = 0.f, slope02 = 0.f,
-                      slope21 = 0.f, ka = 0.f;
-                int fn = -1, dir = 1, lo = 0;
-                if (task < ntasks) {
-                    const int e = (task % 6) >> 1;
-                    axis = task & 1;
-                    const FaceRec *rp = recs + list[task / 6];
-                    const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rp));
-                    const float4 q1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
-                    const float4 q2 = __ldg(reinterpret_cast<const float4 *>(rp) + 2);
-                    const int4 q3 = __ldg(reinterpret_cast<const int4 *>(rp) + 3);
-                    fn = __float_as_int(q2.y);
-                    const int v0 = __float_as_int(q2.z), v1 = __float_as_int(q2.w), v2 = q3.x;
-                    // pixel-space corners along (d0, d1) = (x, y) for axis 0, (y, x) for axis 1
-                    const float ax = to_pix(q0.x, is), ay = to_pix(q0.y, is), bx = to_pix(q0.w, is), by = to_pix(q1.x, is),
-                                cx = to_pix(q1.z, is), cy = to_pix(q1.w, is);
-                    const float a0 = axis ? ay : ax, a1 = axis ? ax : ay, b0 = axis ? by : bx, b1 = axis ? bx : by,
-                                c0 = axis ? cy : cx, c1 = axis ? cx : cy;
-                    // vertex order of this edge: p0 = corner e, p1 = corner e+1, p2 = corner e+2
-                    p0d0 = e == 0 ? a0 : e == 1 ? b0 : c0; p0d1 = e == 0 ? a1 : e == 1 ? b1 : c1;
-                    p1d0 = e == 0 ? b0 : e == 1 ? c0 : a0;
-                    const float p1d1 = e == 0 ? b1 : e == 1 ? c1 : a1;
-                    p2d0 = e == 0 ? c0 : e == 1 ? a0 : b0; p2d1 = e == 0 ? c1 : e == 1 ? a1 : b1;
-                    vid0 = e == 0 ? v0 : e == 1 ? v1 : v2; vid1 = e == 0 ? v1 : e == 1 ? v2 : v0;
-                    if (axis == 0) dir = (p0d0 < p1d0) ? -1 : 1;
-                    else dir = (p0d0 < p1d0) ? 1 : -1;
-                    const int d0_from = __float2int_rz(fmaxf(ceilf(fminf(p0d0, p1d0)), 0.f));
-                    const int d0_to = __float2int_rz(fminf(fmaxf(p0d0, p1d0), (float)(is - 1)));
-                    const int t0 = axis == 0 ? tx0 : ty0;
-                    lo = max(d0_from, t0);
-                    len = max(min(d0_to, t0 + TILE - 1) - lo + 1, 0);
-                    ka = p1d0 - p0d0;
-                    slope = (p1d1 - p0d1) / ka;
-                    slope02 = (p2d1 - p0d1) / (p2d0 - p0d0);
-                    slope21 = (p1d1 - p2d1) / (p1d0 - p2d0);
-                }
-                // inclusive prefix sum of the task lengths over the CTA (warp scans + warp totals)
-                int incl = len;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                __syncthreads();  // previous chunk fully consumed (table, accumulators, wsum)
-                if (lane == 31) wsum[warp] = incl;
-                const int t = threadIdx.x;
-                tt.p0d0[t] = p0d0; tt.p0d1[t] = p0d1; tt.p1d0[t] = p1d0; tt.p2d0[t] = p2d0; tt.p2d1[t] = p2d1;
-                tt.slope[t] = slope; tt.slope02[t] = slope02; tt.slope21[t] = slope21; tt.ka[t] = ka;
-                tt.packed[t] = (lo & 0xffff) | (axis << 16) | ((dir > 0 ? 1 : 0) << 17);
-                tt.fn[t] = fn;
-                wacc[t][0] = 0.f;
-                wacc[t][1] = 0.f;
-                if (lane == 0) wqn[warp] = 0;
-                __syncthreads();
-                int offset = 0;
-#pragma unroll
-                for (int w = 0; w < NWARPS; ++w) offset += (w < warp) ? wsum[w] : 0;
-                tt.incl[t] = incl + offset;
-                if (lane == 31) wend[warp] = incl + offset;  // inclusive prefix at the end of each warp block
-                __syncthreads();
+        for (int f0 = 0; f0 < n; f0 += BWD_SUB) {
+        const int *sub = list + f0;
+        const int ntasks = 6 * min(BWD_SUB, n - f0);
+        // ---- the scan-lines of every task are cut into segments of <= SEG lines; counting sort of the
+        //      segments by decreasing length (full segments first)
+        __syncthreads();
+        if (threadIdx.x < SEG + 2) hist[threadIdx.x] = 0;
+        if (threadIdx.x == 0) next = 0;
+        for (int i = threadIdx.x; i < 2 * ntasks; i += NTHREADS) (&wacc[0][0])[i] = 0.f;
+        __syncthreads();
+        for (int task = threadIdx.x; task < ntasks; task += NTHREADS) {
+            const int len = task_params(recs, sub, task, is, tx0, ty0).len;
+            slen[task] = (unsigned char)len;
+            if (len >= SEG) atomicAdd(&hist[SEG], len / SEG);
+            if (len % SEG) atomicAdd(&hist[len % SEG], 1);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {  // hpos[l] = number of segments longer than l
+            int run = 0;
+            for (int l = SEG; l >= 1; --l) { hpos[l] = run; run += hist[l]; }
+            hpos[0] = run;
+        }
+        __syncthreads();
+        for (int task = threadIdx.x; task < ntasks; task += NTHREADS) {
+            const int len = slen[task];
+            const int full = len / SEG;
+            if (full) {
+                const int at = atomicAdd(&hpos[SEG], full);
+                for (int i = 0; i < full; ++i) sorted[at + i] = (unsigned short)(task | (i << 12));
             }
-            const int total = tt.incl[NTHREADS - 1];
+            if (len % SEG) sorted[atomicAdd(&hpos[len % SEG], 1)] = (unsigned short)(task | (full << 12));
+        }
+        __syncthreads();
+        const int nwork = hpos[0];
 
-            // ---- crossings of the whole chunk, 32 per warp per round, dealt round-robin to the warps
-            for (int kb = warp * 32; kb < total; kb += NTHREADS) {
-                const int kk = kb + lane;
-                const bool active = kk < total;
-                // owner task of crossing kk = number of tasks whose inclusive prefix is <= kk: first the warp
-                // block (8 independent compares against the block ends), then 5 dependent steps inside it
-                int j = 0;
+        for (;;) {  // warps pull groups of 32 tasks
+            int g = 0;
+            if (lane == 0) g = atomicAdd(&next, 1);
+            g = __shfl_sync(FULL, g, 0);
+            if (g * 32 >= nwork) break;
+            const bool mine_valid = g * 32 + lane < nwork;
+            const unsigned seg_id = sorted[min(g * 32 + lane, nwork - 1)];
+            const int my_task = seg_id & 0xfffu, seg_lo = (int)(seg_id >> 12) * SEG;
+            const TaskParams tp = task_params(recs, sub, my_task, is, tx0, ty0);
+            // ---- this thread's task
+            const float p0d0 = tp.p0d0, p0d1 = tp.p0d1, p1d0 = tp.p1d0, p2d0 = tp.p2d0, p2d1 = tp.p2d1;
+            const float slope = tp.slope, s02 = tp.slope02, s21 = tp.slope21, ka = tp.ka;
+            const int fn = tp.fn, axis = tp.axis, dir = tp.dir, lo = tp.lo + seg_lo;
+            const int mylen = mine_valid ? min(tp.len - seg_lo, SEG) : 0;
+            int maxlen = mylen;  // (the list is sorted, but tasks of equal length sit in arbitrary order)
 #pragma unroll
-                for (int w = 0; w < NWARPS - 1; ++w) j += (wend[w] <= kk) ? 32 : 0;
-#pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1)
-                    if (tt.incl[j + sft - 1] <= kk) j += sft;
-                const int o = active ? min(j, NTHREADS - 1) : NTHREADS - 1;
-                const int o_excl = o > 0 ? tt.incl[o - 1] : 0, o_pack = tt.packed[o], o_fn = tt.fn[o];
-                const float o_p0d0 = tt.p0d0[o], o_p0d1 = tt.p0d1[o], o_p1d0 = tt.p1d0[o], o_p2d0 = tt.p2d0[o];
-                const float o_p2d1 = tt.p2d1[o], o_slope = tt.slope[o], o_s02 = tt.slope02[o], o_s21 = tt.slope21[o];
-                const float o_ka = tt.ka[o];
-                if (active) {
-                    const int o_axis = (o_pack >> 16) & 1, o_dir = ((o_pack >> 17) & 1) ? 1 : -1;
-                    const int d0 = (o_pack & 0xffff) + (kk - o_excl);
-                    const int t0 = o_axis == 0 ? tx0 : ty0, t1 = o_axis == 0 ? ty0 : tx0;
-                    const int l0 = d0 - t0;
-                    const int lN = o_axis == 0 ? 2 : 0, lP = lN + 1;
+            for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(FULL, maxlen, o));
+            const int t0 = axis == 0 ? tx0 : ty0, t1 = axis == 0 ? ty0 : tx0;
+            const int lN = axis == 0 ? 2 : 0, lP = lN + 1;
+            const int fs0 = axis == 0 ? 1 : TILE, fs1 = axis == 0 ? TILE : 1;
+            // coverage bits of the out pixels: column lines for axis 0, row lines for axis 1 (read through L1)
+            const uint32_t *Ablock = axis == 0 ? cov_col + ((long)b * is + tx0) * W : cov_row + ((long)b * is + ty0) * W;
+            float acc0 = 0.f, acc1 = 0.f;
+            unsigned long long mine = 0ull;  // queue slots holding sweeps of this thread's task
+            int qn = 0;
+
+            // a drain evaluates the first 32 queued sweeps and hands every result to the thread that queued it
+            auto drain = [&](int nq) {
+                evaluate(nq);
+                unsigned m = (unsigned)mine;
+                while (m) {
+                    const int sl = __ffs(m) - 1;
+                    m &= m - 1;
+                    acc0 += q.r0[sl];
+                    acc1 += q.r1[sl];
+                }
+                mine >>= 32;
+                const int rem = qn - nq;  // > 0 only when nq == 32
+                float mx = 0.f, mc0 = 0.f, mc1 = 0.f, mg = 0.f;
+                unsigned mr = 0, mm = 0;
+                if (lane < rem) { mx = q.x[32 + lane]; mc0 = q.c0[32 + lane]; mc1 = q.c1[32 + lane]; mg = q.G[32 + lane]; mr = q.range[32 + lane]; mm = q.meta[32 + lane]; }
+                __syncwarp();
+                if (lane < rem) { q.x[lane] = mx; q.c0[lane] = mc0; q.c1[lane] = mc1; q.G[lane] = mg; q.range[lane] = mr; q.meta[lane] = mm; }
+                qn = max(rem, 0);
+                __syncwarp();
+            };
+            auto push_item = [&](bool has, float x, float c0, float c1, float G, unsigned rng, unsigned meta) {
+                const unsigned m = __ballot_sync(FULL, has);
+                if (!m) return;
+                if (has) {
+                    const int pos = qn + __popc(m & lt_mask);
+                    q.x[pos] = x; q.c0[pos] = c0; q.c1[pos] = c1; q.G[pos] = G; q.range[pos] = rng; q.meta[pos] = meta;
+                    mine |= 1ull << pos;
+                }
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32) drain(32);
+            };
+            // queues the runs of list `ls`, line `l0` that a sweep over [ra, rc] visits (one item each)
+            auto push_sweep = [&](bool has, float x, float c0, float c1, int ls, int l0, unsigned cnt, int ra, int rc, unsigned hb) {
+                if (!__ballot_sync(FULL, has)) return;
+                const bool walk = cnt == RUN_OVERFLOW;
+                const int nr = has ? (walk ? 1 : (int)cnt) : 0;
+                const int rmax = __reduce_max_sync(FULL, nr);
+                for (int r = 0; r < rmax; ++r) {
+                    bool it = false;
+                    unsigned se = 0, meta = hb | (unsigned)ls;
+                    float G = 0.f;
+                    if (r < nr) {
+                        if (walk) {
+                            it = true; se = (unsigned)ra | ((unsigned)rc << 16); meta |= 1u << 10;
+                        } else {
+                            const uint2 run = srun[ls][l0][r];
+                            const int s = max(ra, (int)(run.x & 0xffffu)), e = min(rc, (int)(run.x >> 16));
+                            if (s <= e) { it = true; se = (unsigned)s | ((unsigned)e << 16); G = __uint_as_float(run.y); }
+                        }
+                    }
+                    push_item(it, x, c0, c1, G, se, meta);
+                }
+            };
+
+            for (int k = 0; k < maxlen; ++k) {
+                bool has_out = false, has_in = false;
+                float x = 0.f, c0 = 0.f, c1 = 0.f;
+                int ra_out = 0, rc_out = 0, ra_in = 0, rc_in = 0, ls_in = 0, l0 = 0;
+                unsigned cnt_out = 0, cnt_in = 0, hb = 0;
+                if (k < mylen) {
+                    const int d0 = lo + k;
+                    l0 = d0 - t0;
                     const unsigned cN = scount[lN][l0], cP = scount[lP][l0];
                     if ((cN | cP) != 0u) {  // something to sweep on this line
                         const float fd0 = (float)d0;
-                        const float x = o_slope * (fd0 - o_p0d0) + o_p0d1;
-                        const int d1_in = __float2int_rz(o_dir > 0 ? floorf(x) : ceilf(x));
-                        const int d1_out = d1_in + o_dir;
+                        x = slope * (fd0 - p0d0) + p0d1;
+                        const int d1_in = __float2int_rz(dir > 0 ? floorf(x) : ceilf(x));
+                        const int d1_out = d1_in + dir;
                         if (d1_in >= 0 && d1_in < is && d1_out >= 0 && d1_out < is && d1_in >= t1 && d1_in < t1 + TILE) {
-                            const unsigned meta = (unsigned)o | ((unsigned)d0 << 8);
-                            const int fs0 = o_axis == 0 ? 1 : TILE, fs1 = o_axis == 0 ? TILE : 1;
-                            // sweep 0: out-sweep (missing-coverage list, from the out pixel to the border) when this
-                            // face owns the in pixel; sweep 1: in-sweep (from the in pixel to the opposite edge)
-#pragma unroll 1
-                            for (int sw = 0; sw < 2; ++sw) {
-                                int ls, ra, rc;
-                                if (sw == 0) {
-                                    if (cN == 0u || fi[l0 * fs0 + (d1_in - t1) * fs1] != o_fn) continue;
-                                    const int lim = o_dir > 0 ? is - 1 : 0;
-                                    ls = lN; ra = min(d1_out, lim); rc = max(d1_out, lim);
-                                } else {
-                                    const uint32_t *A = lines + (o_axis == 0 ? LW : 0) + l0 * W;
-                                    const bool alpha_out = (A[d1_out >> 5] >> (d1_out & 31)) & 1u;
-                                    ls = alpha_out ? lN : lP;
-                                    if ((alpha_out ? cN : cP) == 0u) continue;
+                            hb = (p1d0 != fd0 ? 1u << 8 : 0u) | (p0d0 != fd0 ? 1u << 9 : 0u) | ((unsigned)l0 << 2);
+                            // out-sweep (missing-coverage list, from the out pixel to the border) when this face
+                            // owns the in pixel
+                            if (cN != 0u && fi[l0 * fs0 + (d1_in - t1) * fs1] == fn) {
+                                const int lim = dir > 0 ? is - 1 : 0;
+                                const int ra = min(d1_out, lim), rc = max(d1_out, lim);
+                                bool ov = cN == RUN_OVERFLOW;
+                                if (!ov) {  // any run inside [ra, rc]?
+                                    const int first = (int)(srun[lN][l0][0].x & 0xffffu), last = (int)(srun[lN][l0][cN - 1].x >> 16);
+                                    ov = rc >= first && ra <= last;
+                                }
+                                if (ov) { has_out = true; ra_out = ra; rc_out = rc; cnt_out = cN; }
+                            }
+                            // in-sweep (from the in pixel to the opposite edge of the triangle)
+                            {
+                                const bool alpha_out = (__ldg(Ablock + l0 * W + (d1_out >> 5)) >> (d1_out & 31)) & 1u;
+                                const int ls = alpha_out ? lN : lP;
+                                const unsigned cs = alpha_out ? cN : cP;
+                                if (cs != 0u) {
                                     float c2;
-                                    if ((fd0 - o_p0d0) * (fd0 - o_p2d0) < 0.f) c2 = o_s02 * (fd0 - o_p0d0) + o_p0d1;
-                                    else c2 = o_s21 * (fd0 - o_p2d0) + o_p2d1;
-                                    const int lim = __float2int_rz(o_dir > 0 ? ceilf(c2) : floorf(c2));
-                                    ra = max(min(d1_in, lim), 0); rc = min(max(d1_in, lim), is - 1);
-                                }
-                                const unsigned cs = ls == lN ? cN : cP;
-                                if (ra > rc) continue;
-                                if (cs == RUN_OVERFLOW) {
-                                    // more runs than the list holds: walk the bit line (global memory)
-                                    const uint32_t *line = ((ls >> 1) ? m_col : m_row) +
-                                                           ((long)b * 2 * is + (ls >> 1 ? tx0 : ty0) + l0) * W + (ls & 1) * plane;
-                                    float a0 = 0.f, a1 = 0.f;
-                                    sweep(line, FULL, ra, rc, o_axis, d0, x, o_ka, o_p0d0, o_p1d0, ctx, a0, a1);
-                                    acc_add(&wacc[o][0], a0);
-                                    acc_add(&wacc[o][1], a1);
-                                    continue;
-                                }
-                                for (unsigned r = 0; r < cs; ++r) {
-                                    const uint2 run = srun[ls][l0][r];
-                                    const int s = max(ra, (int)(run.x & 0xffffu)), e = min(rc, (int)(run.x >> 16));
-                                    if (s > e) continue;
-                                    const unsigned se = (unsigned)s | ((unsigned)e << 16);
-                                    const int pos = atomicAdd(&wqn[warp], 1);
-                                    if (pos < WQCAP) {
-                                        q.x[pos] = x; q.G[pos] = __uint_as_float(run.y); q.se[pos] = se; q.meta[pos] = meta;
-                                    } else {  // queue full: evaluate in place
-                                        float a0, a1;
-                                        eval_queued(tt, x, __uint_as_float(run.y), se, meta, inv_is2, eps, a0, a1);
-                                        acc_add(&wacc[o][0], a0);
-                                        acc_add(&wacc[o][1], a1);
+                                    if ((fd0 - p0d0) * (fd0 - p2d0) < 0.f) c2 = s02 * (fd0 - p0d0) + p0d1;
+                                    else c2 = s21 * (fd0 - p2d0) + p2d1;
+                                    const int lim = __float2int_rz(dir > 0 ? ceilf(c2) : floorf(c2));
+                                    const int ra = max(min(d1_in, lim), 0), rc = min(max(d1_in, lim), is - 1);
+                                    bool ov = cs == RUN_OVERFLOW;
+                                    if (!ov) {
+                                        const int first = (int)(srun[ls][l0][0].x & 0xffffu), last = (int)(srun[ls][l0][cs - 1].x >> 16);
+                                        ov = rc >= first && ra <= last;
                                     }
+                                    if (ov && ra <= rc) { has_in = true; ra_in = ra; rc_in = rc; cnt_in = cs; ls_in = ls; }
                                 }
                             }
+                            if (has_out || has_in) { c0 = ka / (p1d0 - fd0); c1 = ka / (fd0 - p0d0); }
                         }
                     }
                 }
-                __syncwarp();
-                const int nq = min(wqn[warp], WQCAP);
-                if (nq > WQCAP - 48 || kb + NTHREADS >= total) {
-                    drain_queue(q, tt, nq, wacc, inv_is2, eps);
-                    __syncwarp();
-                    if (lane == 0) wqn[warp] = 0;
-                    __syncwarp();
-                }
+                push_sweep(has_out, x, c0, c1, lN, l0, cnt_out, ra_out, rc_out, hb);
+                push_sweep(has_in, x, c0, c1, ls_in, l0, cnt_in, ra_in, rc_in, hb);
             }
-            __syncthreads();
+            if (qn > 0) drain(qn);
+            if (mine_valid) {  // (shared-memory float adds are CAS loops; two per segment, hardly ever contended)
+                if (acc0 != 0.f) atomicAdd(&wacc[my_task][0], acc0);
+                if (acc1 != 0.f) atomicAdd(&wacc[my_task][1], acc1);
+            }
+        }
+        // ---- one global atomicAdd per face-vertex component and task
+        __syncthreads();
+        for (int task = threadIdx.x; task < ntasks; task += NTHREADS) {
+            const float acc0 = wacc[task][0], acc1 = wacc[task][1];
+            if (acc0 == 0.f && acc1 == 0.f) continue;
+            const int e = (task % 6) >> 1, axis = task & 1;
+            const int *vp = reinterpret_cast<const int *>(recs + sub[task / 6]) + 10;
             // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
-            const float acc0 = wacc[threadIdx.x][0], acc1 = wacc[threadIdx.x][1];
-            if (acc0 != 0.f) atomicAdd(grad_ndc + (long)vid0 * 3 + (1 - axis), acc0);
-            if (acc1 != 0.f) atomicAdd(grad_ndc + (long)vid1 * 3 + (1 - axis), acc1);
+            if (acc0 != 0.f) atomicAdd(grad_ndc + (long)__ldg(vp + e) * 3 + (1 - axis), acc0);
+            if (acc1 != 0.f) atomicAdd(grad_ndc + (long)__ldg(vp + (e + 1) % 3) * 3 + (1 - axis), acc1);
+        }
         }
     }
 }
@@ -1125,8 +1157,7 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
     if (B == 0 || F == 0) return HM_OK;
-    const size_t smem = (size_t)TILE * TILE * 4 + (size_t)2 * TILE * (is / 32) * 4 + NWARPS * sizeof(WarpQueue) +
-                        sizeof(TaskTable);
+    const size_t smem = (size_t)TILE * TILE * 4 + NWARPS * sizeof(SweepQueue);
     HM_UNSUPPORTED(is > 1024, "hm_raster_sil_bwd: raster size %d > 1024 is not supported", is);
     static size_t configured = 0;  // static + dynamic shared memory exceeds the 48 KB default: opt in once per size
     if (smem > configured) {
