@@ -918,27 +918,16 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 __syncwarp();
                 if (qn >= 32) drain(32);
             };
-            // queues the runs of list `ls`, line `l0` that a sweep over [ra, rc] visits (one item each)
-            auto push_sweep = [&](bool has, float x, float c0, float c1, int ls, int l0, unsigned cnt, int ra, int rc, unsigned hb) {
-                if (!__ballot_sync(FULL, has)) return;
-                const bool walk = cnt == RUN_OVERFLOW;
-                const int nr = has ? (walk ? 1 : (int)cnt) : 0;
-                const int rmax = __reduce_max_sync(FULL, nr);
-                for (int r = 0; r < rmax; ++r) {
-                    bool it = false;
-                    unsigned se = 0, meta = hb | (unsigned)ls;
-                    float G = 0.f;
-                    if (r < nr) {
-                        if (walk) {
-                            it = true; se = (unsigned)ra | ((unsigned)rc << 16); meta |= 1u << 10;
-                        } else {
-                            const uint2 run = srun[ls][l0][r];
-                            const int s = max(ra, (int)(run.x & 0xffffu)), e = min(rc, (int)(run.x >> 16));
-                            if (s <= e) { it = true; se = (unsigned)s | ((unsigned)e << 16); G = __uint_as_float(run.y); }
-                        }
-                    }
-                    push_item(it, x, c0, c1, G, se, meta);
+            // bit r of the result: run r of list `ls`, line `l0` has pixels inside [ra, rc] (bit 0 alone for a line
+            // whose run list overflowed: the sweep walks the bit line instead)
+            auto overlap_mask = [&](int ls, int l0, unsigned cnt, int ra, int rc) -> unsigned {
+                if (cnt == RUN_OVERFLOW) return 1u;
+                unsigned mk = 0;
+                for (unsigned r = 0; r < cnt; ++r) {
+                    const unsigned se = srun[ls][l0][r].x;
+                    if (rc >= (int)(se & 0xffffu) && ra <= (int)(se >> 16)) mk |= 1u << r;
                 }
+                return mk;
             };
 
             for (int k = 0; k < maxlen; ++k) {
@@ -962,12 +951,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                             if (cN != 0u && fi[l0 * fs0 + (d1_in - t1) * fs1] == fn) {
                                 const int lim = dir > 0 ? is - 1 : 0;
                                 const int ra = min(d1_out, lim), rc = max(d1_out, lim);
-                                bool ov = cN == RUN_OVERFLOW;
-                                if (!ov) {  // any run inside [ra, rc]?
-                                    const int first = (int)(srun[lN][l0][0].x & 0xffffu), last = (int)(srun[lN][l0][cN - 1].x >> 16);
-                                    ov = rc >= first && ra <= last;
-                                }
-                                if (ov) { has_out = true; ra_out = ra; rc_out = rc; cnt_out = cN; }
+                                has_out = true; ra_out = ra; rc_out = rc; cnt_out = cN;
                             }
                             // in-sweep (from the in pixel to the opposite edge of the triangle)
                             {
@@ -980,20 +964,39 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                                     else c2 = s21 * (fd0 - p2d0) + p2d1;
                                     const int lim = __float2int_rz(dir > 0 ? ceilf(c2) : floorf(c2));
                                     const int ra = max(min(d1_in, lim), 0), rc = min(max(d1_in, lim), is - 1);
-                                    bool ov = cs == RUN_OVERFLOW;
-                                    if (!ov) {
-                                        const int first = (int)(srun[ls][l0][0].x & 0xffffu), last = (int)(srun[ls][l0][cs - 1].x >> 16);
-                                        ov = rc >= first && ra <= last;
-                                    }
-                                    if (ov && ra <= rc) { has_in = true; ra_in = ra; rc_in = rc; cnt_in = cs; ls_in = ls; }
+                                    if (ra <= rc) { has_in = true; ra_in = ra; rc_in = rc; cnt_in = cs; ls_in = ls; }
                                 }
                             }
-                            if (has_out || has_in) { c0 = ka / (p1d0 - fd0); c1 = ka / (fd0 - p0d0); }
+                            if (has_out || has_in) { c0 = __fdividef(ka, p1d0 - fd0); c1 = __fdividef(ka, fd0 - p0d0); }
                         }
                     }
                 }
-                push_sweep(has_out, x, c0, c1, lN, l0, cnt_out, ra_out, rc_out, hb);
-                push_sweep(has_in, x, c0, c1, ls_in, l0, cnt_in, ra_in, rc_in, hb);
+                // runs to visit: bits 0-7 out-sweep, 8-15 in-sweep; one (crossing, run) item per lane and round
+                unsigned todo = 0;
+                if (has_out) todo = overlap_mask(lN, l0, cnt_out, ra_out, rc_out);
+                if (has_in) todo |= overlap_mask(ls_in, l0, cnt_in, ra_in, rc_in) << 8;
+                while (__any_sync(FULL, todo != 0u)) {
+                    bool it = false;
+                    unsigned se = 0, meta = 0;
+                    float G = 0.f;
+                    if (todo) {
+                        const int bit = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const bool in_sw = bit >= 8;
+                        const int r = bit & 7, ls = in_sw ? ls_in : lN;
+                        const int ra = in_sw ? ra_in : ra_out, rc = in_sw ? rc_in : rc_out;
+                        it = true;
+                        meta = hb | (unsigned)ls;
+                        if ((in_sw ? cnt_in : cnt_out) == RUN_OVERFLOW) {
+                            se = (unsigned)ra | ((unsigned)rc << 16); meta |= 1u << 10;
+                        } else {
+                            const uint2 run = srun[ls][l0][r];
+                            se = (unsigned)max(ra, (int)(run.x & 0xffffu)) | ((unsigned)min(rc, (int)(run.x >> 16)) << 16);
+                            G = __uint_as_float(run.y);
+                        }
+                    }
+                    push_item(it, x, c0, c1, G, se, meta);
+                }
             }
             if (qn > 0) drain(qn);
             if (mine_valid) {  // (shared-memory float adds are CAS loops; two per segment, hardly ever contended)
