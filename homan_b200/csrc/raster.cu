@@ -25,7 +25,9 @@ struct __align__(16) FaceRec {
     short bb[4];  // pixel bbox x0 y0 x1 y1 (clamped), empty when x0 > x1
     int pad;
     float inv[9];  // barycentric matrix in pixel coordinates, already divided by its determinant
-    float pad2[7];
+    float iz[3];   // 1 / z of the three corners (fast depth of the forward pass)
+    int exact;     // 1: some corner depth is not a plain positive float -> forward uses the reference arithmetic only
+    float pad2[3];
 };
 static_assert(sizeof(FaceRec) == HM_FACE_RECORD_BYTES, "record size");
 
@@ -167,8 +169,14 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
         const float den = p20 * (p01 - p11) + p00 * (p11 - p21) + p10 * (p21 - p01);
 #pragma unroll
         for (int k = 0; k < 9; ++k) r.inv[k] = m[k] / den;
+        r.exact = 0;
 #pragma unroll
-        for (int k = 0; k < 7; ++k) r.pad2[k] = 0.f;
+        for (int k = 0; k < 3; ++k) {
+            const float z = r.c[3 * k + 2];
+            r.iz[k] = 1.f / z;
+            if (!(z > 1e-20f && z < 1e20f)) r.exact = 1;
+            r.pad2[k] = 0.f;
+        }
     }
     recs[i] = r;
     FaceBox bx;
@@ -243,24 +251,96 @@ __device__ __forceinline__ int next_batch(const FaceBox *__restrict__ boxes, int
 }
 
 // ------------------------------------------------------------------------------------------ forward
+// Depth of the winner search. The reference evaluates, per covered sample, zp = 1 / (w0/ws/z0 + w1/ws/z1 + w2/ws/z2)
+// with seven IEEE divisions. The kernel ranks samples with zp~ = ws / (w0*iz0 + w1*iz1 + w2*iz2) (one MUFU.RCP), which
+// is within a few ulp of the reference value, and records as AMBIGUOUS every pixel at which two samples (or a sample
+// and the near / far planes) came within AMB ulp of each other: only those pixels can rank differently under the
+// reference arithmetic, and they are re-resolved from scratch with it after the main passes. face_index is
+// therefore bit-exact while the common sample costs ~40 instructions instead of ~200.
+constexpr unsigned AMB = 48;   // ulp; the two evaluation orders differ by < 8 ulp each
+constexpr int HZ = 4;          // hierarchical-z block edge (pixels)
+constexpr int HZN = TILE / HZ;
+constexpr int AMBCAP = NWARPS * 64;
+constexpr int FCH = 64;        // face records staged in shared memory at a time
+
+__device__ __forceinline__ bool ulp_close(unsigned a, unsigned b) {
+    const unsigned d = a > b ? a - b : b - a;
+    return d <= AMB;
+}
+
+// The reference's per-sample arithmetic (oracle/csrc/nmr_raster.c), individually rounded operations.
+__device__ __forceinline__ float exact_depth(const float *inv, int xi, int yi, float z0, float z1, float z2) {
+    float w0 = inv[0] * xi + inv[1] * yi + inv[2];
+    float w1 = inv[3] * xi + inv[4] * yi + inv[5];
+    float w2 = inv[6] * xi + inv[7] * yi + inv[8];
+    w0 = fminf(fmaxf(w0, 0.f), 1.f);
+    w1 = fminf(fmaxf(w1, 0.f), 1.f);
+    w2 = fminf(fmaxf(w2, 0.f), 1.f);
+    const float ws = w0 + w1 + w2;
+    w0 /= ws; w1 /= ws; w2 /= ws;
+    return 1.f / (w0 / z0 + w1 / z1 + w2 / z2);
+}
+
+// Coverage of one raster row by one edge. The reference skips a sample when A < (xp - xk) * eky with
+// A = (yp - yk) * ekx (each operation rounded). For a fixed row the right-hand side is a monotone function of the
+// pixel index (rounding is monotone), so the samples that pass form a prefix (eky > 0), a suffix (eky < 0) or all /
+// none (eky == 0) of the row: the boundary is located from the analytic crossing and pinned with the reference
+// predicate itself, which makes the interval exact without testing every sample.
+struct RowCtx {
+    int is;
+    bool pow2;
+    float inv_is;
+};
+__device__ __forceinline__ bool edge_pass(const RowCtx &rc, float A, float xk, float eky, int xi) {
+    const float xp = rc.pow2 ? (float)(2 * xi + 1 - rc.is) * rc.inv_is : (float)(2 * xi + 1 - rc.is) / (float)rc.is;
+    return !(A < (xp - xk) * eky);
+}
+__device__ __forceinline__ void clip_edge(const RowCtx &rc, float A, float xk, float eky, int X0, int X1, int &lo,
+                                          int &hi) {
+    if (eky > 0.f) {
+        const float est = to_pix(xk + __fdividef(A, eky), rc.is);
+        int c = (est == est) ? __float2int_rz(fminf(fmaxf(floorf(est), (float)(X0 - 1)), (float)X1)) : X1;
+        while (c < X1 && edge_pass(rc, A, xk, eky, c + 1)) ++c;
+        while (c >= X0 && !edge_pass(rc, A, xk, eky, c)) --c;
+        hi = min(hi, c);
+    } else if (eky < 0.f) {
+        const float est = to_pix(xk + __fdividef(A, eky), rc.is);
+        int c = (est == est) ? __float2int_rz(fminf(fmaxf(ceilf(est), (float)X0), (float)(X1 + 1))) : X0;
+        while (c > X0 && edge_pass(rc, A, xk, eky, c - 1)) --c;
+        while (c <= X1 && !edge_pass(rc, A, xk, eky, c)) ++c;
+        lo = max(lo, c);
+    } else if (eky == 0.f) {
+        if (A < 0.f) { lo = 1; hi = 0; }  // (xp - xk) * (+-0) = +-0
+    }  // NaN slope: the comparison is false for every sample, all pass
+}
+
 __global__ void __launch_bounds__(NTHREADS)
 raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ boxes, int F, int is, int aa,
                   float near_, float far_, int32_t *__restrict__ face_index, float *__restrict__ alpha,
                   uint32_t *__restrict__ cov_row, uint32_t *__restrict__ cov_col) {
-    __shared__ unsigned long long keys[TILE * TILE];
+    __shared__ __align__(16) unsigned long long keys[TILE * TILE];
     __shared__ int list[LISTCAP];
     __shared__ int cnt, next;
     __shared__ uint32_t roww[TILE][2];
-    __shared__ unsigned short pixq[NWARPS][64];
+    __shared__ uint32_t amb[TILE][2];   // ambiguous pixels (see above)
+    __shared__ int n_amb;
+    __shared__ unsigned hiz[HZN * HZN];  // per 4x4 block: largest winning depth so far (far when a pixel is empty)
+    __shared__ unsigned short ambl[AMBCAP];
+    __shared__ __align__(16) float4 srec[FCH][8];  // staged face records
     __shared__ short spanx[NWARPS][64], spanpre[NWARPS][64];
     const int b = blockIdx.y;
     const int tiles_x = is / TILE;
     const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
     const int lane = threadIdx.x & 31;
-    const bool pow2 = (is & (is - 1)) == 0;
-    const float inv_is = 1.f / (float)is;
-    const unsigned long long empty = ((unsigned long long)__float_as_uint(far_) << 32) | 0xffffffffull;
-    for (int i = threadIdx.x; i < TILE * TILE; i += NTHREADS) keys[i] = empty;
+    RowCtx rc;
+    rc.is = is; rc.pow2 = (is & (is - 1)) == 0; rc.inv_is = 1.f / (float)is;
+    const bool pow2 = rc.pow2;
+    const float inv_is = rc.inv_is;
+    const unsigned near_bits = __float_as_uint(near_), far_bits = __float_as_uint(far_);
+    const unsigned long long empty = ((unsigned long long)far_bits << 32) | 0xffffffffull;
+    for (int i = threadIdx.x; i < TILE * TILE / 2; i += NTHREADS)
+        reinterpret_cast<ulonglong2 *>(keys)[i] = make_ulonglong2(empty, empty);
+    if (threadIdx.x < 2 * TILE) (&amb[0][0])[threadIdx.x] = 0u;
     recs += (long)b * F;
     boxes += (long)b * F;
 
@@ -268,18 +348,35 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     while (base < F) {
         const int n = next_batch(boxes, base, F, tx0, ty0, list, &cnt, &next);
         // two passes: faces kept in their original winding (the outer layer of an outward-wound closed mesh)
-        // first, the reversed copies second, so that early z culls the hidden layer before its depth maths
-        for (;;) {  // warps pull (pass, face) pairs off the list
-            int li0 = 0;
-            if (lane == 0) li0 = atomicAdd(&next, 1);
-            li0 = __shfl_sync(0xffffffffu, li0, 0);
-            if (li0 >= 2 * n) break;
-            const int pass = li0 >= n ? 1 : 0, li = li0 - pass * n;
-            const FaceRec *rp = recs + list[li];
-            const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rp));
-            const float4 q1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
-            const float4 q2 = __ldg(reinterpret_cast<const float4 *>(rp) + 2);
-            const int4 q3 = __ldg(reinterpret_cast<const int4 *>(rp) + 3);
+        // first, the reversed copies second. Between them the winners are summarised per 4x4 block, so that a
+        // hidden-layer face is dropped with one comparison per block instead of one per sample.
+        for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            __syncthreads();
+            hiz[threadIdx.x] = 0u;
+            __syncthreads();
+            for (int k = 0; k < TILE * TILE / NTHREADS; ++k) {  // 256 keys = 4 rows = one row of blocks, conflict-free
+                unsigned m = (unsigned)(keys[k * NTHREADS + threadIdx.x] >> 32);
+                m = max(m, __shfl_xor_sync(0xffffffffu, m, 1));
+                m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
+                if ((lane & 3) == 0) atomicMax(&hiz[k * HZN + (threadIdx.x % TILE) / HZ], m);
+            }
+            __syncthreads();
+        }
+        for (int c0 = 0; c0 < n; c0 += FCH) {
+        // ---- the records of the next FCH listed faces go to shared memory with one cooperative load (a warp
+        //      walking its faces one dependent global load at a time is bound by L2 latency)
+        const int cn = min(FCH, n - c0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < cn * 8; i += NTHREADS)
+            srec[i >> 3][i & 7] = __ldg(reinterpret_cast<const float4 *>(recs + list[c0 + (i >> 3)]) + (i & 7));
+        __syncthreads();
+        for (int j = threadIdx.x >> 5; j < cn; j += NWARPS) {  // faces dealt round-robin to the warps
+            const float4 *rp = srec[j];
+            const float4 q2 = rp[2];
+            if ((__float_as_int(q2.y) >= F ? 1 : 0) != pass) continue;
+            const float4 q0 = rp[0], q1 = rp[1];
+            const int4 q3 = *reinterpret_cast<const int4 *>(rp + 3);
             const float f0 = q0.x, f1 = q0.y, f2 = q0.z, f3 = q0.w, f4 = q1.x, f5 = q1.y, f6 = q1.z, f7 = q1.w,
                         f8 = q2.x;
             const int fn = __float_as_int(q2.y);
@@ -295,33 +392,34 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             // nearest corner (minus rounding slack) is behind the current winner of a pixel cannot win it
             const float zmin = fminf(fminf(f2, f5), f8);
             const unsigned zmin_bits = zmin > 0.f ? __float_as_uint(zmin * (1.f - 1e-5f)) : 0u;
-            // Candidate pixels: per row of the bbox, the conservative x-span of the triangle (each edge bounds x
-            // from one side), flattened over the lanes through a prefix sum of the span lengths - slivers and
-            // diagonal faces cost their area, not their bounding box. The exact test below decides coverage.
+            if (pass == 1) {
+                const int hx0 = (X0 - tx0) / HZ, hx1 = (X1 - tx0) / HZ, hy0 = (Y0 - ty0) / HZ, hy1 = (Y1 - ty0) / HZ;
+                const int hx = hx0 + (lane & (HZN - 1));  // lanes: 16 block columns x 2 block rows
+                bool vis = false;
+                if (hx <= hx1)
+                    for (int hy = hy0 + (lane >> 4); hy <= hy1; hy += 2) vis |= !(zmin_bits > hiz[hy * HZN + hx]);
+                if (!__any_sync(0xffffffffu, vis)) continue;
+            }
+            // Covered pixels: per row of the bbox the exact interval of samples inside the triangle (clip_edge), then
+            // the pixels of all rows flattened over the lanes through a prefix sum of the interval lengths -
+            // slivers and diagonal faces cost their area, not their bounding box, and no sample is tested twice.
             short *rowx = spanx[threadIdx.x >> 5], *rowpre = spanpre[threadIdx.x >> 5];
             int n_px;
             {
-                int len[2], xlo[2];
+                int len[2] = {0, 0}, xlo[2] = {X0, X0};
 #pragma unroll
                 for (int half = 0; half < 2; ++half) {
+                    if (half == 1 && h <= 32) break;  // (warp-uniform)
                     const int r = lane + 32 * half;
-                    len[half] = 0; xlo[half] = X0;
                     if (r < h) {
                         const int yi = Y0 + r;
                         const float yp = pow2 ? (float)(2 * yi + 1 - is) * inv_is : (float)(2 * yi + 1 - is) / (float)is;
-                        float lo = -3.0e38f, hi = 3.0e38f;
-                        bool empty = false;
-                        const float c0 = (yp - f1) * e0x, c1 = (yp - f4) * e1x, c2 = (yp - f7) * e2x;
-                        if (e0y > 0.f) hi = fminf(hi, f0 + __fdividef(c0, e0y)); else if (e0y < 0.f) lo = fmaxf(lo, f0 + __fdividef(c0, e0y)); else empty |= c0 < -1e-6f;
-                        if (e1y > 0.f) hi = fminf(hi, f3 + __fdividef(c1, e1y)); else if (e1y < 0.f) lo = fmaxf(lo, f3 + __fdividef(c1, e1y)); else empty |= c1 < -1e-6f;
-                        if (e2y > 0.f) hi = fminf(hi, f6 + __fdividef(c2, e2y)); else if (e2y < 0.f) lo = fmaxf(lo, f6 + __fdividef(c2, e2y)); else empty |= c2 < -1e-6f;
-                        // NaN bounds (degenerate edges) fall back to the whole row
-                        int a = X0, c = X1;
-                        const float plo = to_pix(lo, is), phi = to_pix(hi, is);
-                        if (plo == plo) a = max(X0, __float2int_rz(fminf(fmaxf(ceilf(plo) - 1.f, -1.f), 70000.f)));
-                        if (phi == phi) c = min(X1, __float2int_rz(fminf(fmaxf(floorf(phi) + 1.f, -1.f), 70000.f)));
-                        xlo[half] = a;
-                        len[half] = empty ? 0 : max(c - a + 1, 0);
+                        int lo = X0, hi = X1;
+                        clip_edge(rc, (yp - f1) * e0x, f0, e0y, X0, X1, lo, hi);
+                        clip_edge(rc, (yp - f4) * e1x, f3, e1y, X0, X1, lo, hi);
+                        clip_edge(rc, (yp - f7) * e2x, f6, e2y, X0, X1, lo, hi);
+                        xlo[half] = lo;
+                        len[half] = max(hi - lo + 1, 0);
                     }
                 }
                 int inc0 = len[0], inc1 = len[1];
@@ -337,87 +435,128 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 n_px = tot0 + tot1;
                 __syncwarp();
             }
-            if (n_px == 0) continue;  // the bounding box touches the tile, the triangle does not
-            // barycentric matrix in pixel coordinates, prepared once per face by the setup kernel
-            float inv[9];
+            if (n_px == 0) continue;  // the bounding box touches the tile, the triangle covers no sample of it
+            // barycentric matrix in pixel coordinates and corner 1/z, prepared once per face by the setup kernel
+            float inv[9], iz0, iz1, iz2;
+            int exact_face;
             {
-                const float4 i0 = __ldg(reinterpret_cast<const float4 *>(rp) + 4);
-                const float4 i1 = __ldg(reinterpret_cast<const float4 *>(rp) + 5);
+                const float4 i0 = rp[4], i1 = rp[5], i2 = rp[6];
                 inv[0] = i0.x; inv[1] = i0.y; inv[2] = i0.z; inv[3] = i0.w;
                 inv[4] = i1.x; inv[5] = i1.y; inv[6] = i1.z; inv[7] = i1.w;
-                inv[8] = __ldg(reinterpret_cast<const float *>(rp) + 24);
+                inv[8] = i2.x; iz0 = i2.y; iz1 = i2.z; iz2 = i2.w;
+                exact_face = __float_as_int(rp[7].x);
             }
-            // Inside pixels are compacted into a per-warp queue so that the depth maths (7 IEEE divisions) runs
-            // on full warps.
-            unsigned short *pq = pixq[threadIdx.x >> 5];
-            int qn = 0;
-            for (int i0 = 0; i0 < n_px || qn > 0; i0 += 32) {
-                bool in = false;
-                unsigned packed = 0;
-                const int i = i0 + lane;
-                if (i < n_px) {
-                    int row = 0;
+            for (int i = lane; i < n_px; i += 32) {
+                int row = 0;
+                if (h > 32 && rowpre[32] <= i) row = 32;
 #pragma unroll
-                    for (int sft = 32; sft > 0; sft >>= 1)
-                        if (row + sft < h && rowpre[row + sft] <= i) row += sft;
-                    const int xi = rowx[row] + (i - rowpre[row]), yi = Y0 + row;
-                    // (2i + 1 - is) / is: for a power-of-two raster the division is an exact scaling
+                for (int sft = 16; sft > 0; sft >>= 1)
+                    if (row + sft < h && rowpre[row + sft] <= i) row += sft;
+                const int xi = rowx[row] + (i - rowpre[row]), yi = Y0 + row;
+                const int xl = xi - tx0, yl = yi - ty0;
+                unsigned long long *kp = &keys[yl * TILE + xl];
+                const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
+                if (zmin_bits > (unsigned)(cur >> 32)) continue;
+                float zp;
+                if (exact_face) {
+                    zp = exact_depth(inv, xi, yi, f2, f5, f8);
+                } else {
+                    float w0 = inv[0] * xi + inv[1] * yi + inv[2];
+                    float w1 = inv[3] * xi + inv[4] * yi + inv[5];
+                    float w2 = inv[6] * xi + inv[7] * yi + inv[8];
+                    w0 = fminf(fmaxf(w0, 0.f), 1.f);
+                    w1 = fminf(fmaxf(w1, 0.f), 1.f);
+                    w2 = fminf(fmaxf(w2, 0.f), 1.f);
+                    zp = __fdividef(w0 + w1 + w2, w0 * iz0 + w1 * iz1 + w2 * iz2);
+                }
+                const unsigned zb = __float_as_uint(zp);
+                bool flag = ulp_close(zb, near_bits) || ulp_close(zb, far_bits);
+                if (zp > near_ && zp < far_) {  // also rejects NaN
+                    const unsigned long long key = ((unsigned long long)zb << 32) | (unsigned)fn;
+                    unsigned long long seen = cur;
+                    if (key < cur) seen = atomicMin(kp, key);
+                    flag |= ((unsigned)seen != 0xffffffffu) && ulp_close(zb, (unsigned)(seen >> 32));
+                }
+                if (flag) atomicOr(&amb[yl][xl >> 5], 1u << (xl & 31));
+            }
+            __syncwarp();  // rowx / rowpre are rewritten by the next face
+        }
+        }
+        }
+    }
+
+    // ---- ambiguous pixels: start over with the reference arithmetic, against every face of the image
+    __syncthreads();
+    const int any_amb = __syncthreads_or(threadIdx.x < 2 * TILE && (&amb[0][0])[threadIdx.x] != 0u);
+    for (; any_amb;) {
+        __syncthreads();
+        if (threadIdx.x == 0) n_amb = 0;
+        __syncthreads();
+        if (threadIdx.x < 2 * TILE) {
+            unsigned word = (&amb[0][0])[threadIdx.x];
+            while (word) {
+                const int bit = __ffs(word) - 1;
+                const int pos = atomicAdd(&n_amb, 1);
+                if (pos >= AMBCAP) break;
+                word &= word - 1;
+                const int yl = threadIdx.x >> 1, xl = (threadIdx.x & 1) * 32 + bit;
+                ambl[pos] = (unsigned short)(xl | (yl << 6));
+                keys[yl * TILE + xl] = empty;
+            }
+            (&amb[0][0])[threadIdx.x] = word;
+        }
+        __syncthreads();
+        const int total = n_amb;
+        const int na = min(total, AMBCAP);
+        if (na == 0) break;
+        int base2 = 0;
+        while (base2 < F) {
+            const int n = next_batch(boxes, base2, F, tx0, ty0, list, &cnt, &next);
+            for (int li = threadIdx.x >> 5; li < n; li += NWARPS) {
+                const FaceRec *rp = recs + list[li];
+                const int fn = __ldg(reinterpret_cast<const int *>(rp) + 9);
+                if (fn < 0) continue;
+                float f[9], inv[9];
+#pragma unroll
+                for (int k = 0; k < 9; ++k) { f[k] = __ldg(reinterpret_cast<const float *>(rp) + k); inv[k] = __ldg(reinterpret_cast<const float *>(rp) + 16 + k); }
+                const int q = __ldg(reinterpret_cast<const int *>(rp) + 13), q2 = __ldg(reinterpret_cast<const int *>(rp) + 14);
+                const int bx0 = (short)(q & 0xffff), by0 = (short)(q >> 16), bx1 = (short)(q2 & 0xffff), by1 = (short)(q2 >> 16);
+                for (int j = lane; j < na; j += 32) {
+                    const unsigned e = ambl[j];
+                    const int xl = e & 63u, yl = e >> 6;
+                    const int xi = tx0 + xl, yi = ty0 + yl;
+                    if (xi < bx0 || xi > bx1 || yi < by0 || yi > by1) continue;
                     const float yp = pow2 ? (float)(2 * yi + 1 - is) * inv_is : (float)(2 * yi + 1 - is) / (float)is;
                     const float xp = pow2 ? (float)(2 * xi + 1 - is) * inv_is : (float)(2 * xi + 1 - is) / (float)is;
-                    in = !((yp - f1) * e0x < (xp - f0) * e0y) && !((yp - f4) * e1x < (xp - f3) * e1y) &&
-                         !((yp - f7) * e2x < (xp - f6) * e2y);
-                    packed = (unsigned)(xi - tx0) | ((unsigned)(yi - ty0) << 6);
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, in);
-                if (in) pq[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)packed;
-                qn += __popc(m);
-                __syncwarp();
-                if (qn >= 32 || (i0 + 32 >= n_px && qn > 0)) {
-                    const int take = min(qn, 32);
-                    if (lane < take) {
-                        const unsigned e = pq[lane];
-                        const int xl = e & 63u, yl = e >> 6;
-                        const int xi = tx0 + xl, yi = ty0 + yl;
-                        unsigned long long *kp = &keys[yl * TILE + xl];
-                        const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
-                        if (!(zmin_bits > (unsigned)(cur >> 32))) {
-                            float w0 = inv[0] * xi + inv[1] * yi + inv[2];
-                            float w1 = inv[3] * xi + inv[4] * yi + inv[5];
-                            float w2 = inv[6] * xi + inv[7] * yi + inv[8];
-                            w0 = fminf(fmaxf(w0, 0.f), 1.f);
-                            w1 = fminf(fmaxf(w1, 0.f), 1.f);
-                            w2 = fminf(fmaxf(w2, 0.f), 1.f);
-                            const float ws = w0 + w1 + w2;
-                            w0 /= ws; w1 /= ws; w2 /= ws;
-                            const float zp = 1.f / (w0 / f2 + w1 / f5 + w2 / f8);
-                            if (zp > near_ && zp < far_) {  // also rejects NaN
-                                const unsigned long long key = ((unsigned long long)__float_as_uint(zp) << 32) | (unsigned)fn;
-                                if (key < cur) atomicMin(kp, key);
-                            }
-                        }
-                    }
-                    const int rem = qn - take;
-                    const unsigned short carry = (lane < rem) ? pq[32 + lane] : (unsigned short)0;
-                    __syncwarp();
-                    if (lane < rem) pq[lane] = carry;
-                    qn = rem;
-                    __syncwarp();
+                    if ((yp - f[1]) * (f[3] - f[0]) < (xp - f[0]) * (f[4] - f[1])) continue;
+                    if ((yp - f[4]) * (f[6] - f[3]) < (xp - f[3]) * (f[7] - f[4])) continue;
+                    if ((yp - f[7]) * (f[0] - f[6]) < (xp - f[6]) * (f[1] - f[7])) continue;
+                    const float zp = exact_depth(inv, xi, yi, f[2], f[5], f[8]);
+                    if (zp > near_ && zp < far_)
+                        atomicMin(&keys[yl * TILE + xl], ((unsigned long long)__float_as_uint(zp) << 32) | (unsigned)fn);
                 }
             }
         }
+        if (total <= AMBCAP) break;
     }
     __syncthreads();
 
-    // ---- write-out: face_index rows (coalesced), coverage words
-    for (int i = threadIdx.x; i < TILE * TILE; i += NTHREADS) {
-        const int yl = i / TILE, xl = i % TILE;
-        const unsigned lo = (unsigned)(keys[i] & 0xffffffffull);
-        const bool cov = lo != 0xffffffffu;
-        face_index[((long)b * is + (ty0 + yl)) * is + tx0 + xl] = cov ? (int)lo : -1;
-        const unsigned m = __ballot_sync(0xffffffffu, cov);
-        if (lane == 0) {
-            roww[yl][xl >> 5] = m;
-            if (cov_row) cov_row[((long)b * is + (ty0 + yl)) * (is / 32) + ((tx0 + xl) >> 5)] = m;
+    // ---- write-out: face_index rows (four pixels per thread, 16-byte stores), coverage words
+    for (int i = threadIdx.x; i < TILE * TILE / 4; i += NTHREADS) {
+        const int yl = i / (TILE / 4), x4 = i % (TILE / 4);  // a warp covers two rows of the tile
+        const ulonglong2 k01 = *reinterpret_cast<const ulonglong2 *>(&keys[4 * i]);
+        const ulonglong2 k23 = *reinterpret_cast<const ulonglong2 *>(&keys[4 * i + 2]);
+        const int4 fi4 = make_int4((int)(unsigned)k01.x, (int)(unsigned)k01.y, (int)(unsigned)k23.x, (int)(unsigned)k23.y);
+        *reinterpret_cast<int4 *>(face_index + ((long)b * is + (ty0 + yl)) * is + tx0 + 4 * x4) = fi4;  // empty = -1
+        unsigned nib = (fi4.x != -1 ? 1u : 0u) | (fi4.y != -1 ? 2u : 0u) | (fi4.z != -1 ? 4u : 0u) | (fi4.w != -1 ? 8u : 0u);
+        nib <<= 4 * (lane & 7);  // eight consecutive lanes make one 32-pixel word
+        nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
+        nib |= __shfl_xor_sync(0xffffffffu, nib, 2);
+        nib |= __shfl_xor_sync(0xffffffffu, nib, 4);
+        if ((lane & 7) == 0) {
+            const int w = x4 >> 3;
+            roww[yl][w] = nib;
+            if (cov_row) cov_row[((long)b * is + (ty0 + yl)) * (is / 32) + (tx0 >> 5) + w] = nib;
         }
     }
     __syncthreads();
@@ -629,8 +768,14 @@ __device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, 
 }
 
 constexpr int BWD_LISTCAP = 1024;
-constexpr int BWD_SUB = 128;  // faces whose tasks are sorted and processed together
-constexpr int SEG = 8;        // scan-lines one thread walks
+#ifndef HM_BWD_SUB
+#define HM_BWD_SUB 128
+#endif
+#ifndef HM_SEG
+#define HM_SEG 8
+#endif
+constexpr int BWD_SUB = HM_BWD_SUB;  // faces whose tasks are sorted and processed together
+constexpr int SEG = HM_SEG;          // scan-lines one thread walks
 constexpr int SQCAP = 64;  // per-warp queue of (crossing, run) items
 
 // A queued (crossing, run) item: crossing position x on its scan-line, the two distance coefficients of the
