@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(NTHREADS)
 raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ boxes, int F, int is, int aa,
                   float near_, float far_, int32_t *__restrict__ face_index, float *__restrict__ alpha,
                   uint32_t *__restrict__ cov_row, uint32_t *__restrict__ cov_col) {
-    __shared__ __align__(16) unsigned long long keys[TILE * TILE];
+    extern __shared__ __align__(16) unsigned long long keys[];  // [TILE * TILE] z-buffer (dynamic: static + this > 48 KB)
     __shared__ int list[LISTCAP];
     __shared__ int cnt, next;
     __shared__ uint32_t roww[TILE][2];
@@ -771,6 +771,9 @@ constexpr int BWD_LISTCAP = 1024;
 #ifndef HM_BWD_SUB
 #define HM_BWD_SUB 128
 #endif
+#ifndef HM_DIRECT_ATOMICS
+#define HM_DIRECT_ATOMICS 1
+#endif
 #ifndef HM_SEG
 #define HM_SEG 8
 #endif
@@ -793,16 +796,12 @@ struct TaskParams {
     float p0d0, p0d1, p1d0, p2d0, p2d1, slope, slope02, slope21, ka;
     int fn, dir, lo, len, axis, vid0, vid1;
 };
-__device__ __forceinline__ TaskParams task_params(const FaceRec *__restrict__ recs, const int *list, int task, int is,
-                                                  int tx0, int ty0) {
+__device__ __forceinline__ TaskParams task_params(const float4 *rp, int task, int is, int tx0, int ty0) {
     TaskParams p;
     const int e = (task % 6) >> 1;
     p.axis = task & 1;
-    const FaceRec *rp = recs + list[task / 6];
-    const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rp));
-    const float4 q1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1);
-    const float4 q2 = __ldg(reinterpret_cast<const float4 *>(rp) + 2);
-    const int4 q3 = __ldg(reinterpret_cast<const int4 *>(rp) + 3);
+    const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
+    const int4 q3 = *reinterpret_cast<const int4 *>(rp + 3);
     p.fn = __float_as_int(q2.y);
     const int v0 = __float_as_int(q2.z), v1 = __float_as_int(q2.w), v2 = q3.x;
     // pixel-space corners along (d0, d1) = (x, y) for axis 0, (y, x) for axis 1
@@ -891,7 +890,11 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     __shared__ int hist[TILE + 2], hpos[TILE + 2];
     __shared__ unsigned char slen[6 * BWD_SUB];                 // scan-lines of every task of the sub-batch
     __shared__ unsigned short sorted[6 * BWD_SUB * (TILE / SEG)];  // segments (task | index << 12), longest first
+#if HM_DIRECT_ATOMICS
+    __shared__ __align__(16) float4 srec[BWD_SUB][4];            // first 64 bytes of the sub-batch's face records
+#else
     __shared__ float wacc[6 * BWD_SUB][2];                       // per-task sums of the sub-batch
+#endif
     __shared__ __align__(8) uint64_t bar;
     const int W = is / 32;
     // dynamic shared memory: face_index tile | per-warp queues
@@ -978,10 +981,19 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
         __syncthreads();
         if (threadIdx.x < SEG + 2) hist[threadIdx.x] = 0;
         if (threadIdx.x == 0) next = 0;
+#if HM_DIRECT_ATOMICS
+        for (int i = threadIdx.x; i < ntasks / 6 * 4; i += NTHREADS)
+            srec[i >> 2][i & 3] = __ldg(reinterpret_cast<const float4 *>(recs + sub[i >> 2]) + (i & 3));
+#else
         for (int i = threadIdx.x; i < 2 * ntasks; i += NTHREADS) (&wacc[0][0])[i] = 0.f;
+#endif
         __syncthreads();
         for (int task = threadIdx.x; task < ntasks; task += NTHREADS) {
-            const int len = task_params(recs, sub, task, is, tx0, ty0).len;
+            #if HM_DIRECT_ATOMICS
+            const int len = task_params(srec[task / 6], task, is, tx0, ty0).len;
+#else
+            const int len = task_params(reinterpret_cast<const float4 *>(recs + sub[task / 6]), task, is, tx0, ty0).len;
+#endif
             slen[task] = (unsigned char)len;
             if (len >= SEG) atomicAdd(&hist[SEG], len / SEG);
             if (len % SEG) atomicAdd(&hist[len % SEG], 1);
@@ -1013,7 +1025,11 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             const bool mine_valid = g * 32 + lane < nwork;
             const unsigned seg_id = sorted[min(g * 32 + lane, nwork - 1)];
             const int my_task = seg_id & 0xfffu, seg_lo = (int)(seg_id >> 12) * SEG;
-            const TaskParams tp = task_params(recs, sub, my_task, is, tx0, ty0);
+#if HM_DIRECT_ATOMICS
+            const TaskParams tp = task_params(srec[my_task / 6], my_task, is, tx0, ty0);
+#else
+            const TaskParams tp = task_params(reinterpret_cast<const float4 *>(recs + sub[my_task / 6]), my_task, is, tx0, ty0);
+#endif
             // ---- this thread's task
             const float p0d0 = tp.p0d0, p0d1 = tp.p0d1, p1d0 = tp.p1d0, p2d0 = tp.p2d0, p2d1 = tp.p2d1;
             const float slope = tp.slope, s02 = tp.slope02, s21 = tp.slope21, ka = tp.ka;
@@ -1144,6 +1160,14 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 }
             }
             if (qn > 0) drain(qn);
+#if HM_DIRECT_ATOMICS
+            if (mine_valid) {
+                // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
+                if (acc0 != 0.f) atomicAdd(grad_ndc + (long)tp.vid0 * 3 + (1 - axis), acc0);
+                if (acc1 != 0.f) atomicAdd(grad_ndc + (long)tp.vid1 * 3 + (1 - axis), acc1);
+            }
+        }
+#else
             if (mine_valid) {  // (shared-memory float adds are CAS loops; two per segment, hardly ever contended)
                 if (acc0 != 0.f) atomicAdd(&wacc[my_task][0], acc0);
                 if (acc1 != 0.f) atomicAdd(&wacc[my_task][1], acc1);
@@ -1160,6 +1184,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             if (acc0 != 0.f) atomicAdd(grad_ndc + (long)__ldg(vp + e) * 3 + (1 - axis), acc0);
             if (acc1 != 0.f) atomicAdd(grad_ndc + (long)__ldg(vp + (e + 1) % 3) * 3 + (1 - axis), acc1);
         }
+#endif
         }
     }
 }
@@ -1266,7 +1291,17 @@ int hm_raster_sil_fwd(const void *records, const void *bboxes, int B, int F, int
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
     if (B == 0) return HM_OK;
     dim3 grid((is / TILE) * (is / TILE), B);
-    raster_fwd_kernel<<<grid, NTHREADS, 0, hm_stream(stream)>>>(
+    const int fwd_smem = TILE * TILE * (int)sizeof(unsigned long long);
+    static bool fwd_configured = false;  // static + dynamic shared memory exceeds the 48 KB default: opt in once
+    if (!fwd_configured) {
+        cudaError_t e = cudaFuncSetAttribute(raster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem);
+        if (e != cudaSuccess) {
+            hm_set_error("hm_raster_sil_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            return HM_ERR_CUDA;
+        }
+        fwd_configured = true;
+    }
+    raster_fwd_kernel<<<grid, NTHREADS, fwd_smem, hm_stream(stream)>>>(
         static_cast<const FaceRec *>(records), static_cast<const FaceBox *>(bboxes), F, is, anti_aliasing, near_, far_,
         face_index, alpha, cov_row, cov_col);
     HM_CHECK_LAUNCH("hm_raster_sil_fwd");
