@@ -307,6 +307,67 @@ __global__ void argmin_kernel(const float *__restrict__ total, int C, int I, int
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------ object-pose initialiser
+// PoseOptimizer.compute_offscreen_loss (homan/pose_optimization.py:112-134) on projected vertices [u, v, z]:
+// sum over vertices of relu(u - 1) + relu(v - 1) + relu(-1 - u) + relu(-1 - v) + relu(-z) + relu(z - far).
+// One CTA per image; the gradient (weight * d/d ndc, 0 at ties as torch.max(x, 0) of torch 1.6) is accumulated.
+__global__ void __launch_bounds__(NT)
+offscreen_kernel(const float *__restrict__ ndc, int V, float far_, float weight, float *__restrict__ partials,
+                 float *__restrict__ grad_ndc) {
+    __shared__ float scratch[32];
+    const int b = blockIdx.x;
+    const float *p = ndc + (long)b * V * 3;
+    float *g = grad_ndc ? grad_ndc + (long)b * V * 3 : nullptr;
+    float acc[1] = {0.f};
+    for (int i = threadIdx.x; i < V; i += NT) {
+        const float u = p[3 * i], v = p[3 * i + 1], z = p[3 * i + 2];
+        acc[0] += fmaxf(u - 1.f, 0.f) + fmaxf(v - 1.f, 0.f) + fmaxf(-1.f - u, 0.f) + fmaxf(-1.f - v, 0.f) +
+                  fmaxf(-z, 0.f) + fmaxf(z - far_, 0.f);
+        if (g) {
+            const float gu = (u > 1.f ? 1.f : 0.f) - (u < -1.f ? 1.f : 0.f);
+            const float gv = (v > 1.f ? 1.f : 0.f) - (v < -1.f ? 1.f : 0.f);
+            const float gz = (z > far_ ? 1.f : 0.f) - (z < 0.f ? 1.f : 0.f);
+            if (gu != 0.f) g[3 * i] += weight * gu;
+            if (gv != 0.f) g[3 * i + 1] += weight * gv;
+            if (gz != 0.f) g[3 * i + 2] += weight * gz;
+        }
+    }
+    block_sum<1>(acc, scratch);
+    if (threadIdx.x == 0) partials[(long)b * HM_NPART + HM_PART_OFFSCREEN] = acc[0];
+}
+
+// Best candidate ever seen by find_optimal_pose (homan/pose_optimization.py:349-353): when the smallest loss of
+// this iteration beats the record, the record takes that loss and the CURRENT parameters of that candidate
+// (the reference reads them after optimizer.step()). best = {loss, rot6d[6], trans[3]}. One CTA.
+__global__ void __launch_bounds__(NT)
+track_best_kernel(const float *__restrict__ total, int N, const float *__restrict__ rot6d,
+                  const float *__restrict__ trans, float *__restrict__ best, int32_t *__restrict__ best_index) {
+    __shared__ float sv[NT];
+    __shared__ int si[NT];
+    float v = INFINITY;
+    int idx = 0x7fffffff;
+    for (int i = threadIdx.x; i < N; i += NT) {
+        const float t = total[i];
+        if (t < v) { v = t; idx = i; }
+    }
+    sv[threadIdx.x] = v; si[threadIdx.x] = idx;
+    __syncthreads();
+    for (int o = NT / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            const float ov = sv[threadIdx.x + o];
+            const int oi = si[threadIdx.x + o];
+            if (ov < sv[threadIdx.x] || (ov == sv[threadIdx.x] && oi < si[threadIdx.x])) { sv[threadIdx.x] = ov; si[threadIdx.x] = oi; }
+        }
+        __syncthreads();
+    }
+    if (sv[0] < best[0] && si[0] < N) {  // (block-uniform)
+        const int w = si[0];
+        if (threadIdx.x == 0) { best[0] = sv[0]; if (best_index) best_index[0] = w; }
+        if (threadIdx.x < 6) best[1 + threadIdx.x] = rot6d[(long)w * 6 + threadIdx.x];
+        else if (threadIdx.x < 9) best[1 + threadIdx.x] = trans[(long)w * 3 + threadIdx.x - 6];
+    }
+}
+
 extern "C" {
 
 int hm_rigid_fwd(const float *mesh, int mesh_batch, const float *rot6d, const float *trans, const float *scale,
@@ -382,4 +443,22 @@ int hm_argmin_over_inits(const float *total, int C, int I, int32_t *best_index, 
     return HM_OK;
 }
 
+int hm_offscreen_loss_fwd_bwd(const float *ndc, int B, int V, float far_, float weight, float *partials,
+                              float *grad_ndc, void *stream) {
+    HM_REQUIRE(ndc && partials, "hm_offscreen_loss_fwd_bwd: null pointer");
+    HM_REQUIRE(B >= 0 && V >= 0, "hm_offscreen_loss_fwd_bwd: bad sizes");
+    if (B == 0) return HM_OK;
+    offscreen_kernel<<<B, NT, 0, hm_stream(stream)>>>(ndc, V, far_, weight, partials, grad_ndc);
+    HM_CHECK_LAUNCH("hm_offscreen_loss_fwd_bwd");
+    return HM_OK;
+}
+int hm_track_best(const float *total, int N, const float *rot6d, const float *trans, float *best,
+                  int32_t *best_index, void *stream) {
+    HM_REQUIRE(total && rot6d && trans && best, "hm_track_best: null pointer");
+    HM_REQUIRE(N >= 0, "hm_track_best: bad size");
+    if (N == 0) return HM_OK;
+    track_best_kernel<<<1, NT, 0, hm_stream(stream)>>>(total, N, rot6d, trans, best, best_index);
+    HM_CHECK_LAUNCH("hm_track_best");
+    return HM_OK;
+}
 }  // extern "C"

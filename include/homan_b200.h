@@ -151,6 +151,7 @@ int hm_rigid_bwd(const float *mesh, int mesh_batch, const float *rot6d, const fl
 #define HM_PART_CONTACT 11
 #define HM_PART_MINDIST 12    /* metric: min hand-object vertex distance of the image */
 #define HM_PART_INTER_FLAG 13
+#define HM_PART_OFFSCREEN 14  /* object-pose initialiser only (hm_offscreen_loss_fwd_bwd) */
 #define HM_NPART 16
 int hm_vertex_losses(const float *verts_hand, const float *verts_obj, const float *camintr,
                      const float *ref_verts2d, const float *pca, int pca_dim, int B, int T, int Vo,
@@ -198,6 +199,19 @@ int hm_adam_step(float *params, const float *grads, float *exp_avg, float *exp_a
 /* best init of every clip: total [C, I] -> best_index [C], best_loss [C] (first minimum). */
 int hm_argmin_over_inits(const float *total, int C, int I, int32_t *best_index, float *best_loss,
                          void *stream);
+
+/* ---------------------------------------------------------------- object-pose multi-init fitter
+ * PoseOptimizer.compute_offscreen_loss (homan/pose_optimization.py:112-134) on projected vertices
+ * ndc [B,V,3] = nr.projection output: partials[b*HM_NPART + HM_PART_OFFSCREEN] = sum over vertices of
+ * relu(u-1) + relu(v-1) + relu(-1-u) + relu(-1-v) + relu(-z) + relu(z-far); grad_ndc += weight * d/d ndc
+ * (may be NULL). The reference weights the term by 100000 (pose_optimization.py:148). */
+int hm_offscreen_loss_fwd_bwd(const float *ndc, int B, int V, float far_, float weight, float *partials,
+                              float *grad_ndc, void *stream);
+/* Best candidate ever of find_optimal_pose (homan/pose_optimization.py:349-353): if min_i total[i] < best[0],
+ * best = {that loss, rot6d[i] (6), trans[i] (3)} with the CURRENT parameters (the reference reads them after
+ * optimizer.step()); best_index (may be NULL) receives i. best[0] starts at +inf. */
+int hm_track_best(const float *total, int N, const float *rot6d, const float *trans, float *best,
+                  int32_t *best_index, void *stream);
 
 #ifdef __cplusplus
 }

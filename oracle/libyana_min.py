@@ -64,3 +64,24 @@ def check_shape(tensor, exp_shape, name="tensor"):
     shape = tuple(tensor.shape)
     if len(shape) != len(exp_shape) or any(e != -1 and s != e for s, e in zip(shape, exp_shape)):
         raise ValueError(f"{name}: expected shape {exp_shape}, got {shape}")
+
+
+def get_K_crop_resize(K, boxes, crop_resize, invert_xy=False):
+    """libyana.lib3d.kcrop.get_K_crop_resize (call site /root/reference/homan/pose_optimization.py:247-249):
+    intrinsics of the crop `boxes` (xyxy) resized to crop_resize; skew not handled. Recalled from upstream
+    (cosypose-derived), parity unpinned. K [B,3,3], boxes [B,4] -> [B,3,3]."""
+    assert K.shape[1:] == (3, 3) and boxes.shape[1:] == (4,)
+    K, boxes = K.float(), boxes.float()
+    new_K = K.clone()
+    final_width, final_height = float(max(crop_resize)), float(min(crop_resize))
+    crop_width, crop_height = boxes[:, 2] - boxes[:, 0], boxes[:, 3] - boxes[:, 1]
+    crop_cj, crop_ci = (boxes[:, 0] + boxes[:, 2]) / 2, (boxes[:, 1] + boxes[:, 3]) / 2
+    cx = K[:, 0, 2] + (crop_width - 1) / 2 - crop_cj
+    cy = K[:, 1, 2] + (crop_height - 1) / 2 - crop_ci
+    center_x, center_y = (crop_width - 1) / 2, (crop_height - 1) / 2
+    scale_x, scale_y = final_width / crop_width, final_height / crop_height
+    new_K[:, 0, 0] = scale_x * K[:, 0, 0]
+    new_K[:, 1, 1] = scale_y * K[:, 1, 1]
+    new_K[:, 0, 2] = (final_width - 1) / 2 + scale_x * (cx - center_x)
+    new_K[:, 1, 2] = (final_height - 1) / 2 + scale_y * (cy - center_y)
+    return new_K

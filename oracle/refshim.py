@@ -82,7 +82,7 @@ def install(scratch_dir, mano_assets):
     _module("libyana.vidutils.np2vid", make_video=_noop)
     _module("libyana.lib3d")
     _module("libyana.lib3d.trans3d", rot_points=lambda pts, *a, **k: pts)
-    _module("libyana.lib3d.kcrop", get_K_crop_resize=_noop)
+    _module("libyana.lib3d.kcrop", get_K_crop_resize=libyana_min.get_K_crop_resize)
     _module("libyana.verify")
     _module("libyana.verify.checkshape", check_shape=libyana_min.check_shape)
     _module("libyana.camutils")

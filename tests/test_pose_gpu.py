@@ -1,0 +1,140 @@
+"""GPU: the object-pose multi-init fitter (homan_b200/pose_optimization.py) against golden
+vectors recorded from the UNMODIFIED reference /root/reference/homan/pose_optimization.py on CPU
+(tests/golden/ref_pose_init.npz, scripts/make_golden_pose.py) and against the CPU oracle (oracle/pose_ref.py).
+
+Bars: silhouette pixel counts (mask loss of a binary render) equal up to boundary pixels that an ulp of difference
+in the rigid transform / projection moves across a pixel centre (<= 0.2 % of the count); IoU 1e-3; the off-screen term
+1e-5 relative; gradients 1e-3 of their scale."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "ref_pose_init.npz")
+
+
+def _golden():
+    return np.load(GOLDEN)
+
+
+def _engine(g, rot6d, trans, **kw):
+    from homan_b200.pose_optimization import PoseFitEngine
+    return PoseFitEngine(g["in_vertices"], g["in_faces"], g["in_mask"], g["K_roi"], rot6d, trans, **kw)
+
+
+def _close_counts(a, b):
+    return np.all(np.abs(a - b) <= np.maximum(2.0, 2e-3 * np.abs(b)))
+
+
+def test_teacher_forced_losses_at_every_reference_iterate():
+    g = _golden()
+    for k in range(int(g["iters"])):
+        eng = _engine(g, g["it_rot"][k], g["it_trans"][k], use_graph=False)
+        ld = eng.evaluate()
+        torch.cuda.synchronize()
+        assert _close_counts(ld["mask"].cpu().numpy(), g["it_mask"][k]), (k, ld["mask"].cpu().numpy(), g["it_mask"][k])
+        assert np.allclose(ld["offscreen"].cpu().numpy(), g["it_offscreen"][k], rtol=1e-5, atol=1e-3)
+        assert np.allclose(eng.iou.cpu().numpy(), g["it_iou"][k], atol=1e-3)
+
+
+def test_offscreen_term_and_first_gradients():
+    g = _golden()
+    eng = _engine(g, g["po_rot6d"], g["po_trans"], use_graph=False)
+    eng._iteration()  # forward + backward + Adam; the gradient buffers keep d loss / d parameters
+    torch.cuda.synchronize()
+    ld = eng.loss_dict()
+    assert _close_counts(ld["mask"].cpu().numpy(), g["po_mask"])
+    assert np.allclose(ld["offscreen"].cpu().numpy(), g["po_offscreen"], rtol=1e-5)
+    gr, gt = eng.grad_rotations.cpu().numpy(), eng.grad_translations.cpu().numpy()
+    for got, ref in ((gr, g["po_grad_rot"]), (gt, g["po_grad_trans"])):
+        for i in range(got.shape[0]):  # per candidate: the off-screen ones carry gradients 1e5 times larger
+            scale = np.abs(ref[i]).max()
+            assert np.abs(got[i] - ref[i]).max() <= 1e-3 * scale, (i, got[i], ref[i])
+
+
+def test_dropin_pose_optimizer_autograd_path():
+    from homan_b200.pose_optimization import PoseOptimizer
+    g = _golden()
+    model = PoseOptimizer(ref_image=g["in_mask"], vertices=torch.from_numpy(g["in_vertices"]),
+                          faces=torch.from_numpy(g["in_faces"]), textures=None,
+                          rotation_init=torch.from_numpy(g["po_rot6d"]), translation_init=torch.from_numpy(g["po_trans"]),
+                          num_initializations=4, K=torch.from_numpy(g["K_roi"]))
+    assert [n for n, _ in model.named_parameters()] == ["rotations", "translations"]
+    loss_dict, iou, image = model()
+    assert set(loss_dict) == {"mask", "chamfer", "offscreen"} and image.shape == (4, 256, 256)
+    sum(loss_dict.values()).sum().backward()
+    assert _close_counts(loss_dict["mask"].detach().cpu().numpy(), g["po_mask"])
+    assert np.allclose(loss_dict["offscreen"].detach().cpu().numpy(), g["po_offscreen"], rtol=1e-5)
+    assert np.allclose(iou.cpu().numpy(), g["po_iou"], atol=1e-3)
+    for got, ref in ((model.rotations.grad.cpu().numpy(), g["po_grad_rot"]),
+                     (model.translations.grad.cpu().numpy(), g["po_grad_trans"])):
+        for i in range(4):
+            assert np.abs(got[i] - ref[i]).max() <= 1e-3 * np.abs(ref[i]).max(), (i, got[i], ref[i])
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_free_running_fit_follows_the_reference(use_graph):
+    g = _golden()
+    iters = int(g["iters"])
+    eng = _engine(g, g["in_rotations_init"][:, :, :2], g["it_trans"][0], use_graph=use_graph)
+    hist = eng.fit(iters, record=True).cpu().numpy()
+    ref = g["it_mask"] + g["it_offscreen"]
+    assert _close_counts(hist[0], ref[0])
+    # Adam's first step moves every parameter by lr * sign(grad): iteration 1 is pinned as well
+    assert np.allclose(hist[1], ref[1], rtol=5e-3), (hist[1], ref[1])
+    # later iterates: the silhouette loss is a step function of the pose and Adam's normalised step amplifies
+    # fp32-level differences of the gradient (the same happens between two runs of the upstream renderer, whose
+    # backward accumulates in a non-deterministic order); the teacher-forced test above pins every iterate
+    assert np.allclose(hist, ref, rtol=0.25), (hist, ref)
+    assert np.allclose(eng.rotations.cpu().numpy(), g["plain_rotations"], atol=2e-2)
+    assert np.allclose(eng.translations.cpu().numpy(), g["plain_translations"], atol=2e-2)
+    # best-ever tracking: loss of the best candidate seen, parameters read after the step
+    assert np.isclose(float(eng.best[0]), ref.min(), rtol=5e-3)
+
+
+def test_find_optimal_pose_surface_and_ordering():
+    from homan_b200 import pose_optimization as po
+    g = _golden()
+    kw = dict(vertices=g["in_vertices"], faces=g["in_faces"], mask=g["in_mask"], bbox=g["in_bbox"],
+              square_bbox=g["in_square_bbox"], image_size=tuple(g["in_image_size"]), K=g["in_K"],
+              num_iterations=int(g["iters"]), num_initializations=6, rotations_init=g["in_rotations_init"])
+    plain = po.find_optimal_pose(sort_best=False, **kw)
+    assert np.allclose(plain.K.cpu().numpy(), g["K_roi"], atol=1e-6)
+    assert np.allclose(plain.rotations.detach().cpu().numpy(), g["plain_rotations"], atol=2e-2)
+    assert np.allclose(plain.translations.detach().cpu().numpy(), g["plain_translations"], atol=2e-2)
+    srt, eng = po.find_optimal_pose(sort_best=True, return_engine=True, **kw)
+    # sort_best: best-ever candidate first, then the candidates by their last evaluated loss (minus the worst)
+    order = torch.argsort(eng.total)
+    assert torch.equal(srt.rotations.detach()[0], eng.best[1:7].view(3, 2))
+    assert torch.equal(srt.rotations.detach()[1:], eng.rotations[order][:-1])
+    assert torch.equal(srt.translations.detach()[1:], eng.translations[order][:-1])
+    assert np.allclose(srt.rotations.detach().cpu().numpy()[0], g["sorted_rotations"][0], atol=2e-2)
+    loss_dict, iou, _ = srt()
+    assert torch.isfinite(loss_dict["mask"]).all() and iou.shape == (6,)
+
+
+def test_find_optimal_poses_two_frames_many_inits():
+    """256 random candidates over two frames: shapes of the reference's output dicts, the chosen motion has the best
+    mean IoU, and fitting improves the best candidate."""
+    from homan_b200 import pose_optimization as po
+    g = _golden()
+    ann = {"target_crop_mask": g["in_mask"], "bbox": g["in_bbox"], "square_bbox": g["in_square_bbox"],
+           "full_mask": torch.zeros(8, 8)}
+    torch.manual_seed(0)
+    out = po.find_optimal_poses(tuple(g["in_image_size"]), faces=g["in_faces"], vertices=g["in_vertices"],
+                                annotations=[ann, ann], images=None, Ks=[g["in_K"], g["in_K"]], num_iterations=30,
+                                num_initializations=256)
+    assert len(out) == 2
+    for fp in out:
+        assert fp["rotations"].shape == (1, 3, 3) and fp["translations"].shape == (1, 1, 3)
+        assert fp["verts_trans"].shape == (1, 42, 3) and fp["K_roi"].shape == (1, 1, 3, 3)
+        assert fp["target_masks"].shape == (1, 256, 256)
+        R = fp["rotations"][0]
+        assert torch.allclose(R.T @ R, torch.eye(3, device=R.device), atol=1e-4)
+    # the winner explains the mask: IoU of its render well above chance
+    eng = po.PoseFitEngine(g["in_vertices"], g["in_faces"], g["in_mask"], g["K_roi"],
+                           out[-1]["rotations"][:, :, :2].contiguous(), out[-1]["translations"], use_graph=False)
+    eng.evaluate()
+    assert float(eng.iou[0]) > 0.7, float(eng.iou[0])
