@@ -1,0 +1,14 @@
+#!/bin/bash
+# Collects the numbers profiles/ records for a round on the GPU box (one B200): bench lines, ncu launch list,
+# full ncu capture of the raster kernels, comparator benchmark, pose-init benchmark. Outputs under gpurun_out/.
+set -x
+mkdir -p gpurun_out
+python bench.py > gpurun_out/bench_cfg3_n1.json 2> gpurun_out/bench_cfg3_n1.err
+python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/ncu_launches.csv \
+    python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'raster_bwd|raster_fwd' -s 8 -c 4 -f \
+    -o gpurun_out/prof_raster_final python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/prof_raster_final.log 2>&1
+python scripts/bench_raster_vs_nmr_style.py > gpurun_out/raster_vs_nmr_style.json 2> gpurun_out/raster_vs_nmr_style.err
+python scripts/bench_pose_init.py --out gpurun_out/pose_init.json > /dev/null 2> gpurun_out/pose_init.err
+tail -c 400 gpurun_out/bench_cfg3_n1.json; tail -c 300 gpurun_out/bench_reference.json
