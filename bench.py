@@ -199,7 +199,9 @@ def run_ours(args):
     from homan_b200.workload import CONFIGS, make_workload
     cfg = CONFIGS[args.workload]
     asset = synth.make_mano_asset(0, "right")
-    batch, lw = make_workload(args.workload, clip_index=rank, mano_asset=asset)
+    # weak scaling: every rank fits the same clip from its own block of P random initialisations (equal work per
+    # GPU); the job's answer is the argmin over all N*P inits, gathered once at the end
+    batch, lw = make_workload(args.workload, clip_index=0, init_shard=rank, mano_asset=asset)
     eng = FitEngine(batch, lw, lr=1e-2, mano_asset=asset, use_graph=True)
     host = eng.stage_host(batch, pin=True)
     eng.capture()
@@ -294,6 +296,7 @@ def run_ours(args):
         "config": {"workload": args.workload, "inits": eng.P, "frames": eng.T, "images_per_step_per_gpu": eng.B,
                    "object": cfg["obj"], "faces": [int(eng.faces_hand.shape[1]), int(eng.faces_obj.shape[1])],
                    "losses": cfg["lw"], "render": "256^2 (512^2 raster, AA)", "cuda_graph": True,
+                   "sharding": "inits: every rank fits the clip from its own block of P random inits, one all_gather of the best init at the end",
                    "l2": "inputs larger than L2 (face_index maps alone are %d MB per step)" %
                          (eng.B * 2 * 512 * 512 * 4 // 2 ** 20),
                    "problem_frame_iters_per_s": value * eng.B},
