@@ -23,7 +23,7 @@ struct __align__(16) FaceRec {
     int fn;       // face number in the doubled (fill_back) numbering, -1 = culled
     int v[3];     // vertex indices in that winding
     short bb[4];  // pixel bbox x0 y0 x1 y1 (clamped), empty when x0 > x1
-    int pad;
+    int pad;      // bit 0: both windings are front-facing (degenerate face): forward and backward also process F + f
     float inv[9];  // barycentric matrix in pixel coordinates, already divided by its determinant
     float iz[3];   // 1 / z of the three corners (fast depth of the forward pass)
     int exact;     // 1: some corner depth is not a plain positive float -> forward uses the reference arithmetic only
@@ -125,12 +125,15 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
         p[k][0] = q[0]; p[k][1] = q[1]; p[k][2] = q[2];
     }
     int fn = -1;
-    bool rev = false;
+    bool rev = false, both = false;
     // back-face test of the original winding, then of the reversed copy appended by fill_back
-    if (!((p[2][1] - p[0][1]) * (p[1][0] - p[0][0]) < (p[1][1] - p[0][1]) * (p[2][0] - p[0][0]))) {
+    const bool front_orig = !((p[2][1] - p[0][1]) * (p[1][0] - p[0][0]) < (p[1][1] - p[0][1]) * (p[2][0] - p[0][0]));
+    const bool front_rev = fill_back &&
+                           !((p[0][1] - p[2][1]) * (p[1][0] - p[2][0]) < (p[1][1] - p[2][1]) * (p[0][0] - p[2][0]));
+    if (front_orig) {
         fn = f;
-    } else if (fill_back &&
-               !((p[0][1] - p[2][1]) * (p[1][0] - p[2][0]) < (p[1][1] - p[2][1]) * (p[0][0] - p[2][0]))) {
+        both = front_rev;  // signed area exactly 0 in fp32: the reference keeps BOTH copies (f and F + f)
+    } else if (front_rev) {
         fn = F + f;
         rev = true;
     }
@@ -159,7 +162,7 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
     }
     r.fn = fn;
     r.bb[0] = (short)x0; r.bb[1] = (short)y0; r.bb[2] = (short)x1; r.bb[3] = (short)y1;
-    r.pad = 0;
+    r.pad = both ? 1 : 0;
     {   // barycentric matrix of the stored winding (same expressions as the oracle's per-face setup)
         const float p00 = to_pix(r.c[0], is), p01 = to_pix(r.c[1], is), p10 = to_pix(r.c[3], is), p11 = to_pix(r.c[4], is),
                     p20 = to_pix(r.c[6], is), p21 = to_pix(r.c[7], is);
@@ -375,18 +378,28 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             const float4 *rp = srec[j];
             const float4 q2 = rp[2];
             if ((__float_as_int(q2.y) >= F ? 1 : 0) != pass) continue;
-            const float4 q0 = rp[0], q1 = rp[1];
             const int4 q3 = *reinterpret_cast<const int4 *>(rp + 3);
+            const float4 q0 = rp[0], q1 = rp[1];
             const float f0 = q0.x, f1 = q0.y, f2 = q0.z, f3 = q0.w, f4 = q1.x, f5 = q1.y, f6 = q1.z, f7 = q1.w,
                         f8 = q2.x;
             const int fn = __float_as_int(q2.y);
-            if ((fn >= F ? 1 : 0) != pass) continue;
             const int bx0 = (short)(q3.y & 0xffff), by0 = (short)(q3.y >> 16);
             const int bx1 = (short)(q3.z & 0xffff), by1 = (short)(q3.z >> 16);
             const int X0 = max(bx0, tx0), X1 = min(bx1, tx0 + TILE - 1);
             const int Y0 = max(by0, ty0), Y1 = min(by1, ty0 + TILE - 1);
             const int w = X1 - X0 + 1, h = Y1 - Y0 + 1;
             if (w <= 0 || h <= 0) continue;
+            if (q3.w & 1) {
+                // degenerate face whose two windings are both front-facing: the reference also rasterises the
+                // reversed copy F + f. Every pixel of its bounding box goes to the exact resolution below, which
+                // handles both copies (such faces are rare and small).
+                for (int r = lane; r < h; r += 32) {
+                    const int yl = Y0 - ty0 + r, a = X0 - tx0, c = X1 - tx0;
+                    const unsigned long long m = ((c == 63 ? ~0ull : ((1ull << (c + 1)) - 1ull)) >> a) << a;
+                    if ((unsigned)m) atomicOr(&amb[yl][0], (unsigned)m);
+                    if ((unsigned)(m >> 32)) atomicOr(&amb[yl][1], (unsigned)(m >> 32));
+                }
+            }
             const float e0x = f3 - f0, e0y = f4 - f1, e1x = f6 - f3, e1y = f7 - f4, e2x = f0 - f6, e2y = f1 - f7;
             // early z: the interpolated depth is a convex combination of the corner depths, so a face whose
             // nearest corner (minus rounding slack) is behind the current winner of a pixel cannot win it
@@ -514,26 +527,38 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             const int n = next_batch(boxes, base2, F, tx0, ty0, list, &cnt, &next);
             for (int li = threadIdx.x >> 5; li < n; li += NWARPS) {
                 const FaceRec *rp = recs + list[li];
-                const int fn = __ldg(reinterpret_cast<const int *>(rp) + 9);
+                int fn = __ldg(reinterpret_cast<const int *>(rp) + 9);
                 if (fn < 0) continue;
                 float f[9], inv[9];
 #pragma unroll
                 for (int k = 0; k < 9; ++k) { f[k] = __ldg(reinterpret_cast<const float *>(rp) + k); inv[k] = __ldg(reinterpret_cast<const float *>(rp) + 16 + k); }
                 const int q = __ldg(reinterpret_cast<const int *>(rp) + 13), q2 = __ldg(reinterpret_cast<const int *>(rp) + 14);
                 const int bx0 = (short)(q & 0xffff), by0 = (short)(q >> 16), bx1 = (short)(q2 & 0xffff), by1 = (short)(q2 >> 16);
-                for (int j = lane; j < na; j += 32) {
-                    const unsigned e = ambl[j];
-                    const int xl = e & 63u, yl = e >> 6;
-                    const int xi = tx0 + xl, yi = ty0 + yl;
-                    if (xi < bx0 || xi > bx1 || yi < by0 || yi > by1) continue;
-                    const float yp = pow2 ? (float)(2 * yi + 1 - is) * inv_is : (float)(2 * yi + 1 - is) / (float)is;
-                    const float xp = pow2 ? (float)(2 * xi + 1 - is) * inv_is : (float)(2 * xi + 1 - is) / (float)is;
-                    if ((yp - f[1]) * (f[3] - f[0]) < (xp - f[0]) * (f[4] - f[1])) continue;
-                    if ((yp - f[4]) * (f[6] - f[3]) < (xp - f[3]) * (f[7] - f[4])) continue;
-                    if ((yp - f[7]) * (f[0] - f[6]) < (xp - f[6]) * (f[1] - f[7])) continue;
-                    const float zp = exact_depth(inv, xi, yi, f[2], f[5], f[8]);
-                    if (zp > near_ && zp < far_)
-                        atomicMin(&keys[yl * TILE + xl], ((unsigned long long)__float_as_uint(zp) << 32) | (unsigned)fn);
+                const int copies = (__ldg(reinterpret_cast<const int *>(rp) + 15) & 1) ? 2 : 1;
+#pragma unroll 1
+                for (int copy = 0; copy < copies; ++copy) {
+                    if (copy == 1) {  // the reversed copy F + f of a degenerate face
+#pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            float t = f[k]; f[k] = f[6 + k]; f[6 + k] = t;
+                            t = inv[k]; inv[k] = inv[6 + k]; inv[6 + k] = t;
+                        }
+                        fn += F;
+                    }
+                    for (int j = lane; j < na; j += 32) {
+                        const unsigned e = ambl[j];
+                        const int xl = e & 63u, yl = e >> 6;
+                        const int xi = tx0 + xl, yi = ty0 + yl;
+                        if (xi < bx0 || xi > bx1 || yi < by0 || yi > by1) continue;
+                        const float yp = pow2 ? (float)(2 * yi + 1 - is) * inv_is : (float)(2 * yi + 1 - is) / (float)is;
+                        const float xp = pow2 ? (float)(2 * xi + 1 - is) * inv_is : (float)(2 * xi + 1 - is) / (float)is;
+                        if ((yp - f[1]) * (f[3] - f[0]) < (xp - f[0]) * (f[4] - f[1])) continue;
+                        if ((yp - f[4]) * (f[6] - f[3]) < (xp - f[3]) * (f[7] - f[4])) continue;
+                        if ((yp - f[7]) * (f[0] - f[6]) < (xp - f[6]) * (f[1] - f[7])) continue;
+                        const float zp = exact_depth(inv, xi, yi, f[2], f[5], f[8]);
+                        if (zp > near_ && zp < far_)
+                            atomicMin(&keys[yl * TILE + xl], ((unsigned long long)__float_as_uint(zp) << 32) | (unsigned)fn);
+                    }
                 }
             }
         }
@@ -771,9 +796,6 @@ constexpr int BWD_LISTCAP = 1024;
 #ifndef HM_BWD_SUB
 #define HM_BWD_SUB 128
 #endif
-#ifndef HM_DIRECT_ATOMICS
-#define HM_DIRECT_ATOMICS 1
-#endif
 #ifndef HM_SEG
 #define HM_SEG 8
 #endif
@@ -887,14 +909,10 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     __shared__ int cnt, next;
     __shared__ __align__(16) uint2 srun[4][TILE][RCAP];  // run lists: mn_row, mp_row, mn_col, mp_col
     __shared__ __align__(16) unsigned scount[4][TILE];
-    __shared__ int hist[TILE + 2], hpos[TILE + 2];
+    __shared__ int hist[TILE + 2], hpos[TILE + 2], has_both;
     __shared__ unsigned char slen[6 * BWD_SUB];                 // scan-lines of every task of the sub-batch
     __shared__ unsigned short sorted[6 * BWD_SUB * (TILE / SEG)];  // segments (task | index << 12), longest first
-#if HM_DIRECT_ATOMICS
     __shared__ __align__(16) float4 srec[BWD_SUB][4];            // first 64 bytes of the sub-batch's face records
-#else
-    __shared__ float wacc[6 * BWD_SUB][2];                       // per-task sums of the sub-batch
-#endif
     __shared__ __align__(8) uint64_t bar;
     const int W = is / 32;
     // dynamic shared memory: face_index tile | per-warp queues
@@ -973,27 +991,56 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             __syncthreads();
             staged = true;
         }
-        for (int f0 = 0; f0 < n; f0 += BWD_SUB) {
+        // pass 0: the faces as recorded; pass 1: the reversed copies F + f of the degenerate faces whose two windings
+        // are both front-facing (the reference differentiates both copies)
+        int nb = n;
+        if (threadIdx.x == 0) has_both = 0;  // (ordered before its readers / writers by the barriers below)
+        for (int rev = 0; rev < 2; ++rev) {
+        if (rev == 1) {
+            __syncthreads();
+            if (!has_both) break;
+            int keep[BWD_LISTCAP / NTHREADS];
+            int k = 0;
+            __syncthreads();
+            if (threadIdx.x == 0) cnt = 0;
+            for (int i = threadIdx.x; i < n; i += NTHREADS) {
+                const int f = list[i];
+                keep[k++] = (__ldg(reinterpret_cast<const int *>(recs + f) + 15) & 1) ? f : -1;
+            }
+            __syncthreads();
+            for (int j = 0; j < k; ++j)
+                if (keep[j] >= 0) list[atomicAdd(&cnt, 1)] = keep[j];
+            __syncthreads();
+            nb = cnt;
+            if (nb == 0) break;
+        }
+        for (int f0 = 0; f0 < nb; f0 += BWD_SUB) {
         const int *sub = list + f0;
-        const int ntasks = 6 * min(BWD_SUB, n - f0);
+        const int ntasks = 6 * min(BWD_SUB, nb - f0);
         // ---- the scan-lines of every task are cut into segments of <= SEG lines; counting sort of the
         //      segments by decreasing length (full segments first)
         __syncthreads();
         if (threadIdx.x < SEG + 2) hist[threadIdx.x] = 0;
         if (threadIdx.x == 0) next = 0;
-#if HM_DIRECT_ATOMICS
-        for (int i = threadIdx.x; i < ntasks / 6 * 4; i += NTHREADS)
-            srec[i >> 2][i & 3] = __ldg(reinterpret_cast<const float4 *>(recs + sub[i >> 2]) + (i & 3));
-#else
-        for (int i = threadIdx.x; i < 2 * ntasks; i += NTHREADS) (&wacc[0][0])[i] = 0.f;
-#endif
+        if (rev == 0) {
+            for (int i = threadIdx.x; i < ntasks / 6 * 4; i += NTHREADS) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(recs + sub[i >> 2]) + (i & 3));
+                srec[i >> 2][i & 3] = v;
+                if ((i & 3) == 3 && (__float_as_int(v.w) & 1)) has_both = 1;
+            }
+        } else {
+            for (int i = threadIdx.x; i < ntasks / 6; i += NTHREADS) {  // corners 0 and 2 trade places, fn -> F + f
+                const float4 *rp = reinterpret_cast<const float4 *>(recs + sub[i]);
+                const float4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
+                srec[i][0] = make_float4(q1.z, q1.w, q2.x, q0.w);
+                srec[i][1] = make_float4(q1.x, q1.y, q0.x, q0.y);
+                srec[i][2] = make_float4(q0.z, __int_as_float(__float_as_int(q2.y) + F), q3.x, q2.w);
+                srec[i][3] = make_float4(q2.z, q3.y, q3.z, q3.w);
+            }
+        }
         __syncthreads();
         for (int task = threadIdx.x; task < ntasks; task += NTHREADS) {
-            #if HM_DIRECT_ATOMICS
             const int len = task_params(srec[task / 6], task, is, tx0, ty0).len;
-#else
-            const int len = task_params(reinterpret_cast<const float4 *>(recs + sub[task / 6]), task, is, tx0, ty0).len;
-#endif
             slen[task] = (unsigned char)len;
             if (len >= SEG) atomicAdd(&hist[SEG], len / SEG);
             if (len % SEG) atomicAdd(&hist[len % SEG], 1);
@@ -1025,11 +1072,7 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             const bool mine_valid = g * 32 + lane < nwork;
             const unsigned seg_id = sorted[min(g * 32 + lane, nwork - 1)];
             const int my_task = seg_id & 0xfffu, seg_lo = (int)(seg_id >> 12) * SEG;
-#if HM_DIRECT_ATOMICS
             const TaskParams tp = task_params(srec[my_task / 6], my_task, is, tx0, ty0);
-#else
-            const TaskParams tp = task_params(reinterpret_cast<const float4 *>(recs + sub[my_task / 6]), my_task, is, tx0, ty0);
-#endif
             // ---- this thread's task
             const float p0d0 = tp.p0d0, p0d1 = tp.p0d1, p1d0 = tp.p1d0, p2d0 = tp.p2d0, p2d1 = tp.p2d1;
             const float slope = tp.slope, s02 = tp.slope02, s21 = tp.slope21, ka = tp.ka;
@@ -1125,7 +1168,15 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                                     else c2 = s21 * (fd0 - p2d0) + p2d1;
                                     const int lim = __float2int_rz(dir > 0 ? ceilf(c2) : floorf(c2));
                                     const int ra = max(min(d1_in, lim), 0), rc = min(max(d1_in, lim), is - 1);
-                                    if (ra <= rc) { has_in = true; ra_in = ra; rc_in = rc; cnt_in = cs; ls_in = ls; }
+                                    if (ra <= rc) {
+                                        has_in = true; ra_in = ra; rc_in = rc; ls_in = ls;
+                                        // an in-sweep can straddle its crossing: by one pixel when the triangle is
+                                        // thinner than a pixel there (eval_item copes with up to NEAR_N - 1 pixels
+                                        // on the near side), by many when its far end is the extrapolation of an
+                                        // edge that does not span the scan-line (degenerate faces): the closed
+                                        // form assumes one side, so such a sweep walks the bit line instead
+                                        cnt_in = ((float)ra < x - (float)(NEAR_N - 1) && (float)rc > x) ? RUN_OVERFLOW : cs;
+                                    }
                                 }
                             }
                             if (has_out || has_in) { c0 = __fdividef(ka, p1d0 - fd0); c1 = __fdividef(ka, fd0 - p0d0); }
@@ -1160,31 +1211,13 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 }
             }
             if (qn > 0) drain(qn);
-#if HM_DIRECT_ATOMICS
             if (mine_valid) {
                 // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
                 if (acc0 != 0.f) atomicAdd(grad_ndc + (long)tp.vid0 * 3 + (1 - axis), acc0);
                 if (acc1 != 0.f) atomicAdd(grad_ndc + (long)tp.vid1 * 3 + (1 - axis), acc1);
             }
         }
-#else
-            if (mine_valid) {  // (shared-memory float adds are CAS loops; two per segment, hardly ever contended)
-                if (acc0 != 0.f) atomicAdd(&wacc[my_task][0], acc0);
-                if (acc1 != 0.f) atomicAdd(&wacc[my_task][1], acc1);
-            }
         }
-        // ---- one global atomicAdd per face-vertex component and task
-        __syncthreads();
-        for (int task = threadIdx.x; task < ntasks; task += NTHREADS) {
-            const float acc0 = wacc[task][0], acc1 = wacc[task][1];
-            if (acc0 == 0.f && acc1 == 0.f) continue;
-            const int e = (task % 6) >> 1, axis = task & 1;
-            const int *vp = reinterpret_cast<const int *>(recs + sub[task / 6]) + 10;
-            // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
-            if (acc0 != 0.f) atomicAdd(grad_ndc + (long)__ldg(vp + e) * 3 + (1 - axis), acc0);
-            if (acc1 != 0.f) atomicAdd(grad_ndc + (long)__ldg(vp + (e + 1) % 3) * 3 + (1 - axis), acc1);
-        }
-#endif
         }
     }
 }
@@ -1269,11 +1302,12 @@ int hm_project_bwd(const float *verts, const float *K, int K_batch, const float 
 int hm_raster_setup(const float *ndc, const int32_t *faces, int faces_batch, int B, int V, int F,
                     int image_size, int anti_aliasing, int fill_back, void *records, void *bboxes,
                     void *stream) {
-    HM_REQUIRE(ndc && faces && records && bboxes, "hm_raster_setup: null pointer");
-    HM_REQUIRE(B >= 0 && V > 0 && F >= 0 && (faces_batch == 1 || faces_batch == B), "hm_raster_setup: bad sizes");
+    HM_REQUIRE(B >= 0 && V >= 0 && F >= 0 && (faces_batch == 1 || faces_batch == B), "hm_raster_setup: bad sizes");
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
-    if ((long)B * F == 0) return HM_OK;
+    if ((long)B * F == 0) return HM_OK;  // nothing to set up (empty batch or empty mesh)
+    HM_REQUIRE(ndc && faces && records && bboxes, "hm_raster_setup: null pointer");
+    HM_REQUIRE(V > 0, "hm_raster_setup: bad sizes");
     const long n = (long)B * F;
     face_setup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, hm_stream(stream)>>>(
         ndc, faces, faces_batch, B, V, F, is, fill_back, static_cast<FaceRec *>(records),
@@ -1285,11 +1319,11 @@ int hm_raster_setup(const float *ndc, const int32_t *faces, int faces_batch, int
 int hm_raster_sil_fwd(const void *records, const void *bboxes, int B, int F, int image_size,
                       int anti_aliasing, float near_, float far_, int32_t *face_index, float *alpha,
                       uint32_t *cov_row, uint32_t *cov_col, void *stream) {
-    HM_REQUIRE(records && bboxes && face_index && alpha, "hm_raster_sil_fwd: null pointer");
     HM_REQUIRE(B >= 0 && F >= 0 && B <= 65535, "hm_raster_sil_fwd: bad sizes (B <= 65535)");
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
     if (B == 0) return HM_OK;
+    HM_REQUIRE((F == 0 || (records && bboxes)) && face_index && alpha, "hm_raster_sil_fwd: null pointer");
     dim3 grid((is / TILE) * (is / TILE), B);
     const int fwd_smem = TILE * TILE * (int)sizeof(unsigned long long);
     static bool fwd_configured = false;  // static + dynamic shared memory exceeds the 48 KB default: opt in once
@@ -1311,12 +1345,12 @@ int hm_raster_sil_fwd(const void *records, const void *bboxes, int B, int F, int
 int hm_raster_grad_prep(const float *grad_alpha, const uint32_t *cov_row, const uint32_t *cov_col, int B,
                         int image_size, int anti_aliasing, uint32_t *m_row, uint32_t *m_col, void *runs,
                         uint32_t *run_counts, void *stream) {
-    HM_REQUIRE(grad_alpha && cov_row && cov_col && m_row && m_col && runs && run_counts,
-               "hm_raster_grad_prep: null pointer");
     HM_REQUIRE(B >= 0 && B <= 65535, "hm_raster_grad_prep: bad sizes");
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
     if (B == 0) return HM_OK;
+    HM_REQUIRE(grad_alpha && cov_row && cov_col && m_row && m_col && runs && run_counts,
+               "hm_raster_grad_prep: null pointer");
     dim3 grid((is / TILE) * (is / TILE), B);
     grad_prep_kernel<<<grid, NTHREADS, 0, hm_stream(stream)>>>(grad_alpha, cov_row, cov_col, is, anti_aliasing, m_row,
                                                                m_col);
@@ -1333,13 +1367,14 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
                       const uint32_t *m_row, const uint32_t *m_col, const void *runs, const uint32_t *run_counts,
                       int B, int V, int F, int image_size, int anti_aliasing, float eps, float *grad_ndc,
                       void *stream) {
-    HM_REQUIRE(records && bboxes && face_index && grad_alpha && cov_row && cov_col && m_row && m_col && runs &&
-                   run_counts && grad_ndc,
-               "hm_raster_sil_bwd: null pointer");
-    HM_REQUIRE(B >= 0 && F >= 0 && V > 0 && B <= 65535, "hm_raster_sil_bwd: bad sizes");
+    HM_REQUIRE(B >= 0 && F >= 0 && V >= 0 && B <= 65535, "hm_raster_sil_bwd: bad sizes");
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
     if (B == 0 || F == 0) return HM_OK;
+    HM_REQUIRE(records && bboxes && face_index && grad_alpha && cov_row && cov_col && m_row && m_col && runs &&
+                   run_counts && grad_ndc,
+               "hm_raster_sil_bwd: null pointer");
+    HM_REQUIRE(V > 0, "hm_raster_sil_bwd: bad sizes");
     const size_t smem = (size_t)TILE * TILE * 4 + NWARPS * sizeof(SweepQueue);
     HM_UNSUPPORTED(is > 1024, "hm_raster_sil_bwd: raster size %d > 1024 is not supported", is);
     static size_t configured = 0;  // static + dynamic shared memory exceeds the 48 KB default: opt in once per size
