@@ -614,70 +614,106 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
 // ------------------------------------------------------------------------------------------ sweep masks
 // m_row[b][0] = uncovered & grad < 0 ("missing coverage"), m_row[b][1] = covered & grad > 0 ("excess"),
 // at raster resolution in the raster frame; m_col the same, transposed (one line per column).
+// Streaming kernel, one thread per group of output words, no shared memory: the first n_row threads of an image
+// produce row words (coalesced reads of grad_alpha rows), the others column words (coalesced across columns).
+// With anti-aliasing an output pixel (r, c) is the 2x2 raster block rows is-1-2r, is-2-2r / columns 2c, 2c+1,
+// so 16 gradient signs expand to one 32-bit word of two raster lines.
+__device__ __forceinline__ unsigned dup_bits16(unsigned v) {  // bit k -> bits 2k, 2k + 1
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v | (v << 1);
+}
+
+template <bool AA>
 __global__ void __launch_bounds__(NTHREADS)
 grad_prep_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restrict__ cov_row,
-                 const uint32_t *__restrict__ cov_col, int is, int aa, uint32_t *__restrict__ m_row,
+                 const uint32_t *__restrict__ cov_col, int is, uint32_t *__restrict__ m_row,
                  uint32_t *__restrict__ m_col) {
-    __shared__ float gs[TILE][TILE + 1];
-    __shared__ uint32_t a_row[TILE][2], a_col[TILE][2], out_w[4][TILE][2];
     const int b = blockIdx.y;
-    const int tiles_x = is / TILE;
-    const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int W = is / 32;
-    {   // coverage words of the tile: 64 rows x 2 words, 64 columns x 2 words (one load per thread)
-        const int l = (threadIdx.x >> 1) & 63, w = threadIdx.x & 1;
-        if (threadIdx.x < 128) a_row[l][w] = cov_row[((long)b * is + (ty0 + l)) * W + (tx0 >> 5) + w];
-        else a_col[l][w] = cov_col[((long)b * is + (tx0 + l)) * W + (ty0 >> 5) + w];
-    }
-    if (aa) {
-        const int R = is / 2, rtop = R - 1 - (ty0 >> 1);
-        for (int i = threadIdx.x; i < (TILE / 2) * (TILE / 2); i += NTHREADS) {
-            const int m = i / (TILE / 2), cc = i % (TILE / 2);
-            gs[m][cc] = grad_alpha[((long)b * R + (rtop - m)) * R + (tx0 >> 1) + cc];
+    const int W = is / 32, R = AA ? is / 2 : is;
+    const int n_half = R * W;  // row groups, then as many column groups
+    const int idx = blockIdx.x * NTHREADS + threadIdx.x;
+    if (idx >= 2 * n_half) return;
+    const float *g = grad_alpha + (long)b * R * R;
+    const long plane = (long)is * W;
+    if (idx < n_half) {
+        // ---- row words: output row r, word w
+        const int r = idx / W, w = idx % W;
+        unsigned neg = 0, pos = 0;
+        if (AA) {
+            const float4 *p = reinterpret_cast<const float4 *>(g + (long)r * R + 16 * w);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float4 v = __ldg(p + k);
+                const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    neg |= (a[j] < 0.f ? 1u : 0u) << (4 * k + j);
+                    pos |= (a[j] > 0.f ? 1u : 0u) << (4 * k + j);
+                }
+            }
+            neg = dup_bits16(neg); pos = dup_bits16(pos);
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const int y = is - 1 - 2 * r - d;
+                const long o = ((long)b * 2 * is + y) * W + w;
+                const unsigned A = __ldg(cov_row + ((long)b * is + y) * W + w);
+                m_row[o] = neg & ~A;
+                m_row[o + plane] = pos & A;
+            }
+        } else {
+            const float4 *p = reinterpret_cast<const float4 *>(g + (long)r * R + 32 * w);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float4 v = __ldg(p + k);
+                const float a[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    neg |= (a[j] < 0.f ? 1u : 0u) << (4 * k + j);
+                    pos |= (a[j] > 0.f ? 1u : 0u) << (4 * k + j);
+                }
+            }
+            const int y = is - 1 - r;
+            const long o = ((long)b * 2 * is + y) * W + w;
+            const unsigned A = __ldg(cov_row + ((long)b * is + y) * W + w);
+            m_row[o] = neg & ~A;
+            m_row[o + plane] = pos & A;
         }
     } else {
-        for (int i = threadIdx.x; i < TILE * TILE; i += NTHREADS) {
-            const int yl = i / TILE, xl = i % TILE;
-            gs[yl][xl] = grad_alpha[((long)b * is + (is - 1 - ty0 - yl)) * is + tx0 + xl];
-        }
-    }
-    __syncthreads();
-    const int sh = aa ? 1 : 0;
-    const long plane = (long)is * W;
-    for (int task = warp; task < 2 * TILE; task += NWARPS) {
-        {   // row words: line = raster row, bit = x
-            const int yl = task >> 1, w = task & 1, xl = w * 32 + lane;
-            const float g = gs[yl >> sh][xl >> sh];
-            const unsigned neg = __ballot_sync(0xffffffffu, g < 0.f), pos = __ballot_sync(0xffffffffu, g > 0.f);
-            if (lane == 0) {
-                const unsigned A = a_row[yl][w];
-                out_w[0][yl][w] = neg & ~A;
-                out_w[1][yl][w] = pos & A;
+        // ---- column words: output column c, word w (bit j <-> raster row y = 32 w + j); adjacent threads take
+        //      adjacent columns, so the strided reads down a column coalesce across the warp
+        const int k2 = idx - n_half;
+        const int w = k2 / R, c = k2 % R;
+        unsigned neg = 0, pos = 0;
+        if (AA) {
+#pragma unroll 4
+            for (int k = 0; k < 16; ++k) {
+                const float v = __ldg(g + (long)(R - 1 - 16 * w - k) * R + c);  // rows y = 32 w + 2k, 32 w + 2k + 1
+                neg |= (v < 0.f ? 1u : 0u) << k;
+                pos |= (v > 0.f ? 1u : 0u) << k;
             }
-        }
-        {   // column words: line = raster column, bit = y
-            const int xl = task >> 1, w = task & 1, yl = w * 32 + lane;
-            const float g = gs[yl >> sh][xl >> sh];
-            const unsigned neg = __ballot_sync(0xffffffffu, g < 0.f), pos = __ballot_sync(0xffffffffu, g > 0.f);
-            if (lane == 0) {
-                const unsigned A = a_col[xl][w];
-                out_w[2][xl][w] = neg & ~A;
-                out_w[3][xl][w] = pos & A;
+            neg = dup_bits16(neg); pos = dup_bits16(pos);
+#pragma unroll
+            for (int d = 0; d < 2; ++d) {
+                const int x = 2 * c + d;
+                const long o = ((long)b * 2 * is + x) * W + w;
+                const unsigned A = __ldg(cov_col + ((long)b * is + x) * W + w);
+                m_col[o] = neg & ~A;
+                m_col[o + plane] = pos & A;
             }
-        }
-    }
-    __syncthreads();
-    {   // one store per thread and plane
-        const int l = (threadIdx.x >> 1) & 63, w = threadIdx.x & 1;
-        if (threadIdx.x < 128) {
-            const long o = ((long)b * 2 * is + (ty0 + l)) * W + (tx0 >> 5) + w;
-            m_row[o] = out_w[0][l][w];
-            m_row[o + plane] = out_w[1][l][w];
         } else {
-            const long o = ((long)b * 2 * is + (tx0 + l)) * W + (ty0 >> 5) + w;
-            m_col[o] = out_w[2][l][w];
-            m_col[o + plane] = out_w[3][l][w];
+#pragma unroll 4
+            for (int j = 0; j < 32; ++j) {
+                const float v = __ldg(g + (long)(is - 1 - 32 * w - j) * R + c);
+                neg |= (v < 0.f ? 1u : 0u) << j;
+                pos |= (v > 0.f ? 1u : 0u) << j;
+            }
+            const long o = ((long)b * 2 * is + c) * W + w;
+            const unsigned A = __ldg(cov_col + ((long)b * is + c) * W + w);
+            m_col[o] = neg & ~A;
+            m_col[o + plane] = pos & A;
         }
     }
 }
@@ -1351,9 +1387,13 @@ int hm_raster_grad_prep(const float *grad_alpha, const uint32_t *cov_row, const 
     if (B == 0) return HM_OK;
     HM_REQUIRE(grad_alpha && cov_row && cov_col && m_row && m_col && runs && run_counts,
                "hm_raster_grad_prep: null pointer");
-    dim3 grid((is / TILE) * (is / TILE), B);
-    grad_prep_kernel<<<grid, NTHREADS, 0, hm_stream(stream)>>>(grad_alpha, cov_row, cov_col, is, anti_aliasing, m_row,
-                                                               m_col);
+    const int out_size = anti_aliasing ? is / 2 : is;
+    HM_UNSUPPORTED(out_size % 32 != 0, "hm_raster_grad_prep: image size %d must be a multiple of 32", out_size);
+    dim3 grid((2 * out_size * (is / 32) + NTHREADS - 1) / NTHREADS, B);
+    if (anti_aliasing)
+        grad_prep_kernel<true><<<grid, NTHREADS, 0, hm_stream(stream)>>>(grad_alpha, cov_row, cov_col, is, m_row, m_col);
+    else
+        grad_prep_kernel<false><<<grid, NTHREADS, 0, hm_stream(stream)>>>(grad_alpha, cov_row, cov_col, is, m_row, m_col);
     HM_CHECK_LAUNCH("hm_raster_grad_prep");
     dim3 grid2((4 * is + NTHREADS - 1) / NTHREADS, B);
     build_runs_kernel<<<grid2, NTHREADS, 0, hm_stream(stream)>>>(grad_alpha, m_row, m_col, is, anti_aliasing,

@@ -11,4 +11,7 @@ ncu --set full --clock-control none --import-source on -k regex:'raster_bwd|rast
     -o gpurun_out/prof_raster_final python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/prof_raster_final.log 2>&1
 python scripts/bench_raster_vs_nmr_style.py > gpurun_out/raster_vs_nmr_style.json 2> gpurun_out/raster_vs_nmr_style.err
 python scripts/bench_pose_init.py --out gpurun_out/pose_init.json > /dev/null 2> gpurun_out/pose_init.err
+python bench.py --workload cfg5 --steps 20 --no-cpu-baseline > gpurun_out/bench_cfg5_n1.json 2> gpurun_out/bench_cfg5_n1.err
+python bench.py --workload cfg2 --steps 50 --no-cpu-baseline > gpurun_out/bench_cfg2_n1.json 2> gpurun_out/bench_cfg2_n1.err
+python -c 'import __graft_entry__ as g; g.smoke()' > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
 tail -c 400 gpurun_out/bench_cfg3_n1.json; tail -c 300 gpurun_out/bench_reference.json
