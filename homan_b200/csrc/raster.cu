@@ -1258,6 +1258,46 @@ raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     }
 }
 
+// ------------------------------------------------------------------------------------------ RGB / depth (visualisation)
+// Forward of nr.rasterize_rgbad for texture_size 1 on top of the face_index map: a covered raster sample takes the
+// lit colour of its face (doubled numbering: f or F + f) and the reference's interpolated depth (same arithmetic
+// as the z-buffer of the oracle), an uncovered one the background colour and `far`; vertical flip and, with
+// anti-aliasing, the 2x2 average. One thread per output pixel. Visualisation only (no backward).
+__global__ void __launch_bounds__(NTHREADS)
+raster_shade_kernel(const FaceRec *__restrict__ recs, const int32_t *__restrict__ face_index,
+                    const float *__restrict__ colours, int colours_batch, int B, int F, int is, int aa, float far_,
+                    float bg0, float bg1, float bg2, float *__restrict__ rgb, float *__restrict__ depth) {
+    const int R = aa ? is / 2 : is;
+    const long i = (long)blockIdx.x * NTHREADS + threadIdx.x;
+    if (i >= (long)B * R * R) return;
+    const int b = (int)(i / ((long)R * R)), r = (int)((i / R) % R), c = (int)(i % R);
+    const int n = aa ? 2 : 1;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // torch's avg_pool2d sums the window row by row (flipped rows 2r, 2r + 1 = raster rows is-1-2r, is-2-2r)
+    for (int dy = 0; dy < n; ++dy)
+        for (int dx = 0; dx < n; ++dx) {
+            const int yi = is - 1 - (n * r + dy), xi = n * c + dx;
+            const int fn = face_index[((long)b * is + yi) * is + xi];
+            float px[4] = {bg0, bg1, bg2, far_};
+            if (fn >= 0) {
+                const FaceRec &rec = recs[(long)b * F + (fn >= F ? fn - F : fn)];
+                const float *col = colours + ((long)(colours_batch > 1 ? b : 0) * 2 * F + fn) * 3;
+                px[0] = col[0]; px[1] = col[1]; px[2] = col[2];
+                px[3] = exact_depth(rec.inv, xi, yi, rec.c[2], rec.c[5], rec.c[8]);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) acc[k] += px[k];
+        }
+    const float s = aa ? 0.25f : 1.f;
+    const long plane = (long)R * R, o = (long)r * R + c;
+    if (rgb) {
+        rgb[((long)b * 3 + 0) * plane + o] = acc[0] * s;
+        rgb[((long)b * 3 + 1) * plane + o] = acc[1] * s;
+        rgb[((long)b * 3 + 2) * plane + o] = acc[2] * s;
+    }
+    if (depth) depth[(long)b * plane + o] = acc[3] * s;
+}
+
 // ------------------------------------------------------------------------------------------ silhouette loss
 __global__ void __launch_bounds__(NTHREADS)
 sil_loss_kernel(const float *__restrict__ alpha, const int8_t *__restrict__ target, const float *__restrict__ norm,
@@ -1443,6 +1483,22 @@ int hm_sil_loss_fwd_bwd(const float *alpha, const int8_t *target, const float *n
     sil_loss_kernel<<<B, NTHREADS, 0, hm_stream(stream)>>>(alpha, target, norm, weight, image_size * image_size,
                                                            loss_img, loss_stride, iou_img, iou_stride, grad_alpha);
     HM_CHECK_LAUNCH("hm_sil_loss_fwd_bwd");
+    return HM_OK;
+}
+
+int hm_raster_shade(const void *records, const int32_t *face_index, const float *colours, int colours_batch, int B,
+                    int F, int image_size, int anti_aliasing, float far_, float bg_r, float bg_g, float bg_b,
+                    float *rgb, float *depth, void *stream) {
+    HM_REQUIRE(B >= 0 && F >= 0 && (colours_batch == 1 || colours_batch == B), "hm_raster_shade: bad sizes");
+    int is;
+    if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
+    if (B == 0) return HM_OK;
+    HM_REQUIRE(face_index && (F == 0 || (records && colours)) && (rgb || depth), "hm_raster_shade: null pointer");
+    const long n = (long)B * image_size * image_size;
+    raster_shade_kernel<<<(unsigned)((n + NTHREADS - 1) / NTHREADS), NTHREADS, 0, hm_stream(stream)>>>(
+        static_cast<const FaceRec *>(records), face_index, colours, colours_batch, B, F, is, anti_aliasing, far_, bg_r,
+        bg_g, bg_b, rgb, depth);
+    HM_CHECK_LAUNCH("hm_raster_shade");
     return HM_OK;
 }
 

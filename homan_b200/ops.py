@@ -133,3 +133,45 @@ def rasterize_silhouettes(ndc, faces, image_size=256, anti_aliasing=True, fill_b
                           eps=RASTER_EPS, return_face_index=False):
     alpha, face_index = _RasterizeSilhouettes.apply(ndc, faces, image_size, anti_aliasing, fill_back, near, far, eps)
     return (alpha, face_index) if return_face_index else alpha
+
+
+# ------------------------------------------------------------------------------------------ RGB / depth (visualisation)
+def lighting(faces_xyz, colours, intensity_ambient=0.5, intensity_directional=0.5, color_ambient=(1, 1, 1),
+             color_directional=(1, 1, 1), direction=(0, 1, 0)):
+    """nr.lighting for flat per-face colours: faces_xyz [B,nf,3,3] (3-D corners), colours [B,nf,3] -> lit colours."""
+    dev = faces_xyz.device
+    ca = torch.as_tensor(color_ambient, dtype=torch.float32, device=dev).view(1, 1, 3)
+    cd = torch.as_tensor(color_directional, dtype=torch.float32, device=dev).view(1, 1, 3)
+    d = torch.as_tensor(direction, dtype=torch.float32, device=dev).view(1, 1, 3)
+    light = torch.zeros_like(colours)
+    if intensity_ambient != 0:
+        light = light + intensity_ambient * ca
+    if intensity_directional != 0:
+        n = torch.cross(faces_xyz[:, :, 0] - faces_xyz[:, :, 1], faces_xyz[:, :, 2] - faces_xyz[:, :, 1], dim=2)
+        n = torch.nn.functional.normalize(n, dim=2, eps=1e-5)
+        light = light + intensity_directional * cd * torch.relu((n * d).sum(2, keepdim=True))
+    return colours * light
+
+
+def render_rgbd(ndc, faces, lit_colours, image_size=256, anti_aliasing=True, fill_back=True, near=NEAR, far=FAR,
+                background_color=(0, 0, 0)):
+    """Forward of nr.rasterize_rgbad for texture_size 1 (visualisation, no gradient): ndc [B,V,3] projected
+    vertices, faces [1|B,F,3], lit_colours [1|B,2F,3] (doubled numbering) -> rgb [B,3,R,R], depth [B,R,R],
+    alpha [B,R,R]."""
+    _check_cuda(ndc, faces, lit_colours)
+    with torch.no_grad():
+        ndc_c = _f32(ndc)
+        faces_c = faces.detach().contiguous().int()
+        if faces_c.dim() == 2:
+            faces_c = faces_c[None]
+        B, V = ndc_c.shape[:2]
+        F = faces_c.shape[1]
+        buf = RasterBuffers(B, V, F, image_size, anti_aliasing, ndc_c.device)
+        raster_forward(buf, ndc_c, faces_c, fill_back, near, far)
+        col = _f32(lit_colours).view(-1, 2 * F, 3)
+        rgb = torch.empty(B, 3, image_size, image_size, device=ndc_c.device)
+        depth = torch.empty(B, image_size, image_size, device=ndc_c.device)
+        bg = [float(x) for x in background_color]
+        call("hm_raster_shade", ptr(buf.records), ptr(buf.face_index), ptr(col), col.shape[0], B, F, image_size,
+             int(bool(anti_aliasing)), float(far), bg[0], bg[1], bg[2], ptr(rgb), ptr(depth), current_stream())
+        return rgb, depth, buf.alpha

@@ -1,8 +1,8 @@
 """Drop-in for the `neural_renderer` package on the reference's path (silhouette mode):
 `nr.renderer.Renderer(image_size, K, R, t, orig_size, ...)(vertices, faces, mode="silhouettes", K=...)`
 (/root/reference/homan/losses.py:73-77,172-176,187; homan/homan.py:168-176) and `nr.projection`
-(/root/reference/homan/losses.py:34-41). RGB / depth rendering (`mode=None`, `.render`) is visualisation and
-is not provided."""
+(/root/reference/homan/losses.py:34-41), plus the forward of the RGB / depth render the reference uses for
+visualisation (`mode=None`, `.render`; /root/reference/homan/homan.py:510-613) for texture_size-1 textures."""
 import sys
 import types
 
@@ -47,7 +47,39 @@ class Renderer(nn.Module):
                 orig_size=None):
         if mode == "silhouettes":
             return self.render_silhouettes(vertices, faces, K, R, t, dist_coeffs, orig_size)
-        raise NotImplementedError("homan_b200 Renderer: only mode='silhouettes' (RGB / depth rendering is visualisation)")
+        if mode is None:
+            return self.render(vertices, faces, textures, K, R, t, dist_coeffs, orig_size)
+        raise NotImplementedError("homan_b200 Renderer: mode=None (rgb, depth, alpha) or mode='silhouettes'")
+
+    def render(self, vertices, faces, textures, K=None, R=None, t=None, dist_coeffs=None, orig_size=None):
+        """(rgb [B,3,R,R], depth [B,R,R], alpha [B,R,R]) for texture_size-1 textures [B,F,1,1,1,3]: flat lighting on the
+        3-D faces, projection, z-buffer, colour / depth of the winning face. Forward only (visualisation)."""
+        if textures.shape[2] != 1:
+            raise NotImplementedError("homan_b200 Renderer.render: texture_size 1 (flat colour per face) only")
+        K = self.K if K is None else K
+        R = self.R if R is None else R
+        t = self.t if t is None else t
+        dist_coeffs = self.dist_coeffs if dist_coeffs is None else dist_coeffs
+        orig_size = self.orig_size if orig_size is None else orig_size
+        with torch.no_grad():
+            B, F = vertices.shape[0], faces.shape[-2]
+            f = faces if faces.dim() == 3 else faces[None]
+            f = f.expand(B, -1, -1)
+            colours = textures.reshape(textures.shape[0], F, 3).float().expand(B, -1, -1)
+            if self.fill_back:
+                f2 = torch.cat((f, f.flip(-1)), dim=1)
+                colours = torch.cat((colours, colours), dim=1)
+            else:
+                f2 = f
+                colours = torch.cat((colours, torch.zeros_like(colours)), dim=1)
+            lit = ops.lighting(vertices_to_faces(vertices.float(), f2), colours[:, :f2.shape[1]],
+                               self.light_intensity_ambient, self.light_intensity_directional,
+                               self.light_color_ambient, self.light_color_directional, self.light_direction)
+            if not self.fill_back:
+                lit = torch.cat((lit, torch.zeros_like(lit)), dim=1)
+            ndc = ops.project(vertices, K, R, t, dist_coeffs, orig_size)
+            return ops.render_rgbd(ndc, f, lit, self.image_size, self.anti_aliasing, self.fill_back, self.near,
+                                   self.far, self.background_color)
 
     def render_silhouettes(self, vertices, faces, K=None, R=None, t=None, dist_coeffs=None, orig_size=None):
         K = self.K if K is None else K

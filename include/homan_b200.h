@@ -80,6 +80,14 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
                       int B, int V, int F, int image_size, int anti_aliasing, float eps, float *grad_ndc,
                       void *stream);
 
+/* Forward of nr.Renderer.render / rasterize_rgbad for texture_size 1 (visualisation: homan/homan.py:510-613,
+ * homan/visualize.py:44-128, homan/utils/nmr_renderer.py:71,164,209), on top of hm_raster_setup + hm_raster_sil_fwd:
+ * colours [colours_batch, 2F, 3] = lit colour of every face in the doubled numbering (f, F + f);
+ * rgb [B,3,R,R] (may be NULL) = colour of the winning face or the background, depth [B,R,R] (may be NULL) = the
+ * reference's interpolated depth or `far`; both after the vertical flip and the 2x2 average when anti-aliasing. */
+int hm_raster_shade(const void *records, const int32_t *face_index, const float *colours, int colours_batch, int B,
+                    int F, int image_size, int anti_aliasing, float far_, float bg_r, float bg_g, float bg_b,
+                    float *rgb, float *depth, void *stream);
 /* Losses.compute_sil_loss_object (homan/losses.py:183-197) on a rendered alpha:
  * target int8 [B,R,R] in {-1 occluded, 0, 1}; norm [B] = 1 / (sum keep * T) of the image's problem;
  * loss_img[b*loss_stride] = norm * sum (keep*alpha - ref)^2 ; iou_img[b*iou_stride] (mask IoU, metric);

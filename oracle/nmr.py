@@ -1,7 +1,7 @@
 """ORACLE (test infrastructure; never imported by the product).
 
 CPU stand-in for the `neural_renderer` package (Kato NMR, PyTorch port of
-hassony2/multiperson), silhouette path only, as used by the reference at
+hassony2/multiperson): the silhouette path and the forward of the RGB / depth render, as used by the reference at
 /root/reference/homan/losses.py:34-41,73-77,172-176,187 and
 /root/reference/homan/homan.py:168-176.  Semantics: SURVEY.md Appendix A.1-A.3
 (third-party package absent from the reference tree: parity unpinned).
@@ -95,6 +95,56 @@ def rasterize_silhouettes(faces, image_size=256, anti_aliasing=True, near=DEFAUL
     return alpha
 
 
+def lighting(faces, textures, intensity_ambient=0.5, intensity_directional=0.5, color_ambient=(1, 1, 1),
+             color_directional=(1, 1, 1), direction=(0, 1, 0)):
+    """nr.lighting (Appendix A.1): flat shading, light = ambient + directional * relu(n . direction) with the face normal
+    n = normalize(cross(v0 - v1, v2 - v1), eps=1e-5). faces [B,nf,3,3] (3-D, before projection), textures
+    [B,nf,ts,ts,ts,3] -> lit textures."""
+    bs, nf = faces.shape[:2]
+    ca = torch.as_tensor(color_ambient, dtype=torch.float32).view(1, 3)
+    cd = torch.as_tensor(color_directional, dtype=torch.float32).view(1, 3)
+    d = torch.as_tensor(direction, dtype=torch.float32).view(1, 1, 3)
+    light = torch.zeros(bs, nf, 3)
+    if intensity_ambient != 0:
+        light = light + intensity_ambient * ca[:, None, :]
+    if intensity_directional != 0:
+        f = faces.reshape(bs * nf, 3, 3)
+        normals = torch.nn.functional.normalize(torch.cross(f[:, 0] - f[:, 1], f[:, 2] - f[:, 1], dim=1), eps=1e-5)
+        cos = torch.relu(torch.sum(normals.reshape(bs, nf, 3) * d, dim=2))
+        light = light + intensity_directional * (cd[:, None, :] * cos[:, :, None])
+    return textures * light[:, :, None, None, None, :]
+
+
+def rasterize_rgbad(faces, textures, image_size=256, anti_aliasing=True, near=DEFAULT_NEAR, far=DEFAULT_FAR,
+                    background_color=(0, 0, 0)):
+    """Forward of nr.rasterize_rgbad for texture_size 1 (flat colour per face; the reference's textures are
+    [B,F,1,1,1,3], /root/reference/homan/homan.py:510-518): rgb [B,3,R,R], depth [B,R,R], alpha [B,R,R] after the
+    vertical flip and, with anti-aliasing, the 2x2 average pool. Visualisation only: no backward."""
+    if textures.shape[2] != 1:
+        raise NotImplementedError("oracle rasterize_rgbad: texture_size 1 only")
+    lib = _build.lib()
+    is_ = image_size * 2 if anti_aliasing else image_size
+    faces_c = faces.detach().contiguous().float()
+    B, nf = faces_c.shape[:2]
+    face_index = torch.empty(B, is_, is_, dtype=torch.int32)
+    depth = torch.empty(B, is_, is_)
+    lib.nmr_face_index_map(_ptr(faces_c), B, nf, is_, near, far, _ptr(face_index), _ptr(depth))
+    covered = face_index >= 0
+    colours = textures.detach().reshape(B, nf, 3).float()
+    idx = face_index.clamp(min=0).long().view(B, -1)
+    rgb = torch.gather(colours, 1, idx[:, :, None].expand(-1, -1, 3)).view(B, is_, is_, 3)
+    bg = torch.as_tensor(background_color, dtype=torch.float32)
+    rgb = torch.where(covered[..., None], rgb, bg.view(1, 1, 1, 3).expand_as(rgb))
+    alpha = covered.float()
+    flip = list(reversed(range(is_)))
+    rgb = rgb.permute(0, 3, 1, 2)[:, :, flip, :]
+    alpha, depth = alpha[:, flip, :], depth[:, flip, :]
+    if anti_aliasing:
+        pool = lambda x: torch.nn.functional.avg_pool2d(x, kernel_size=(2, 2))  # noqa: E731
+        rgb, alpha, depth = pool(rgb), pool(alpha[:, None])[:, 0], pool(depth[:, None])[:, 0]
+    return rgb, depth, alpha
+
+
 class Renderer(nn.Module):
     """Subset of nr.renderer.Renderer used by the reference (Appendix A.1)."""
 
@@ -134,7 +184,9 @@ class Renderer(nn.Module):
                 orig_size=None):
         if mode == "silhouettes":
             return self.render_silhouettes(vertices, faces, K, R, t, dist_coeffs, orig_size)
-        raise NotImplementedError("oracle Renderer implements mode='silhouettes' only (RGB render is viz)")
+        if mode is None:
+            return self.render(vertices, faces, textures, K, R, t, dist_coeffs, orig_size)
+        raise NotImplementedError("oracle Renderer implements mode=None and mode='silhouettes'")
 
     def project_faces(self, vertices, faces, K=None, R=None, t=None, dist_coeffs=None, orig_size=None):
         if self.fill_back:
@@ -150,3 +202,18 @@ class Renderer(nn.Module):
     def render_silhouettes(self, vertices, faces, K=None, R=None, t=None, dist_coeffs=None, orig_size=None):
         faces_v = self.project_faces(vertices, faces, K, R, t, dist_coeffs, orig_size)
         return rasterize_silhouettes(faces_v, self.image_size, self.anti_aliasing)
+
+    def render(self, vertices, faces, textures, K=None, R=None, t=None, dist_coeffs=None, orig_size=None):
+        """Renderer.render (Appendix A.1): fill_back, flat lighting on the 3-D faces, projection, rasterize_rgbad ->
+        (rgb [B,3,R,R], depth [B,R,R], alpha [B,R,R]). Used by the reference for visualisation
+        (/root/reference/homan/homan.py:535, homan/utils/nmr_renderer.py:71,164,209)."""
+        faces_l = faces
+        if self.fill_back:
+            faces_l = torch.cat((faces, faces[:, :, list(reversed(range(faces.shape[-1])))]), dim=1)
+            textures = torch.cat((textures, textures.permute((0, 1, 4, 3, 2, 5))), dim=1)
+        textures = lighting(vertices_to_faces(vertices, faces_l), textures, self.light_intensity_ambient,
+                            self.light_intensity_directional, self.light_color_ambient, self.light_color_directional,
+                            self.light_direction)
+        faces_v = self.project_faces(vertices, faces, K, R, t, dist_coeffs, orig_size)
+        return rasterize_rgbad(faces_v, textures, self.image_size, self.anti_aliasing, self.near, self.far,
+                               self.background_color)
