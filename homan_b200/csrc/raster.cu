@@ -801,7 +801,10 @@ __device__ __forceinline__ float harmonic_span(float z1, float n) {
 // are evaluated with the reference's expression; beyond, every pixel has the same weight G and the sum of
 // 1 / dist is the harmonic sum G / K * sum 1 / (z + k + eps / |K|), taken in closed form (dist = K (d1 - x) +- eps,
 // K = c * 2 / is). Straight-line code: every lane of a warp does the same work whatever its item looks like.
-constexpr int NEAR_N = 4;
+#ifndef HM_NEAR_N
+#define HM_NEAR_N 4
+#endif
+constexpr int NEAR_N = HM_NEAR_N;
 __device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, int s, int e, bool has0, bool has1,
                                           float inv_is2, float eps, float &a0, float &a1) {
     const float K0 = c0 * inv_is2, K1 = c1 * inv_is2;
