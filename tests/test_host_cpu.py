@@ -66,3 +66,27 @@ def test_no_cpu_fallback(mano_assets):
     from homan_b200 import ops
     with pytest.raises(_lib.HomanB200Error):
         ops.project(torch.zeros(1, 4, 3), torch.eye(3)[None])
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the behaviour on a machine without a GPU")
+def test_no_cpu_fallback_pose_fitter_and_render():
+    """The rows added after the hot path (object-pose initialiser, RGB / depth render) fail loudly without a GPU too."""
+    from homan_b200 import ops, pose_optimization as po
+    verts, faces = synth.make_object("cube")
+    with pytest.raises(_lib.HomanB200Error):
+        po.PoseFitEngine(verts, faces, np.zeros((256, 256), np.float32), np.eye(3, dtype=np.float32),
+                         np.zeros((2, 3, 2), np.float32), np.zeros((2, 3), np.float32))
+    with pytest.raises(_lib.HomanB200Error):
+        ops.render_rgbd(torch.zeros(1, 8, 3), torch.zeros(1, 12, 3, dtype=torch.int32), torch.zeros(1, 24, 3), 64)
+    with pytest.raises(_lib.HomanB200Error):
+        ops.rasterize_silhouettes(torch.zeros(1, 8, 3), torch.zeros(1, 12, 3, dtype=torch.int32), 64)
+
+
+def test_header_declares_every_new_entry_point_with_a_reference_citation():
+    text = open(_lib.HEADER_PATH).read()
+    for name, cite in (("hm_offscreen_loss_fwd_bwd", "pose_optimization.py:112-134"),
+                       ("hm_track_best", "pose_optimization.py:349-353"), ("hm_raster_shade", "homan/homan.py:510-613")):
+        assert name in _lib.SIGNATURES, name
+        assert cite in text, cite
+    handle = _lib.lib()
+    assert all(hasattr(handle, n) for n in ("hm_offscreen_loss_fwd_bwd", "hm_track_best", "hm_raster_shade"))
