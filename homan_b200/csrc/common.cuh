@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <atomic>
+
 #include "../../include/homan_b200.h"
 
 void hm_set_error(const char *fmt, ...);
@@ -36,6 +38,31 @@ void hm_set_error(const char *fmt, ...);
     } while (0)
 
 static inline cudaStream_t hm_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// Opt-in to more than 48 KB of dynamic shared memory. The attribute belongs to the (device, kernel) pair, so the
+// bookkeeping is per device: one slot per ordinal, written with relaxed atomics (two host threads racing on the same
+// device both issue the call, which is idempotent). `state` is one zero-initialised array per kernel.
+constexpr int HM_MAX_DEVICES = 64;
+struct HmSmemOptIn {
+    std::atomic<size_t> configured[HM_MAX_DEVICES];
+};
+template <class Kernel>
+static inline int hm_smem_opt_in(Kernel kernel, size_t bytes, HmSmemOptIn &state, const char *who) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess && dev >= 0 && dev < HM_MAX_DEVICES &&
+        state.configured[dev].load(std::memory_order_relaxed) >= bytes)
+        return HM_OK;
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) {
+        hm_set_error("%s: cudaFuncSetAttribute(%zu bytes of shared memory): %s", who, bytes, cudaGetErrorString(e));
+        (void)cudaGetLastError();
+        return HM_ERR_CUDA;
+    }
+    if (dev >= 0 && dev < HM_MAX_DEVICES) state.configured[dev].store(bytes, std::memory_order_relaxed);
+    return HM_OK;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -69,7 +69,8 @@ contact_kernel(const float *__restrict__ vh, const float *__restrict__ vo, int T
         acc[0] += thresh * th;
         mind[0] = fmaxf(mind[0], -sqrtf(fmaxf(best[s], 0.f)));
         if (weight != 0.f) {
-            const float c = weight * scale * (1.f - th * th) / a;  // d/d a of thresh*tanh(a/thresh), over a
+            // d/d a of thresh*tanh(a/thresh), over a; coincident vertices: subgradient 0 (torch.norm backward at 0)
+            const float c = a > 0.f ? weight * scale * (1.f - th * th) / a : 0.f;
             const float gx = c * dx, gy = c * dy, gz = c * dz;
             if (g_vo) {
                 float *g = g_vo + ((long)b * Vo + bi[s]) * 3;

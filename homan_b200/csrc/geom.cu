@@ -121,7 +121,7 @@ vertex_losses_kernel(const float *__restrict__ vh, const float *__restrict__ vo,
                 const float *q = h - NVH * 3 + 3 * i;
                 dp[0] = x - q[0]; dp[1] = y - q[1]; dp[2] = z - q[2];
             }
-            const float c = w_sh * 2.f / n_sh;
+            const float c = T > 1 ? w_sh * 2.f / n_sh : 0.f;  // T == 1: no frame pair, no gradient (not inf * 0)
             gx += c * (dp[0] - dn[0]); gy += c * (dp[1] - dn[1]); gz += c * (dp[2] - dn[2]);
         }
         if (do_v2d) {
@@ -166,7 +166,7 @@ vertex_losses_kernel(const float *__restrict__ vh, const float *__restrict__ vo,
                 dp[0] = x - q[0]; dp[1] = y - q[1]; dp[2] = z - q[2];
             }
             if (g_vo) {
-                const float c = w_so * 2.f / n_so;
+                const float c = T > 1 ? w_so * 2.f / n_so : 0.f;
                 float *g = g_vo + ((long)b * Vo + i) * 3;
                 g[0] += c * (dp[0] - dn[0]); g[1] += c * (dp[1] - dn[1]); g[2] += c * (dp[2] - dn[2]);
             }

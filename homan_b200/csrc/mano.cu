@@ -473,15 +473,8 @@ int hm_mano_bwd(const float *model, int ncomps, int left, const float *pca, int 
     HM_REQUIRE(B >= 0 && ncomps >= 0 && ncomps <= 45 && pca_stride >= ncomps, "hm_mano_bwd: bad sizes");
     if (B == 0) return HM_OK;
     const size_t smem = ((sizeof(Shared) + 15) / 16) * 16 + sizeof(SharedBwd);
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(mano_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            hm_set_error("hm_mano_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return HM_ERR_CUDA;
-        }
-        configured = true;
-    }
+    static HmSmemOptIn opt_in;
+    if (int rc = hm_smem_opt_in(mano_bwd_kernel, smem, opt_in, "hm_mano_bwd")) return rc;
     mano_bwd_kernel<<<B, NT, smem, hm_stream(stream)>>>(model, ncomps, left, pca, pca_stride, rot, betas, mano_trans,
                                                         rot6d, trans, scale, grad_verts, grad_centroid_det, grad_pca,
                                                         grad_rot, grad_betas, grad_mano_trans, grad_rot6d, grad_trans);

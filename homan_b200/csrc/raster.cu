@@ -1405,15 +1405,8 @@ int hm_raster_sil_fwd(const void *records, const void *bboxes, int B, int F, int
     HM_REQUIRE((F == 0 || (records && bboxes)) && face_index && alpha, "hm_raster_sil_fwd: null pointer");
     dim3 grid((is / TILE) * (is / TILE), B);
     const int fwd_smem = TILE * TILE * (int)sizeof(unsigned long long);
-    static bool fwd_configured = false;  // static + dynamic shared memory exceeds the 48 KB default: opt in once
-    if (!fwd_configured) {
-        cudaError_t e = cudaFuncSetAttribute(raster_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem);
-        if (e != cudaSuccess) {
-            hm_set_error("hm_raster_sil_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return HM_ERR_CUDA;
-        }
-        fwd_configured = true;
-    }
+    static HmSmemOptIn opt_in;  // static + dynamic shared memory exceeds the 48 KB default
+    if (int rc = hm_smem_opt_in(raster_fwd_kernel, fwd_smem, opt_in, "hm_raster_sil_fwd")) return rc;
     raster_fwd_kernel<<<grid, NTHREADS, fwd_smem, hm_stream(stream)>>>(
         static_cast<const FaceRec *>(records), static_cast<const FaceBox *>(bboxes), F, is, anti_aliasing, near_, far_,
         face_index, alpha, cov_row, cov_col);
@@ -1460,15 +1453,8 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
     HM_REQUIRE(V > 0, "hm_raster_sil_bwd: bad sizes");
     const size_t smem = (size_t)TILE * TILE * 4 + NWARPS * sizeof(SweepQueue);
     HM_UNSUPPORTED(is > 1024, "hm_raster_sil_bwd: raster size %d > 1024 is not supported", is);
-    static size_t configured = 0;  // static + dynamic shared memory exceeds the 48 KB default: opt in once per size
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(raster_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            hm_set_error("hm_raster_sil_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return HM_ERR_CUDA;
-        }
-        configured = smem;
-    }
+    static HmSmemOptIn opt_in;  // static + dynamic shared memory exceeds the 48 KB default
+    if (int rc = hm_smem_opt_in(raster_bwd_kernel, smem, opt_in, "hm_raster_sil_bwd")) return rc;
     dim3 grid((is / TILE) * (is / TILE), B);
     raster_bwd_kernel<<<grid, NTHREADS, smem, hm_stream(stream)>>>(
         static_cast<const FaceRec *>(records), static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps,

@@ -329,15 +329,8 @@ int hm_sdf_pair(const float *verts_g, const int32_t *faces_g, const float *verts
     const size_t smem = (size_t)((Vg * 3 + 3) / 4) * 4 * sizeof(float) + (size_t)Fg * 4 * sizeof(float);
     HM_UNSUPPORTED(smem > 160 * 1024, "hm_sdf_pair: grid mesh with %d vertices does not fit shared memory", Vg);
     if (B == 0) return HM_OK;
-    static size_t configured = 0;
-    if (smem > configured) {
-        cudaError_t e = cudaFuncSetAttribute(sdf_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) {
-            hm_set_error("hm_sdf_pair: cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            return HM_ERR_CUDA;
-        }
-        configured = smem;
-    }
+    static HmSmemOptIn opt_in;
+    if (int rc = hm_smem_opt_in(sdf_pair_kernel, smem, opt_in, "hm_sdf_pair")) return rc;
     const float half_factor = (float)((1.0 + (double)scale_factor) * 0.5);
     sdf_pair_kernel<<<B, PNT, smem, hm_stream(stream)>>>(verts_g, faces_g, verts_s, Vg, Fg, Vs, half_factor, weight,
                                                         phi_scratch, partials, grad_verts_s);

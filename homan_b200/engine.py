@@ -302,7 +302,7 @@ class FitEngine:
         call("hm_rigid_bwd", ptr(self.mesh_obj), 1, ptr(self.params["rotations_object"]), ptr(self.scale_obj), B,
              self.Vo, ptr(self.g_verts_obj), ptr(g["rotations_object"]), ptr(g["translations_object"]), s)
         call("hm_finalize_losses", ptr(self.partials), ptr(self.weights_part), self.P, T, ptr(self.losses),
-             ptr(self.total), ptr(self.step_counter), s)
+             ptr(self.total), ptr(self.step_counter) if adam else None, s)   # forward-only: Adam's step count untouched
         n += 3
         if adam:
             call("hm_adam_step", ptr(self.flat), ptr(self.grad_flat), ptr(self.exp_avg), ptr(self.exp_avg_sq),
@@ -315,7 +315,6 @@ class FitEngine:
     def evaluate(self):
         """Forward + backward at the current parameters, no Adam update. Leaves losses / grads filled."""
         self._iteration(adam=False)
-        self.step_counter.zero_()
         return self.loss_dict()
 
     def capture(self):

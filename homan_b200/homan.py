@@ -32,8 +32,7 @@ class _FusedLosses(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, weights, *params):
         eng = model.engine
-        eng._iteration(adam=False)
-        eng.step_counter.zero_()
+        eng._iteration(adam=False)   # forward-only: the Adam step counter is not touched
         ctx.model, ctx.weights = model, weights
         names = model._loss_names
         vals = torch.stack([eng.losses[:, model._slot_of[n]].sum() for n in names]) if names else eng.losses.new_zeros(0)
