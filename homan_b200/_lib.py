@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhoman_b200.so")
+LIB_PATH = os.environ.get("HOMAN_B200_LIB") or os.path.join(_HERE, "libhoman_b200.so")   # env: an alternative build
 
 _P, _I, _F = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
 

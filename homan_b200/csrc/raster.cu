@@ -29,7 +29,20 @@ struct __align__(16) FaceRec {
     int exact;     // 1: some corner depth is not a plain positive float -> forward uses the reference arithmetic only
     float pad2[3];
 };
-static_assert(sizeof(FaceRec) == HM_FACE_RECORD_BYTES, "record size");
+static_assert(sizeof(FaceRec) == 128, "record size");
+
+// Backward record: pixel-space corners of the stored winding and the slope of every edge along both sweep axes
+// (the quotients backward_pixel_map evaluates per crossing, computed once with the same rounded operations).
+struct __align__(16) BwdRec {
+    float px[3], py[3];   // to_pix of the corners
+    float slope[3][2];    // edge e = corner e -> e + 1: [0] = dy / dx (axis 0: lines x = d0), [1] = dx / dy (axis 1)
+    int v[3];             // vertex indices
+    int meta;             // < 0: culled / off screen; else fn | BWD_IRREGULAR | BWD_BOTH
+};
+static_assert(sizeof(BwdRec) == 64 && sizeof(FaceRec) + sizeof(BwdRec) == HM_FACE_RECORD_BYTES, "record size");
+constexpr int BWD_FN_MASK = (1 << 29) - 1;
+constexpr int BWD_IRREGULAR = 1 << 29;   // a corner on an integer pixel coordinate (or not finite): never skipped
+constexpr int BWD_BOTH = 1 << 30;        // both windings are front-facing: F + f is differentiated too
 
 struct __align__(8) FaceBox {
     short x0, y0, x1, y1;
@@ -110,7 +123,7 @@ __device__ __forceinline__ float to_pix(float v, int is) { return 0.5f * (v * is
 
 __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *__restrict__ faces, int faces_batch,
                                   int B, int V, int F, int is, int fill_back, FaceRec *__restrict__ recs,
-                                  FaceBox *__restrict__ boxes) {
+                                  BwdRec *__restrict__ brecs, FaceBox *__restrict__ boxes) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long)B * F) return;
     const int b = (int)(i / F), f = (int)(i % F);
@@ -182,6 +195,26 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
         }
     }
     recs[i] = r;
+    {
+        BwdRec br;
+        bool irregular = false;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            br.px[k] = to_pix(r.c[3 * k], is);
+            br.py[k] = to_pix(r.c[3 * k + 1], is);
+            br.v[k] = r.v[k];
+            irregular |= !(fabsf(br.px[k]) < 1e30f) || !(fabsf(br.py[k]) < 1e30f) || br.px[k] == floorf(br.px[k]) ||
+                         br.py[k] == floorf(br.py[k]);
+        }
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const int e1 = e == 2 ? 0 : e + 1;
+            br.slope[e][0] = (br.py[e1] - br.py[e]) / (br.px[e1] - br.px[e]);
+            br.slope[e][1] = (br.px[e1] - br.px[e]) / (br.py[e1] - br.py[e]);
+        }
+        br.meta = fn < 0 ? -1 : (fn | (irregular ? BWD_IRREGULAR : 0) | (both ? BWD_BOTH : 0));
+        brecs[i] = br;
+    }
     FaceBox bx;
     bx.x0 = (short)x0; bx.y0 = (short)y0; bx.x1 = (short)x1; bx.y1 = (short)y1;
     boxes[i] = bx;
@@ -724,9 +757,11 @@ grad_prep_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restric
 // handful of values and is constant over whole missing / excess regions). A sweep then costs O(runs on the
 // line) instead of O(set pixels). Lines with more than HM_RASTER_RUN_CAP runs keep the bit-line path.
 //   runs       [B][4][is][HM_RASTER_RUN_CAP] uint2 {start | end << 16, |grad| bits}
-//   run_counts [B][4][is]  (0xffffffff = overflow);  list 0 mn_row, 1 mp_row, 2 mn_col, 3 mp_col
+//   run_counts [B][4][is]  count (15 = overflow) | first set pixel << 4 | last set pixel << 16
+//   list 0 mn_row, 1 mp_row, 2 mn_col, 3 mp_col
 constexpr int RCAP = HM_RASTER_RUN_CAP;
-constexpr unsigned RUN_OVERFLOW = 0xffffffffu;
+constexpr unsigned RUN_OVERFLOW = 15u;
+static_assert(RCAP < 15, "run count field");
 
 struct BwdCtx {
     const float *grad;  // grad_alpha of this image [R,R]
@@ -753,7 +788,7 @@ build_runs_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restri
     ctx.is = is; ctx.aa = aa; ctx.R = aa ? is / 2 : is; ctx.eps = 0.f;
     ctx.grad = grad_alpha + (long)b * ctx.R * ctx.R;
     uint2 *out = runs + (((long)b * 4 + l4) * is + line) * RCAP;
-    int n = 0, rs = -1, re = -1;
+    int n = 0, rs = -1, re = -1, first = 0;
     float rg = 0.f;
     for (int w = 0; w < W; ++w) {
         unsigned bits = words[w];
@@ -761,6 +796,7 @@ build_runs_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restri
             const int bit = __ffs(bits) - 1;
             bits &= bits - 1;
             const int d1 = w * 32 + bit;
+            if (rs < 0) first = d1;
             const float g = fabsf(col ? fetch_grad(ctx, d1, line) : fetch_grad(ctx, line, d1));
             if (rs >= 0 && d1 == re + 1 && g == rg) {
                 re = d1;
@@ -778,16 +814,25 @@ build_runs_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restri
         if (n < RCAP) out[n] = make_uint2((unsigned)rs | ((unsigned)re << 16), __float_as_uint(rg));
         ++n;
     }
-    run_counts[((long)b * 4 + l4) * is + line] = n > RCAP ? RUN_OVERFLOW : (unsigned)n;
+    run_counts[((long)b * 4 + l4) * is + line] =
+        (n > RCAP ? RUN_OVERFLOW : (unsigned)n) | ((unsigned)first << 4) | ((unsigned)max(re, 0) << 16);
 }
 
 // ------------------------------------------------------------------------------------------ backward
-// psi(z2) - psi(z1) = sum_{k=0}^{n-1} 1 / (z1 + k) for z2 = z1 + n, z1 >= 4 (asymptotic series, error < 1e-7)
+// One MUFU.RCP (1 ulp) instead of the IEEE reciprocal sequence: the sweep sums tolerate it (parity bar 1e-4).
+__device__ __forceinline__ float rcp_fast(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// psi(z2) - psi(z1) = sum_{k=0}^{n-1} 1 / (z1 + k) for z2 = z1 + n, z1 >= 4 (asymptotic series, error < 1e-7).
+// The logarithm is MUFU.LG2 of 1 + n / z1: absolute error ~1e-7, against a sum whose leading terms are O(1 / z).
 __device__ __forceinline__ float harmonic_span(float z1, float n) {
     const float z2 = z1 + n;
-    const float i1 = __frcp_rn(z1), i2 = __frcp_rn(z2);
+    const float i1 = rcp_fast(z1), i2 = rcp_fast(z2);
     const float a1 = i1 * i1, a2 = i2 * i2;
-    float r = log1pf(n * i1);
+    float r = __logf(1.f + n * i1);
     r += 0.5f * (i1 - i2);
     r += (1.f / 12.f) * (a1 - a2);
     r -= (1.f / 120.f) * (a1 * a1 - a2 * a2);
@@ -808,7 +853,7 @@ constexpr int NEAR_N = HM_NEAR_N;
 __device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, int s, int e, bool has0, bool has1,
                                           float inv_is2, float eps, float &a0, float &a1) {
     const float K0 = c0 * inv_is2, K1 = c1 * inv_is2;
-    const float rK0 = __frcp_rn(K0), rK1 = __frcp_rn(K1);
+    const float rK0 = rcp_fast(K0), rK1 = rcp_fast(K1);
     const float del0 = eps * fabsf(rK0), del1 = eps * fabsf(rK1);
     const bool left = (float)e <= x;
     const float sgn = left ? -1.f : 1.f;
@@ -821,7 +866,7 @@ __device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, 
         float dist0 = K0 * dd, dist1 = K1 * dd;
         dist0 = (0.f < dist0) ? dist0 + eps : dist0 - eps;
         dist1 = (0.f < dist1) ? dist1 + eps : dist1 - eps;
-        const float t0 = __frcp_rn(dist0), t1 = __frcp_rn(dist1);
+        const float t0 = rcp_fast(dist0), t1 = rcp_fast(dist1);
         if (k < n) { h0 += t0; h1 += t1; }
     }
     const float nf = (float)max(n - NEAR_N, 0), zf = z + (float)NEAR_N;
@@ -831,74 +876,6 @@ __device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, 
     a1 = has1 ? -G * h1 : 0.f;
 }
 
-constexpr int BWD_LISTCAP = 1024;
-#ifndef HM_BWD_SUB
-#define HM_BWD_SUB 128
-#endif
-#ifndef HM_SEG
-#define HM_SEG 8
-#endif
-constexpr int BWD_SUB = HM_BWD_SUB;  // faces whose tasks are sorted and processed together
-constexpr int SEG = HM_SEG;          // scan-lines one thread walks
-constexpr int SQCAP = 64;  // per-warp queue of (crossing, run) items
-
-// A queued (crossing, run) item: crossing position x on its scan-line, the two distance coefficients of the
-// reference (ka / (p1.d0 - d0) and ka / (d0 - p0.d0)), the run's weight and its pixels inside the sweep.
-struct SweepQueue {
-    float x[SQCAP], c0[SQCAP], c1[SQCAP], G[SQCAP];
-    unsigned range[SQCAP];  // s | e << 16
-    unsigned meta[SQCAP];   // list (2 bits) | line << 2 (6 bits) | has0 << 8 | has1 << 9 | bit-line walk << 10
-    float r0[32], r1[32];   // results of the 32 items evaluated by one drain
-};
-
-// One (face, edge, axis) task of backward_pixel_map: the scan-lines d0 = lo .. lo + len - 1 of one edge inside
-// the tile, swept along d1 (axis 0: d0 = x, d1 = y; axis 1 swapped).
-struct TaskParams {
-    float p0d0, p0d1, p1d0, p2d0, p2d1, slope, slope02, slope21, ka;
-    int fn, dir, lo, len, axis, vid0, vid1;
-};
-__device__ __forceinline__ TaskParams task_params(const float4 *rp, int task, int is, int tx0, int ty0) {
-    TaskParams p;
-    const int e = (task % 6) >> 1;
-    p.axis = task & 1;
-    const float4 q0 = rp[0], q1 = rp[1], q2 = rp[2];
-    const int4 q3 = *reinterpret_cast<const int4 *>(rp + 3);
-    p.fn = __float_as_int(q2.y);
-    const int v0 = __float_as_int(q2.z), v1 = __float_as_int(q2.w), v2 = q3.x;
-    // pixel-space corners along (d0, d1) = (x, y) for axis 0, (y, x) for axis 1
-    const float ax = to_pix(q0.x, is), ay = to_pix(q0.y, is), bx = to_pix(q0.w, is), by = to_pix(q1.x, is),
-                cx = to_pix(q1.z, is), cy = to_pix(q1.w, is);
-    const float a0 = p.axis ? ay : ax, a1 = p.axis ? ax : ay, b0 = p.axis ? by : bx, b1 = p.axis ? bx : by,
-                c0 = p.axis ? cy : cx, c1 = p.axis ? cx : cy;
-    // vertex order of this edge: p0 = corner e, p1 = corner e+1, p2 = corner e+2
-    p.p0d0 = e == 0 ? a0 : e == 1 ? b0 : c0; p.p0d1 = e == 0 ? a1 : e == 1 ? b1 : c1;
-    p.p1d0 = e == 0 ? b0 : e == 1 ? c0 : a0;
-    const float p1d1 = e == 0 ? b1 : e == 1 ? c1 : a1;
-    p.p2d0 = e == 0 ? c0 : e == 1 ? a0 : b0; p.p2d1 = e == 0 ? c1 : e == 1 ? a1 : b1;
-    p.vid0 = e == 0 ? v0 : e == 1 ? v1 : v2; p.vid1 = e == 0 ? v1 : e == 1 ? v2 : v0;
-    if (p.axis == 0) p.dir = (p.p0d0 < p.p1d0) ? -1 : 1;
-    else p.dir = (p.p0d0 < p.p1d0) ? 1 : -1;
-    const int d0_from = __float2int_rz(fmaxf(ceilf(fminf(p.p0d0, p.p1d0)), 0.f));
-    const int d0_to = __float2int_rz(fminf(fmaxf(p.p0d0, p.p1d0), (float)(is - 1)));
-    const int t0 = p.axis == 0 ? tx0 : ty0, t1 = p.axis == 0 ? ty0 : tx0;
-    p.lo = max(d0_from, t0);
-    int hi = min(d0_to, t0 + TILE - 1);
-    p.ka = p.p1d0 - p.p0d0;
-    p.slope = (p1d1 - p.p0d1) / p.ka;
-    p.slope02 = (p.p2d1 - p.p0d1) / (p.p2d0 - p.p0d0);
-    p.slope21 = (p1d1 - p.p2d1) / (p.p1d0 - p.p2d0);
-    // only crossings whose in-pixel lies in this tile are handled here: restrict the scan-lines to where the
-    // edge passes the tile's d1 range (slack of a pixel; steep enough edges only, so the bound is accurate)
-    const float as = fabsf(p.slope);
-    if (as > 1e-2f && as < 1e6f) {
-        const float u0 = p.p0d0 + ((float)(t1 - 2) - p.p0d1) / p.slope, u1 = p.p0d0 + ((float)(t1 + TILE + 1) - p.p0d1) / p.slope;
-        p.lo = max(p.lo, __float2int_rz(fmaxf(floorf(fminf(u0, u1)) - 1.f, -1.f)));
-        hi = min(hi, __float2int_rz(fminf(ceilf(fmaxf(u0, u1)) + 1.f, 70000.f)));
-    }
-    p.len = p.fn >= 0 ? max(hi - p.lo + 1, 0) : 0;
-    return p;
-}
-
 // Bit-line walk for lines whose run list overflowed: visits the set bits of `line` in [a, c].
 __device__ __forceinline__ void sweep_bits(const uint32_t *line, int a, int c, int axis, int d0, float d1_cross,
                                            float c0, float c1, bool has0, bool has1, const BwdCtx &ctx, float &acc0,
@@ -906,7 +883,7 @@ __device__ __forceinline__ void sweep_bits(const uint32_t *line, int a, int c, i
     if (a > c) return;
     const int wa = a >> 5, wc = c >> 5;
     for (int w = wa; w <= wc; ++w) {
-        unsigned bits = line[w];
+        unsigned bits = __ldg(line + w);
         if (w == wa) bits &= 0xffffffffu << (a & 31);
         if (w == wc) bits &= 0xffffffffu >> (31 - (c & 31));
         while (bits) {
@@ -930,335 +907,521 @@ __device__ __forceinline__ void sweep_bits(const uint32_t *line, int a, int c, i
     }
 }
 
-// One CTA per (image, 64x64 tile). The (face, edge, axis) tasks of the faces touching the tile are sorted by
-// length (counting sort in shared memory); warps pull groups of 32 tasks of similar length off the sorted list
-// and every thread walks the scan-line crossings of ONE task with the task's parameters in registers. A crossing whose out-sweep / in-sweep has runs to visit queues the sweep in
-// a per-warp shared queue (ballot compaction); 32 queued sweeps are evaluated at a time on a full warp, and every
-// thread collects the results of the sweeps it queued itself (it remembers their slots in a bit mask), so the
-// per-task sums stay in registers: no shared-memory float atomics, one global atomicAdd per face-vertex component.
-__global__ void __launch_bounds__(NTHREADS, 3)
-raster_bwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
-                  float eps, const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
-                  const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ cov_col,
-                  const uint32_t *__restrict__ m_row, const uint32_t *__restrict__ m_col,
-                  const uint2 *__restrict__ runs, const uint32_t *__restrict__ run_counts,
-                  float *__restrict__ grad_ndc) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ int list[BWD_LISTCAP];
-    __shared__ int cnt, next;
-    __shared__ __align__(16) uint2 srun[4][TILE][RCAP];  // run lists: mn_row, mp_row, mn_col, mp_col
-    __shared__ __align__(16) unsigned scount[4][TILE];
-    __shared__ int hist[TILE + 2], hpos[TILE + 2], has_both;
-    __shared__ unsigned char slen[6 * BWD_SUB];                 // scan-lines of every task of the sub-batch
-    __shared__ unsigned short sorted[6 * BWD_SUB * (TILE / SEG)];  // segments (task | index << 12), longest first
-    __shared__ __align__(16) float4 srec[BWD_SUB][4];            // first 64 bytes of the sub-batch's face records
-    __shared__ __align__(8) uint64_t bar;
-    const int W = is / 32;
-    // dynamic shared memory: face_index tile | per-warp queues
-    int *fi = reinterpret_cast<int *>(smem_raw);
-    SweepQueue *sq = reinterpret_cast<SweepQueue *>(smem_raw + TILE * TILE * sizeof(int));
+// ------------------------------------------------------------------------------------------ backward kernel
+// backward_pixel_map visits, per (face, edge, axis, scan-line) crossing, an out-sweep (only when the face owns the
+// in-pixel) and an in-sweep (always). Enumerating every crossing costs far more than the sweeps that contribute, so
+// the kernel finds the contributing crossings from the data instead (scripts/proto/bwd_proto.c is the scalar model
+// of this enumeration, checked against the oracle on the adversarial inputs):
+//
+//  role A, CTA per (image, 64x64 tile) - OUT-SWEEPS FROM THE PIXELS. The in-pixel of an out-sweep is owned by the
+//     face and sits at most one pixel before the end of a span of the face_index map along the sweep direction (the
+//     pixel two steps further lies more than a pixel outside the edge, and the coverage predicate and the crossing
+//     arithmetic agree to ~1e-2 px when |slope| <= SMAX). So every span end (owner changes between neighbouring
+//     pixels: one ballot per row and direction) that has missing-coverage pixels beyond it looks up the three edges
+//     of its owner; the edge whose crossing has this in-pixel sweeps the run list of the line. ~1 candidate per real
+//     out-sweep instead of ~8 enumerated crossings.
+//  role B, thread per face - IN-SWEEPS AND STEEP TASKS. An in-sweep reads alpha at the out-pixel and mismatch pixels
+//     inside the triangle's span: a face whose pixel bounding box is fully covered cannot contribute (alpha_out = 1
+//     selects the missing-coverage list, which is empty on covered pixels), unless a corner sits exactly on an integer
+//     pixel coordinate (the reference then extrapolates the far end of the sweep from an edge that does not span the
+//     line: "irregular" faces are never skipped). Only faces at the silhouette are enumerated. Tasks with
+//     |slope| > SMAX (at most a few lines long) take their out-sweeps here too, tested with face_index as the
+//     reference does.
+// Per-crossing sums stay in registers; role A merges the crossings of one (face, edge, axis) task inside a warp
+// (match.any) before the global atomicAdd into grad_ndc (the vertices_to_faces scatter-add is fused).
+constexpr float SMAX = 128.f;
+constexpr int FIS = TILE + 4;           // row stride of the face_index tile with its one-pixel halo (ints)
+constexpr int CQCAP = 32 + 8 * TILE;    // per-warp candidate queue: a leftover batch + one tile row of candidates
+constexpr int BFACES = NTHREADS;        // faces per role-B CTA
+constexpr int TQCAP = 12 * 32;          // per-warp task list of role B (6 tasks x 2 copies x 32 faces)
+static_assert(TQCAP <= CQCAP, "role B reuses the candidate queues");
+
+constexpr int IQCAP = 64;               // per-warp queue of (crossing, run) items
+struct ItemQueue {
+    float x[IQCAP], c0[IQCAP], c1[IQCAP], G[IQCAP];   // crossing position, distance coefficients, run weight
+    unsigned range[IQCAP];                            // pixels of the run inside the sweep: s | e << 16
+    unsigned key[IQCAP];                              // (owner * 3 + edge) * 2 + axis
+    unsigned meta[IQCAP];                             // d0 | axis << 12 | has0 << 13 | has1 << 14 | walk << 15
+};
+
+struct TaskGeom {
+    float p0d0, p0d1, p1d0, p2d0, p2d1, slope, s02, s21, ka;
+    int dir, d0_from, d0_to, vid0, vid1;
+};
+
+__device__ __forceinline__ float sel3(const float (&a)[3], int i) { return i == 0 ? a[0] : i == 1 ? a[1] : a[2]; }
+// The quotient of an edge walked backwards: (-a) / (-b) rounds like a / b, except that b = +0 both ways (x - x = +0),
+// so an infinite slope changes sign.
+__device__ __forceinline__ float backwards(float slope) { return fabsf(slope) == INFINITY ? -slope : slope; }
+
+// The backward record of a face, optionally as its reversed (fill_back) copy.
+struct BwdFace {
+    float px[3], py[3], sl[3][2];
+    int v[3], fn;
+    bool both, irregular;
+};
+__device__ __forceinline__ BwdFace load_bwd_face(const BwdRec *rp) {
+    BwdFace f;
+    const float4 q0 = __ldg(reinterpret_cast<const float4 *>(rp)), q1 = __ldg(reinterpret_cast<const float4 *>(rp) + 1),
+                 q2 = __ldg(reinterpret_cast<const float4 *>(rp) + 2);
+    const int4 q3 = __ldg(reinterpret_cast<const int4 *>(rp) + 3);
+    f.px[0] = q0.x; f.px[1] = q0.y; f.px[2] = q0.z; f.py[0] = q0.w; f.py[1] = q1.x; f.py[2] = q1.y;
+    f.sl[0][0] = q1.z; f.sl[0][1] = q1.w; f.sl[1][0] = q2.x; f.sl[1][1] = q2.y; f.sl[2][0] = q2.z; f.sl[2][1] = q2.w;
+    f.v[0] = q3.x; f.v[1] = q3.y; f.v[2] = q3.z;
+    f.fn = q3.w < 0 ? -1 : (q3.w & BWD_FN_MASK);
+    f.both = q3.w >= 0 && (q3.w & BWD_BOTH);
+    f.irregular = q3.w >= 0 && (q3.w & BWD_IRREGULAR);
+    return f;
+}
+__device__ __forceinline__ void reverse_bwd_face(BwdFace &f, int F) {  // corners 0 and 2 trade places, fn -> F + f
+    float t = f.px[0]; f.px[0] = f.px[2]; f.px[2] = t;
+    t = f.py[0]; f.py[0] = f.py[2]; f.py[2] = t;
+    t = f.sl[0][0]; f.sl[0][0] = f.sl[1][0]; f.sl[1][0] = t;   // reversed edge 0 = old edge 1 walked backwards
+    t = f.sl[0][1]; f.sl[0][1] = f.sl[1][1]; f.sl[1][1] = t;
+#pragma unroll
+    for (int e = 0; e < 3; ++e) { f.sl[e][0] = backwards(f.sl[e][0]); f.sl[e][1] = backwards(f.sl[e][1]); }
+    const int v = f.v[0]; f.v[0] = f.v[2]; f.v[2] = v;
+    f.fn += F;
+}
+__device__ __forceinline__ TaskGeom task_geom(const BwdFace &f, int e, int axis, int is) {
+    TaskGeom g;
+    const int e1 = e == 2 ? 0 : e + 1, e2 = e == 0 ? 2 : e - 1;
+    // (d0, d1) = (x, y) for axis 0, (y, x) for axis 1   (selects, not indexing: the record stays in registers)
+    const float x0 = sel3(f.px, e), y0 = sel3(f.py, e), x1 = sel3(f.px, e1), y1 = sel3(f.py, e1),
+                x2 = sel3(f.px, e2), y2 = sel3(f.py, e2);
+    g.p0d0 = axis ? y0 : x0; g.p0d1 = axis ? x0 : y0;
+    g.p1d0 = axis ? y1 : x1;
+    g.p2d0 = axis ? y2 : x2; g.p2d1 = axis ? x2 : y2;
+    const float s0 = axis ? f.sl[0][1] : f.sl[0][0], s1 = axis ? f.sl[1][1] : f.sl[1][0], s2 = axis ? f.sl[2][1] : f.sl[2][0];
+    g.slope = e == 0 ? s0 : e == 1 ? s1 : s2;
+    // edge e2 runs corner e2 -> e: the reference's (p2 - p0) quotient walked backwards; edge e1 runs e1 -> e2: (p1 - p2)
+    g.s02 = backwards(e == 0 ? s2 : e == 1 ? s0 : s1);
+    g.s21 = backwards(e == 0 ? s1 : e == 1 ? s2 : s0);
+    g.vid0 = e == 0 ? f.v[0] : e == 1 ? f.v[1] : f.v[2];
+    g.vid1 = e == 0 ? f.v[1] : e == 1 ? f.v[2] : f.v[0];
+    if (axis == 0) g.dir = (g.p0d0 < g.p1d0) ? -1 : 1;
+    else g.dir = (g.p0d0 < g.p1d0) ? 1 : -1;
+    g.d0_from = __float2int_rz(fmaxf(ceilf(fminf(g.p0d0, g.p1d0)), 0.f));
+    g.d0_to = __float2int_rz(fminf(fmaxf(g.p0d0, g.p1d0), (float)(is - 1)));
+    g.ka = g.p1d0 - g.p0d0;
+    return g;
+}
+
+struct SweepSrc {
+    const uint2 *runs;            // [4][is][RCAP] of this image
+    const uint32_t *run_info;     // [4][is] of this image
+    const uint32_t *m_row, *m_col;  // bit lines of this image [2][is][W]
+    int is, W;
+    float inv_is2, eps;
+    BwdCtx ctx;
+};
+
+// Sum over the pixels of list `ls` (0 mn_row, 1 mp_row, 2 mn_col, 3 mp_col) on line d0 inside [ra, rc], seen from the
+// crossing at x. `walk`: visit the bit line pixel by pixel (run list overflowed, or the sweep straddles its crossing).
+__device__ __forceinline__ void sweep_line(const SweepSrc &S, int ls, int d0, int ra, int rc, float x, float c0, float c1,
+                                           bool has0, bool has1, bool walk, float &acc0, float &acc1) {
+    const uint32_t info = __ldg(S.run_info + ls * S.is + d0);
+    const unsigned cnt = info & 15u;
+    if (cnt == 0u) return;
+    if (rc < (int)((info >> 4) & 0xfffu) || ra > (int)(info >> 16)) return;  // no listed pixel inside the sweep
+    if (cnt == RUN_OVERFLOW || walk) {
+        const int col = ls >> 1;
+        const uint32_t *line = (col ? S.m_col : S.m_row) + ((long)(ls & 1) * S.is + d0) * S.W;
+        sweep_bits(line, ra, rc, col ? 0 : 1, d0, x, c0, c1, has0, has1, S.ctx, acc0, acc1);
+        return;
+    }
+    const uint2 *rl = S.runs + ((long)ls * S.is + d0) * RCAP;
+    for (unsigned r = 0; r < cnt; ++r) {
+        const uint2 run = __ldg(rl + r);
+        const int s = max(ra, (int)(run.x & 0xffffu)), e = min(rc, (int)(run.x >> 16));
+        if (s > e) continue;
+        float a0, a1;
+        eval_item(x, c0, c1, __uint_as_float(run.y), s, e, has0, has1, S.inv_is2, S.eps, a0, a1);
+        acc0 += a0;
+        acc1 += a1;
+    }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 4)
+raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
+                  float eps, int n_face_ctas, const int32_t *__restrict__ face_index,
+                  const float *__restrict__ grad_alpha, const uint32_t *__restrict__ cov_row,
+                  const uint32_t *__restrict__ cov_col, const uint32_t *__restrict__ m_row,
+                  const uint32_t *__restrict__ m_col, const uint2 *__restrict__ runs,
+                  const uint32_t *__restrict__ run_info, float *__restrict__ grad_ndc) {
+    __shared__ int fi[(TILE + 2) * FIS];                   // role A: face_index tile, one-pixel halo
+    __shared__ unsigned short cq[NWARPS][CQCAP];           // role A: candidates; role B: task lists (TQCAP <= CQCAP)
+    __shared__ uint32_t ext_row[TILE], ext_col[TILE];      // role A: extent of the missing-coverage list per line
+    __shared__ ItemQueue iqs[NWARPS];                      // role A: (crossing, run) items
     const int b = blockIdx.y;
-    const int tiles_x = is / TILE;
-    const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
+    const int W = is / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
     const unsigned lt_mask = (1u << lane) - 1u;
-    recs += (long)b * F;
+    brecs += (long)b * F;
     boxes += (long)b * F;
     grad_ndc += (long)b * V * 3;
-    BwdCtx ctx;
-    ctx.is = is; ctx.aa = aa; ctx.R = aa ? is / 2 : is; ctx.eps = eps;
-    ctx.grad = grad_alpha + (long)b * ctx.R * ctx.R;
-    const float inv_is2 = 2.f / (float)is;
-    const long plane = (long)is * W;
-    SweepQueue &q = sq[warp];
+    face_index += (long)b * is * is;
+    cov_row += (long)b * is * W;
+    cov_col += (long)b * is * W;
+    SweepSrc S;
+    S.runs = runs + (long)b * 4 * is * RCAP;
+    S.run_info = run_info + (long)b * 4 * is;
+    S.m_row = m_row + (long)b * 2 * is * W;
+    S.m_col = m_col + (long)b * 2 * is * W;
+    S.is = is; S.W = W; S.inv_is2 = 2.f / (float)is; S.eps = eps;
+    S.ctx.is = is; S.ctx.aa = aa; S.ctx.R = aa ? is / 2 : is; S.ctx.eps = eps;
+    S.ctx.grad = grad_alpha + (long)b * S.ctx.R * S.ctx.R;
 
-    // Evaluates the first `nq` (<= 32) queued items, one per lane, and leaves the results in q.r0 / q.r1.
-    auto evaluate = [&](int nq) {
-        float a0 = 0.f, a1 = 0.f;
-        if (lane < nq) {
-            const float x = q.x[lane], c0 = q.c0[lane], c1 = q.c1[lane];
-            const unsigned rng = q.range[lane], meta = q.meta[lane];
-            const int ra = (int)(rng & 0xffffu), rc = (int)(rng >> 16);
-            const bool has0 = (meta >> 8) & 1u, has1 = (meta >> 9) & 1u;
-            if ((meta >> 10) & 1u) {
-                // more runs than the list holds: walk the bit line (global memory)
-                const int ls = meta & 3u, l0 = (meta >> 2) & 63u;
-                const int col = ls >> 1;
-                const uint32_t *line = (col ? m_col : m_row) + ((long)b * 2 * is + (col ? tx0 : ty0) + l0) * W + (ls & 1) * plane;
-                sweep_bits(line, ra, rc, col ? 0 : 1, (col ? tx0 : ty0) + l0, x, c0, c1, has0, has1, ctx, a0, a1);
-            } else {
-                eval_item(x, c0, c1, q.G[lane], ra, rc, has0, has1, inv_is2, eps, a0, a1);
+#ifdef HM_BWD_ROLE_MASK   // development: 1 = role A only, 2 = role B only
+    if (!(((int)blockIdx.x < n_face_ctas ? 2 : 1) & HM_BWD_ROLE_MASK)) return;
+#endif
+    if ((int)blockIdx.x < n_face_ctas) {
+        // =================================================================== role B: in-sweeps, steep tasks
+        const int f = blockIdx.x * BFACES + threadIdx.x;
+        unsigned todo = 0;  // bits 0-5: tasks (edge * 2 + axis) of the face; bits 6-11: of its reversed copy;
+                            // bit 12: the face is at the silhouette (in-sweeps on), else only steep out-sweeps
+        if (f < F) {
+            const BwdFace bf = load_bwd_face(brecs + f);
+            if (bf.fn >= 0) {
+                unsigned steep = 0;
+#pragma unroll
+                for (int t = 0; t < 6; ++t)
+                    if (!(fabsf(bf.sl[t >> 1][t & 1]) <= SMAX)) steep |= 1u << t;
+                bool boundary = bf.irregular;
+                if (!boundary) {
+                    const FaceBox bx = boxes[f];  // clamped pixel bbox with one pixel of slack
+                    const int w0 = bx.x0 >> 5, w1 = bx.x1 >> 5;
+                    for (int y = bx.y0; y <= bx.y1 && !boundary; ++y)
+                        for (int w = w0; w <= w1; ++w) {
+                            const int lo = max(bx.x0 - 32 * w, 0), hi = min(bx.x1 - 32 * w, 31);
+                            const unsigned m = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+                            if (~__ldg(cov_row + (long)y * W + w) & m) { boundary = true; break; }
+                        }
+                }
+                todo = boundary ? (0x3fu | (1u << 12)) : steep;
+                if (bf.both) {   // both windings front-facing: the reversed copy F + f is differentiated too
+                    const unsigned steep_rev = ((steep >> 2) & 3u) | ((steep & 3u) << 2) | (steep & 0x30u);
+                    todo |= (boundary ? 0x3fu : steep_rev) << 6;
+                }
             }
         }
-        q.r0[lane] = a0;
-        q.r1[lane] = a1;
+        // ---- the warp's tasks, compacted: lane | task << 5 | copy << 8 | boundary << 9
+        unsigned short *tq = cq[warp];
+        int nt = 0;
+        {
+            const unsigned tasks = todo & 0xfffu;
+            int mine = __popc(tasks), incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += v;
+            }
+            nt = __shfl_sync(FULL, incl, 31);
+            int pos = incl - mine;
+            unsigned m = tasks;
+            while (m) {
+                const int t = __ffs(m) - 1;
+                m &= m - 1;
+                tq[pos++] = (unsigned short)(lane | ((t % 6) << 5) | ((t / 6) << 8) | (((todo >> 12) & 1u) << 9));
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < nt; i += 32) {
+            const unsigned ent = tq[i];
+            const int fl = ent & 31, task = (ent >> 5) & 7, copy = (ent >> 8) & 1;
+            const bool boundary = (ent >> 9) & 1u;
+            BwdFace bf = load_bwd_face(brecs + blockIdx.x * BFACES + (warp << 5) + fl);
+            if (copy) reverse_bwd_face(bf, F);
+            const int e = task >> 1, axis = task & 1;
+            const TaskGeom g = task_geom(bf, e, axis, is);
+            const bool steep = !(fabsf(g.slope) <= SMAX);
+            const int lN = axis == 0 ? 2 : 0, lP = lN + 1;
+            const uint32_t *cov = axis == 0 ? cov_col : cov_row;   // coverage words of line d0 along d1
+            float acc0 = 0.f, acc1 = 0.f;
+            for (int d0 = g.d0_from; d0 <= g.d0_to; ++d0) {
+                const float fd0 = (float)d0;
+                const float x = g.slope * (fd0 - g.p0d0) + g.p0d1;
+                const int d1_in = __float2int_rz(g.dir > 0 ? floorf(x) : ceilf(x));
+                const int d1_out = d1_in + g.dir;
+                if (d1_in < 0 || d1_in >= is || d1_out < 0 || d1_out >= is) continue;
+                const bool has0 = g.p1d0 != fd0, has1 = g.p0d0 != fd0;
+                const float c0 = __fdividef(g.ka, g.p1d0 - fd0), c1 = __fdividef(g.ka, fd0 - g.p0d0);
+                if (steep) {   // out-sweep of a steep task: the reference's own ownership test
+                    const int own = axis == 0 ? __ldg(face_index + (long)d1_in * is + d0)
+                                              : __ldg(face_index + (long)d0 * is + d1_in);
+                    if (own == bf.fn) {
+                        const int lim = g.dir > 0 ? is - 1 : 0;
+                        sweep_line(S, lN, d0, min(d1_out, lim), max(d1_out, lim), x, c0, c1, has0, has1, false, acc0, acc1);
+                    }
+                }
+                if (!boundary) continue;
+                // in-sweep: from the in-pixel to the opposite edge of the triangle
+                const bool alpha_out = (__ldg(cov + (long)d0 * W + (d1_out >> 5)) >> (d1_out & 31)) & 1u;
+                const int ls = alpha_out ? lN : lP;
+                if ((__ldg(S.run_info + ls * is + d0) & 15u) == 0u) continue;
+                float c2;
+                if ((fd0 - g.p0d0) * (fd0 - g.p2d0) < 0.f) c2 = g.s02 * (fd0 - g.p0d0) + g.p0d1;
+                else c2 = g.s21 * (fd0 - g.p2d0) + g.p2d1;
+                const int lim = __float2int_rz(g.dir > 0 ? ceilf(c2) : floorf(c2));
+                const int ra = max(min(d1_in, lim), 0), rc = min(max(d1_in, lim), is - 1);
+                if (ra > rc) continue;
+                // an in-sweep can straddle its crossing: by a pixel when the triangle is thinner than a pixel there
+                // (eval_item copes with NEAR_N - 1 pixels on the near side), by many when its far end is
+                // extrapolated (irregular faces): the closed form assumes one side, such a sweep walks the bit line
+                const bool walk = (float)ra < x - (float)(NEAR_N - 1) && (float)rc > x;
+                sweep_line(S, ls, d0, ra, rc, x, c0, c1, has0, has1, walk, acc0, acc1);
+            }
+            // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
+            if (acc0 != 0.f) atomicAdd(grad_ndc + (long)g.vid0 * 3 + (1 - axis), acc0);
+            if (acc1 != 0.f) atomicAdd(grad_ndc + (long)g.vid1 * 3 + (1 - axis), acc1);
+        }
+        return;
+    }
+
+    // ======================================================================= role A: out-sweeps from the pixels
+    const int tile = blockIdx.x - n_face_ctas;
+    const int tiles_x = is / TILE;
+    const int tx0 = (tile % tiles_x) * TILE, ty0 = (tile / tiles_x) * TILE;
+    // ---- nothing to do when the tile is empty or no line through it has missing coverage
+    {
+        bool any_cov = false, any_miss = false;
+        if (threadIdx.x < 2 * TILE) {
+            const int r = threadIdx.x >> 1, w = threadIdx.x & 1;
+            any_cov = __ldg(cov_row + (long)(ty0 + r) * W + (tx0 >> 5) + w) != 0u;
+        }
+        if (threadIdx.x < TILE) {
+            const uint32_t er = __ldg(S.run_info + 0 * is + ty0 + threadIdx.x), ec = __ldg(S.run_info + 2 * is + tx0 + threadIdx.x);
+            ext_row[threadIdx.x] = (er & 15u) ? er : 0x0000fff0u;   // empty list: lo = 4095, hi = 0
+            ext_col[threadIdx.x] = (ec & 15u) ? ec : 0x0000fff0u;
+            any_miss = ((er | ec) & 15u) != 0u;
+        }
+        const int cov_any = __syncthreads_or(any_cov);
+        const int miss_any = __syncthreads_or(any_miss);
+        if (!cov_any || !miss_any) return;
+    }
+    // ---- face_index tile with a one-pixel halo (-2 outside the image: never equal to an owner)
+    for (int i = threadIdx.x; i < TILE * TILE / 4; i += NTHREADS) {
+        const int r = i / (TILE / 4), c4 = i % (TILE / 4);
+        const int4 v = __ldg(reinterpret_cast<const int4 *>(face_index + (long)(ty0 + r) * is + tx0) + c4);
+        int *dst = fi + (r + 1) * FIS + 1 + 4 * c4;
+        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    }
+    {
+        const int t = threadIdx.x;   // 4 x 66 halo pixels: rows above / below, columns left / right
+        const int side = t >> 6, k = t & 63;
+        int yy, xx;
+        if (side == 0) { yy = -1; xx = k; } else if (side == 1) { yy = TILE; xx = k; }
+        else if (side == 2) { yy = k; xx = -1; } else { yy = k; xx = TILE; }
+        const int gy = ty0 + yy, gx = tx0 + xx;
+        fi[(yy + 1) * FIS + xx + 1] = (gy >= 0 && gy < is && gx >= 0 && gx < is) ? __ldg(face_index + (long)gy * is + gx) : -2;
+        if (t < 4) fi[(t & 1 ? TILE + 1 : 0) * FIS + (t & 2 ? TILE + 1 : 0)] = -2;   // corners (never read as neighbours)
+    }
+    __syncthreads();
+
+    unsigned short *q = cq[warp];
+    ItemQueue &iq = iqs[warp];
+    int qn = 0, ni = 0;   // queued candidates, queued items
+
+    // Evaluates the first `n` (<= 32) queued items, one per lane; items of one (face, edge, axis) task met in the
+    // batch are merged (match.any) and leave as one atomicAdd per vertex slot. Then the rest of the queue moves up.
+    auto drain = [&](int n) {
+        unsigned key = 0x80000000u | lane;
+        float a0 = 0.f, a1 = 0.f;
+        if (lane < n) {
+            const unsigned meta = iq.meta[lane], rng = iq.range[lane];
+            const int d0 = meta & 0xfffu, axis = (meta >> 12) & 1u;
+            const bool has0 = (meta >> 13) & 1u, has1 = (meta >> 14) & 1u;
+            const int ra = rng & 0xffffu, rc = rng >> 16;
+            key = iq.key[lane];
+            if ((meta >> 15) & 1u) {   // run list overflowed: walk the bit line
+                const uint32_t *line = (axis == 0 ? S.m_col : S.m_row) + (long)d0 * W;
+                sweep_bits(line, ra, rc, axis, d0, iq.x[lane], iq.c0[lane], iq.c1[lane], has0, has1, S.ctx, a0, a1);
+            } else {
+                eval_item(iq.x[lane], iq.c0[lane], iq.c1[lane], iq.G[lane], ra, rc, has0, has1, S.inv_is2, eps, a0, a1);
+            }
+        }
+        const unsigned peers = __match_any_sync(FULL, key);
+        const int leader = __ffs(peers) - 1;
+        unsigned others = lane == leader ? peers & ~(1u << lane) : 0u;
+        const unsigned rounds = __reduce_max_sync(FULL, (unsigned)__popc(others));
+        for (unsigned r = 0; r < rounds; ++r) {
+            const int src = others ? __ffs(others) - 1 : lane;
+            const float t0 = __shfl_sync(FULL, a0, src), t1 = __shfl_sync(FULL, a1, src);
+            if (others) { a0 += t0; a1 += t1; others &= others - 1; }
+        }
+        if (lane < n && lane == leader && (a0 != 0.f || a1 != 0.f)) {
+            // key = (owner * 3 + edge) * 2 + axis: the two vertices of the edge come from the owner's record
+            const int own = (int)(key / 6u), e = (int)((key >> 1) % 3u), axis = (int)(key & 1u);
+            const int4 q3 = __ldg(reinterpret_cast<const int4 *>(brecs + (own >= F ? own - F : own)) + 3);
+            const bool rev = (q3.w & BWD_FN_MASK) != own;   // the reversed copy of a both-windings face
+            const int v0 = rev ? q3.z : q3.x, v1 = q3.y, v2 = rev ? q3.x : q3.z;
+            const int vid0 = e == 0 ? v0 : e == 1 ? v1 : v2, vid1 = e == 0 ? v1 : e == 1 ? v2 : v0;
+            if (a0 != 0.f) atomicAdd(grad_ndc + (long)vid0 * 3 + (1 - axis), a0);
+            if (a1 != 0.f) atomicAdd(grad_ndc + (long)vid1 * 3 + (1 - axis), a1);
+        }
+        const int rem = ni - n;   // > 0 only when n == 32
+        float mx = 0.f, mc0 = 0.f, mc1 = 0.f, mg = 0.f;
+        unsigned mr = 0, mk = 0, mm = 0;
+        if (lane < rem) {
+            mx = iq.x[32 + lane]; mc0 = iq.c0[32 + lane]; mc1 = iq.c1[32 + lane]; mg = iq.G[32 + lane];
+            mr = iq.range[32 + lane]; mk = iq.key[32 + lane]; mm = iq.meta[32 + lane];
+        }
+        __syncwarp();
+        if (lane < rem) {
+            iq.x[lane] = mx; iq.c0[lane] = mc0; iq.c1[lane] = mc1; iq.G[lane] = mg;
+            iq.range[lane] = mr; iq.key[lane] = mk; iq.meta[lane] = mm;
+        }
+        ni = max(rem, 0);
         __syncwarp();
     };
 
-    int base = 0;
-    bool staged = false;
-    while (base < F) {
-        const int n = next_batch(boxes, base, F, tx0, ty0, list, &cnt, &next, BWD_LISTCAP);
-        if (n == 0) continue;
-        if (!staged) {
-            // ---- stage the tile's face_index rows and run lists (TMA bulk copies)
-            //      (tiles no face touches never get here: their face_index is never read)
-            if (threadIdx.x == 0) {
-                mbar_init(&bar, 1);
-                mbar_fence_init();
-            }
-            __syncthreads();
-            if (warp == 0) {
-                if (lane == 0)
-                    mbar_expect_tx(&bar, (uint32_t)(4 * TILE * RCAP * 8 + 4 * TILE * 4));
-                __syncwarp();
-                if (lane >= 8 && lane < 12) {
-                    const int l4 = lane - 8, t0 = (l4 >> 1) ? tx0 : ty0;
-                    tma_bulk_g2s(&srun[l4][0][0], runs + (((long)b * 4 + l4) * is + t0) * RCAP, TILE * RCAP * 8, &bar);
-                    tma_bulk_g2s(&scount[l4][0], run_counts + ((long)b * 4 + l4) * is + t0, TILE * 4, &bar);
-                }
-            }
-            // the face_index tile is 64 rows of 256 B: coalesced 16-byte loads (one bulk copy per row costs more
-            // in TMA issue overhead than the bytes are worth)
-            for (int i = threadIdx.x; i < TILE * TILE / 4; i += NTHREADS) {
-                const int r = i / (TILE / 4), c4 = i % (TILE / 4);
-                const int4 v = __ldg(reinterpret_cast<const int4 *>(face_index + ((long)b * is + ty0 + r) * is + tx0) + c4);
-                reinterpret_cast<int4 *>(fi)[i] = v;
-            }
-            if (warp == 0) mbar_wait(&bar, 0);
-            __syncthreads();
-            staged = true;
-        }
-        // pass 0: the faces as recorded; pass 1: the reversed copies F + f of the degenerate faces whose two windings
-        // are both front-facing (the reference differentiates both copies)
-        int nb = n;
-        if (threadIdx.x == 0) has_both = 0;  // (ordered before its readers / writers by the barriers below)
-        for (int rev = 0; rev < 2; ++rev) {
-        if (rev == 1) {
-            __syncthreads();
-            if (!has_both) break;
-            int keep[BWD_LISTCAP / NTHREADS];
-            int k = 0;
-            __syncthreads();
-            if (threadIdx.x == 0) cnt = 0;
-            for (int i = threadIdx.x; i < n; i += NTHREADS) {
-                const int f = list[i];
-                keep[k++] = (__ldg(reinterpret_cast<const int *>(recs + f) + 15) & 1) ? f : -1;
-            }
-            __syncthreads();
-            for (int j = 0; j < k; ++j)
-                if (keep[j] >= 0) list[atomicAdd(&cnt, 1)] = keep[j];
-            __syncthreads();
-            nb = cnt;
-            if (nb == 0) break;
-        }
-        for (int f0 = 0; f0 < nb; f0 += BWD_SUB) {
-        const int *sub = list + f0;
-        const int ntasks = 6 * min(BWD_SUB, nb - f0);
-        // ---- the scan-lines of every task are cut into segments of <= SEG lines; counting sort of the
-        //      segments by decreasing length (full segments first)
-        __syncthreads();
-        if (threadIdx.x < SEG + 2) hist[threadIdx.x] = 0;
-        if (threadIdx.x == 0) next = 0;
-        if (rev == 0) {
-            for (int i = threadIdx.x; i < ntasks / 6 * 4; i += NTHREADS) {
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(recs + sub[i >> 2]) + (i & 3));
-                srec[i >> 2][i & 3] = v;
-                if ((i & 3) == 3 && (__float_as_int(v.w) & 1)) has_both = 1;
-            }
-        } else {
-            for (int i = threadIdx.x; i < ntasks / 6; i += NTHREADS) {  // corners 0 and 2 trade places, fn -> F + f
-                const float4 *rp = reinterpret_cast<const float4 *>(recs + sub[i]);
-                const float4 q0 = __ldg(rp), q1 = __ldg(rp + 1), q2 = __ldg(rp + 2), q3 = __ldg(rp + 3);
-                srec[i][0] = make_float4(q1.z, q1.w, q2.x, q0.w);
-                srec[i][1] = make_float4(q1.x, q1.y, q0.x, q0.y);
-                srec[i][2] = make_float4(q0.z, __int_as_float(__float_as_int(q2.y) + F), q3.x, q2.w);
-                srec[i][3] = make_float4(q2.z, q3.y, q3.z, q3.w);
-            }
-        }
-        __syncthreads();
-        for (int task = threadIdx.x; task < ntasks; task += NTHREADS) {
-            const int len = task_params(srec[task / 6], task, is, tx0, ty0).len;
-            slen[task] = (unsigned char)len;
-            if (len >= SEG) atomicAdd(&hist[SEG], len / SEG);
-            if (len % SEG) atomicAdd(&hist[len % SEG], 1);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {  // hpos[l] = number of segments longer than l
-            int run = 0;
-            for (int l = SEG; l >= 1; --l) { hpos[l] = run; run += hist[l]; }
-            hpos[0] = run;
-        }
-        __syncthreads();
-        for (int task = threadIdx.x; task < ntasks; task += NTHREADS) {
-            const int len = slen[task];
-            const int full = len / SEG;
-            if (full) {
-                const int at = atomicAdd(&hpos[SEG], full);
-                for (int i = 0; i < full; ++i) sorted[at + i] = (unsigned short)(task | (i << 12));
-            }
-            if (len % SEG) sorted[atomicAdd(&hpos[len % SEG], 1)] = (unsigned short)(task | (full << 12));
-        }
-        __syncthreads();
-        const int nwork = hpos[0];
-
-        for (;;) {  // warps pull groups of 32 tasks
-            int g = 0;
-            if (lane == 0) g = atomicAdd(&next, 1);
-            g = __shfl_sync(FULL, g, 0);
-            if (g * 32 >= nwork) break;
-            const bool mine_valid = g * 32 + lane < nwork;
-            const unsigned seg_id = sorted[min(g * 32 + lane, nwork - 1)];
-            const int my_task = seg_id & 0xfffu, seg_lo = (int)(seg_id >> 12) * SEG;
-            const TaskParams tp = task_params(srec[my_task / 6], my_task, is, tx0, ty0);
-            // ---- this thread's task
-            const float p0d0 = tp.p0d0, p0d1 = tp.p0d1, p1d0 = tp.p1d0, p2d0 = tp.p2d0, p2d1 = tp.p2d1;
-            const float slope = tp.slope, s02 = tp.slope02, s21 = tp.slope21, ka = tp.ka;
-            const int fn = tp.fn, axis = tp.axis, dir = tp.dir, lo = tp.lo + seg_lo;
-            const int mylen = mine_valid ? min(tp.len - seg_lo, SEG) : 0;
-            int maxlen = mylen;  // (the list is sorted, but tasks of equal length sit in arbitrary order)
+    // Turns `n` (<= 32) queued candidates, one per lane, into (crossing, run) items.
+    auto process = [&](int n) {
+        bool matched = false;
+        float x = 0.f, c0 = 0.f, c1 = 0.f;
+        unsigned key = 0, meta = 0;
+        int ra = 0, rc = 0;
+        if (lane < n) {
+            const unsigned c = q[lane];
+            const int xl = c & 63, yl = (c >> 6) & 63, axis = (c >> 12) & 1, dir = (c >> 13) & 1 ? 1 : -1;
+            const int own = fi[(yl + 1) * FIS + xl + 1];
+            BwdFace bf = load_bwd_face(brecs + (own >= F ? own - F : own));
+            if (bf.fn != own && bf.both && bf.fn + F == own) reverse_bwd_face(bf, F);
+            if (bf.fn == own) {
+                const int d0 = axis == 0 ? tx0 + xl : ty0 + yl, q0 = axis == 0 ? ty0 + yl : tx0 + xl;
+                const float fd0 = (float)d0;
+                // the pixel one step back along the sweep (in the tile or its halo)
+                const int prev_own = axis == 0 ? fi[(yl + 1 - dir) * FIS + xl + 1] : fi[(yl + 1) * FIS + xl + 1 - dir];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) maxlen = max(maxlen, __shfl_xor_sync(FULL, maxlen, o));
-            const int t0 = axis == 0 ? tx0 : ty0, t1 = axis == 0 ? ty0 : tx0;
-            const int lN = axis == 0 ? 2 : 0, lP = lN + 1;
-            const int fs0 = axis == 0 ? 1 : TILE, fs1 = axis == 0 ? TILE : 1;
-            // coverage bits of the out pixels: column lines for axis 0, row lines for axis 1 (read through L1)
-            const uint32_t *Ablock = axis == 0 ? cov_col + ((long)b * is + tx0) * W : cov_row + ((long)b * is + ty0) * W;
-            float acc0 = 0.f, acc1 = 0.f;
-            unsigned long long mine = 0ull;  // queue slots holding sweeps of this thread's task
-            int qn = 0;
-
-            // a drain evaluates the first 32 queued sweeps and hands every result to the thread that queued it
-            auto drain = [&](int nq) {
-                evaluate(nq);
-                unsigned m = (unsigned)mine;
-                while (m) {
-                    const int sl = __ffs(m) - 1;
-                    m &= m - 1;
-                    acc0 += q.r0[sl];
-                    acc1 += q.r1[sl];
+                for (int e = 0; e < 3; ++e) {
+                    const TaskGeom g = task_geom(bf, e, axis, is);
+                    if (g.dir != dir || d0 < g.d0_from || d0 > g.d0_to || !(fabsf(g.slope) <= SMAX)) continue;
+                    const float xe = g.slope * (fd0 - g.p0d0) + g.p0d1;
+                    const int d1_in = __float2int_rz(dir > 0 ? floorf(xe) : ceilf(xe));
+                    const int d1_out = d1_in + dir;
+                    if (d1_in < 0 || d1_in >= is || d1_out < 0 || d1_out >= is) continue;
+                    if (d1_in != q0 && !(d1_in == q0 - dir && prev_own == own)) continue;
+                    const bool has0 = g.p1d0 != fd0, has1 = g.p0d0 != fd0;
+                    const float e0 = __fdividef(g.ka, g.p1d0 - fd0), e1 = __fdividef(g.ka, fd0 - g.p0d0);
+                    const int lim = dir > 0 ? is - 1 : 0;
+                    if (!matched) {
+                        matched = true;
+                        x = xe; c0 = e0; c1 = e1;
+                        ra = min(d1_out, lim); rc = max(d1_out, lim);
+                        key = (unsigned)((own * 3 + e) * 2 + axis);
+                        meta = (unsigned)d0 | ((unsigned)axis << 12) | (has0 ? 1u << 13 : 0u) | (has1 ? 1u << 14 : 0u);
+                    } else {   // a second edge of the face through the same pixel (a corner on the line; rare): direct
+                        float a0 = 0.f, a1 = 0.f;
+                        sweep_line(S, axis == 0 ? 2 : 0, d0, min(d1_out, lim), max(d1_out, lim), xe, e0, e1, has0, has1,
+                                   false, a0, a1);
+                        if (a0 != 0.f) atomicAdd(grad_ndc + (long)g.vid0 * 3 + (1 - axis), a0);
+                        if (a1 != 0.f) atomicAdd(grad_ndc + (long)g.vid1 * 3 + (1 - axis), a1);
+                    }
                 }
-                mine >>= 32;
-                const int rem = qn - nq;  // > 0 only when nq == 32
-                float mx = 0.f, mc0 = 0.f, mc1 = 0.f, mg = 0.f;
-                unsigned mr = 0, mm = 0;
-                if (lane < rem) { mx = q.x[32 + lane]; mc0 = q.c0[32 + lane]; mc1 = q.c1[32 + lane]; mg = q.G[32 + lane]; mr = q.range[32 + lane]; mm = q.meta[32 + lane]; }
-                __syncwarp();
-                if (lane < rem) { q.x[lane] = mx; q.c0[lane] = mc0; q.c1[lane] = mc1; q.G[lane] = mg; q.range[lane] = mr; q.meta[lane] = mm; }
-                qn = max(rem, 0);
-                __syncwarp();
-            };
-            auto push_item = [&](bool has, float x, float c0, float c1, float G, unsigned rng, unsigned meta) {
-                const unsigned m = __ballot_sync(FULL, has);
-                if (!m) return;
-                if (has) {
-                    const int pos = qn + __popc(m & lt_mask);
-                    q.x[pos] = x; q.c0[pos] = c0; q.c1[pos] = c1; q.G[pos] = G; q.range[pos] = rng; q.meta[pos] = meta;
-                    mine |= 1ull << pos;
+            }
+        }
+        // ---- runs of the missing-coverage list inside the sweep: bit r = run r (bit 0 alone + walk flag on overflow)
+        unsigned todo = 0;
+        const uint2 *rl = S.runs;
+        if (matched) {
+            const int ls = (meta >> 12) & 1u ? 0 : 2, d0 = meta & 0xfffu;
+            const uint32_t info = __ldg(S.run_info + ls * is + d0);
+            const unsigned cnt = info & 15u;
+            const int lo = (info >> 4) & 0xfffu, hi = info >> 16;
+            if (cnt != 0u && rc >= lo && ra <= hi) {
+                rl += ((long)ls * is + d0) * RCAP;
+                if (cnt == RUN_OVERFLOW) {
+                    todo = 1u;
+                    meta |= 1u << 15;
+                    ra = max(ra, lo); rc = min(rc, hi);
+                } else {
+                    for (unsigned r = 0; r < cnt; ++r) {
+                        const unsigned se = __ldg(&rl[r].x);
+                        if (rc >= (int)(se & 0xffffu) && ra <= (int)(se >> 16)) todo |= 1u << r;
+                    }
+                }
+            }
+        }
+        // ---- one item per lane and round into the warp's queue; 32 queued items are evaluated at a time
+        while (__any_sync(FULL, todo != 0u)) {
+            const bool it = todo != 0u;
+            const unsigned m = __ballot_sync(FULL, it);
+            if (it) {
+                const int r = __ffs(todo) - 1;
+                todo &= todo - 1;
+                unsigned rng = (unsigned)ra | ((unsigned)rc << 16);
+                float G = 0.f;
+                if (!((meta >> 15) & 1u)) {
+                    const uint2 run = __ldg(rl + r);
+                    rng = (unsigned)max(ra, (int)(run.x & 0xffffu)) | ((unsigned)min(rc, (int)(run.x >> 16)) << 16);
+                    G = __uint_as_float(run.y);
+                }
+                const int pos = ni + __popc(m & lt_mask);
+                iq.x[pos] = x; iq.c0[pos] = c0; iq.c1[pos] = c1; iq.G[pos] = G;
+                iq.range[pos] = rng; iq.key[pos] = key; iq.meta[pos] = meta;
+            }
+            ni += __popc(m);
+            __syncwarp();
+            if (ni >= 32) drain(32);
+        }
+    };
+
+    // ---- each warp scans 8 rows of the tile; lane = column (two halves)
+    uint32_t ecol[2];
+    ecol[0] = ext_col[lane]; ecol[1] = ext_col[lane + 32];
+    for (int rr = 0; rr < TILE / NWARPS; ++rr) {
+        const int yl = warp * (TILE / NWARPS) + rr;
+        const int Y = ty0 + yl;
+        const uint32_t er = ext_row[yl];
+        const int row_lo = (er >> 4) & 0xfff, row_hi = er >> 16;
+        const int *rowp = fi + (yl + 1) * FIS + 1;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int xl = lane + 32 * half, X = tx0 + xl;
+            const int c = rowp[xl];
+            const bool cov = c >= 0;
+            if (!__any_sync(FULL, cov)) continue;
+            const int col_lo = (ecol[half] >> 4) & 0xfff, col_hi = ecol[half] >> 16;
+            // span ends with missing coverage beyond them: axis 1 sweeps along x (row lists), axis 0 along y
+            const bool cand[4] = {cov && rowp[xl + 1] != c && row_hi > X,        // axis 1, dir +1
+                                  cov && rowp[xl - 1] != c && row_lo < X,        // axis 1, dir -1
+                                  cov && rowp[xl + FIS] != c && col_hi > Y,      // axis 0, dir +1
+                                  cov && rowp[xl - FIS] != c && col_lo < Y};     // axis 0, dir -1
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned m = __ballot_sync(FULL, cand[k]);
+                if (cand[k]) {
+                    const int axis = k < 2 ? 1 : 0, dirbit = (k & 1) ? 0 : 1;
+                    q[qn + __popc(m & lt_mask)] = (unsigned short)(xl | (yl << 6) | (axis << 12) | (dirbit << 13));
                 }
                 qn += __popc(m);
+            }
+        }
+        __syncwarp();
+        int head = 0;
+        while (qn - head >= 32) {
+            if (head) {   // (process reads q[lane])
+                const unsigned short v = q[head + lane];
                 __syncwarp();
-                if (qn >= 32) drain(32);
-            };
-            // bit r of the result: run r of list `ls`, line `l0` has pixels inside [ra, rc] (bit 0 alone for a line
-            // whose run list overflowed: the sweep walks the bit line instead)
-            auto overlap_mask = [&](int ls, int l0, unsigned cnt, int ra, int rc) -> unsigned {
-                if (cnt == RUN_OVERFLOW) return 1u;
-                unsigned mk = 0;
-                for (unsigned r = 0; r < cnt; ++r) {
-                    const unsigned se = srun[ls][l0][r].x;
-                    if (rc >= (int)(se & 0xffffu) && ra <= (int)(se >> 16)) mk |= 1u << r;
-                }
-                return mk;
-            };
-
-            for (int k = 0; k < maxlen; ++k) {
-                bool has_out = false, has_in = false;
-                float x = 0.f, c0 = 0.f, c1 = 0.f;
-                int ra_out = 0, rc_out = 0, ra_in = 0, rc_in = 0, ls_in = 0, l0 = 0;
-                unsigned cnt_out = 0, cnt_in = 0, hb = 0;
-                if (k < mylen) {
-                    const int d0 = lo + k;
-                    l0 = d0 - t0;
-                    const unsigned cN = scount[lN][l0], cP = scount[lP][l0];
-                    if ((cN | cP) != 0u) {  // something to sweep on this line
-                        const float fd0 = (float)d0;
-                        x = slope * (fd0 - p0d0) + p0d1;
-                        const int d1_in = __float2int_rz(dir > 0 ? floorf(x) : ceilf(x));
-                        const int d1_out = d1_in + dir;
-                        if (d1_in >= 0 && d1_in < is && d1_out >= 0 && d1_out < is && d1_in >= t1 && d1_in < t1 + TILE) {
-                            hb = (p1d0 != fd0 ? 1u << 8 : 0u) | (p0d0 != fd0 ? 1u << 9 : 0u) | ((unsigned)l0 << 2);
-                            // out-sweep (missing-coverage list, from the out pixel to the border) when this face
-                            // owns the in pixel
-                            if (cN != 0u && fi[l0 * fs0 + (d1_in - t1) * fs1] == fn) {
-                                const int lim = dir > 0 ? is - 1 : 0;
-                                const int ra = min(d1_out, lim), rc = max(d1_out, lim);
-                                has_out = true; ra_out = ra; rc_out = rc; cnt_out = cN;
-                            }
-                            // in-sweep (from the in pixel to the opposite edge of the triangle)
-                            {
-                                const bool alpha_out = (__ldg(Ablock + l0 * W + (d1_out >> 5)) >> (d1_out & 31)) & 1u;
-                                const int ls = alpha_out ? lN : lP;
-                                const unsigned cs = alpha_out ? cN : cP;
-                                if (cs != 0u) {
-                                    float c2;
-                                    if ((fd0 - p0d0) * (fd0 - p2d0) < 0.f) c2 = s02 * (fd0 - p0d0) + p0d1;
-                                    else c2 = s21 * (fd0 - p2d0) + p2d1;
-                                    const int lim = __float2int_rz(dir > 0 ? ceilf(c2) : floorf(c2));
-                                    const int ra = max(min(d1_in, lim), 0), rc = min(max(d1_in, lim), is - 1);
-                                    if (ra <= rc) {
-                                        has_in = true; ra_in = ra; rc_in = rc; ls_in = ls;
-                                        // an in-sweep can straddle its crossing: by one pixel when the triangle is
-                                        // thinner than a pixel there (eval_item copes with up to NEAR_N - 1 pixels
-                                        // on the near side), by many when its far end is the extrapolation of an
-                                        // edge that does not span the scan-line (degenerate faces): the closed
-                                        // form assumes one side, so such a sweep walks the bit line instead
-                                        cnt_in = ((float)ra < x - (float)(NEAR_N - 1) && (float)rc > x) ? RUN_OVERFLOW : cs;
-                                    }
-                                }
-                            }
-                            if (has_out || has_in) { c0 = __fdividef(ka, p1d0 - fd0); c1 = __fdividef(ka, fd0 - p0d0); }
-                        }
-                    }
-                }
-                // runs to visit: bits 0-7 out-sweep, 8-15 in-sweep; one (crossing, run) item per lane and round
-                unsigned todo = 0;
-                if (has_out) todo = overlap_mask(lN, l0, cnt_out, ra_out, rc_out);
-                if (has_in) todo |= overlap_mask(ls_in, l0, cnt_in, ra_in, rc_in) << 8;
-                while (__any_sync(FULL, todo != 0u)) {
-                    bool it = false;
-                    unsigned se = 0, meta = 0;
-                    float G = 0.f;
-                    if (todo) {
-                        const int bit = __ffs(todo) - 1;
-                        todo &= todo - 1;
-                        const bool in_sw = bit >= 8;
-                        const int r = bit & 7, ls = in_sw ? ls_in : lN;
-                        const int ra = in_sw ? ra_in : ra_out, rc = in_sw ? rc_in : rc_out;
-                        it = true;
-                        meta = hb | (unsigned)ls;
-                        if ((in_sw ? cnt_in : cnt_out) == RUN_OVERFLOW) {
-                            se = (unsigned)ra | ((unsigned)rc << 16); meta |= 1u << 10;
-                        } else {
-                            const uint2 run = srun[ls][l0][r];
-                            se = (unsigned)max(ra, (int)(run.x & 0xffffu)) | ((unsigned)min(rc, (int)(run.x >> 16)) << 16);
-                            G = __uint_as_float(run.y);
-                        }
-                    }
-                    push_item(it, x, c0, c1, G, se, meta);
-                }
+                q[lane] = v;
+                __syncwarp();
             }
-            if (qn > 0) drain(qn);
-            if (mine_valid) {
-                // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
-                if (acc0 != 0.f) atomicAdd(grad_ndc + (long)tp.vid0 * 3 + (1 - axis), acc0);
-                if (acc1 != 0.f) atomicAdd(grad_ndc + (long)tp.vid1 * 3 + (1 - axis), acc1);
-            }
+            process(32);
+            head += 32;
         }
-        }
+        if (head) {   // move the leftover to the front
+            const int rem = qn - head;
+            unsigned short v = 0;
+            if (lane < rem) v = q[head + lane];
+            __syncwarp();
+            if (lane < rem) q[lane] = v;
+            qn = rem;
+            __syncwarp();
         }
     }
+    if (qn > 0) process(qn);
+    if (ni > 0) drain(ni);
 }
 
 // ------------------------------------------------------------------------------------------ RGB / depth (visualisation)
@@ -1388,9 +1551,10 @@ int hm_raster_setup(const float *ndc, const int32_t *faces, int faces_batch, int
     HM_REQUIRE(ndc && faces && records && bboxes, "hm_raster_setup: null pointer");
     HM_REQUIRE(V > 0, "hm_raster_setup: bad sizes");
     const long n = (long)B * F;
+    HM_UNSUPPORTED(2L * F > BWD_FN_MASK, "hm_raster_setup: too many faces (%d)", F);
     face_setup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, hm_stream(stream)>>>(
         ndc, faces, faces_batch, B, V, F, is, fill_back, static_cast<FaceRec *>(records),
-        static_cast<FaceBox *>(bboxes));
+        reinterpret_cast<BwdRec *>(static_cast<FaceRec *>(records) + n), static_cast<FaceBox *>(bboxes));
     HM_CHECK_LAUNCH("hm_raster_setup");
     return HM_OK;
 }
@@ -1451,14 +1615,13 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
                    run_counts && grad_ndc,
                "hm_raster_sil_bwd: null pointer");
     HM_REQUIRE(V > 0, "hm_raster_sil_bwd: bad sizes");
-    const size_t smem = (size_t)TILE * TILE * 4 + NWARPS * sizeof(SweepQueue);
     HM_UNSUPPORTED(is > 1024, "hm_raster_sil_bwd: raster size %d > 1024 is not supported", is);
-    static HmSmemOptIn opt_in;  // static + dynamic shared memory exceeds the 48 KB default
-    if (int rc = hm_smem_opt_in(raster_bwd_kernel, smem, opt_in, "hm_raster_sil_bwd")) return rc;
-    dim3 grid((is / TILE) * (is / TILE), B);
-    raster_bwd_kernel<<<grid, NTHREADS, smem, hm_stream(stream)>>>(
-        static_cast<const FaceRec *>(records), static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps,
-        face_index, grad_alpha, cov_row, cov_col, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
+    const int n_face_ctas = (F + BFACES - 1) / BFACES;
+    dim3 grid(n_face_ctas + (is / TILE) * (is / TILE), B);
+    raster_bwd_kernel<<<grid, NTHREADS, 0, hm_stream(stream)>>>(
+        reinterpret_cast<const BwdRec *>(static_cast<const FaceRec *>(records) + (long)B * F),
+        static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, n_face_ctas, face_index, grad_alpha, cov_row,
+        cov_col, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
     HM_CHECK_LAUNCH("hm_raster_sil_bwd");
     return HM_OK;
 }

@@ -53,10 +53,11 @@ int hm_project_bwd(const float *verts, const float *K, int K_batch, const float 
  * (z-buffered nearest front face, vertical flip, 2x2 average pool when anti-aliasing) and its
  * hand-crafted backward (backward_pixel_map).  image_size is the OUTPUT size R; the raster size is
  * S = 2R with anti-aliasing.  S must be a multiple of 64. */
-#define HM_FACE_RECORD_BYTES 128
+#define HM_FACE_RECORD_BYTES 192
 #define HM_FACE_BBOX_BYTES 8
-/* ndc [B,V,3], faces [faces_batch,F,3] -> records [B,F,128 B] + bboxes [B,F,8 B] (front-facing
- * winding of every face; never materialises the doubled face array). */
+/* ndc [B,V,3], faces [faces_batch,F,3] -> records (B*F*HM_FACE_RECORD_BYTES bytes: a plane of 128-byte forward
+ * records followed by a plane of 64-byte backward records) + bboxes [B,F,8 B] (front-facing winding of every face;
+ * never materialises the doubled face array). */
 int hm_raster_setup(const float *ndc, const int32_t *faces, int faces_batch, int B, int V, int F,
                     int image_size, int anti_aliasing, int fill_back, void *records, void *bboxes,
                     void *stream);
@@ -67,7 +68,7 @@ int hm_raster_sil_fwd(const void *records, const void *bboxes, int B, int F, int
                       uint32_t *cov_row, uint32_t *cov_col, void *stream);
 /* grad_alpha [B,R,R] + coverage -> sweep masks m_row / m_col [B,2,S,S/32]
  * (0: uncovered & grad<0, 1: covered & grad>0) and their run-length form:
- * runs [B,4,S,HM_RASTER_RUN_CAP] (8 B each), run_counts [B,4,S]. */
+ * runs [B,4,S,HM_RASTER_RUN_CAP] (8 B each), run_counts [B,4,S] (count | first pixel << 4 | last pixel << 16). */
 #define HM_RASTER_RUN_CAP 8
 int hm_raster_grad_prep(const float *grad_alpha, const uint32_t *cov_row, const uint32_t *cov_col, int B,
                         int image_size, int anti_aliasing, uint32_t *m_row, uint32_t *m_col, void *runs,
