@@ -38,11 +38,15 @@ struct __align__(16) BwdRec {
     float slope[3][2];    // edge e = corner e -> e + 1: [0] = dy / dx (axis 0: lines x = d0), [1] = dx / dy (axis 1)
     int v[3];             // vertex indices
     int meta;             // < 0: culled / off screen; else fn | BWD_IRREGULAR | BWD_BOTH
+    uint32_t span[3][2];  // per (edge, axis): scan-lines d0_from | d0_to << 12 (empty: 1, 0), sweep direction > 0 << 24,
+                          //   steep (|slope| > SMAX or not finite) << 25
+    uint32_t pad[2];
 };
-static_assert(sizeof(BwdRec) == 64 && sizeof(FaceRec) + sizeof(BwdRec) == HM_FACE_RECORD_BYTES, "record size");
+static_assert(sizeof(BwdRec) == 96 && sizeof(FaceRec) + sizeof(BwdRec) == HM_FACE_RECORD_BYTES, "record size");
 constexpr int BWD_FN_MASK = (1 << 29) - 1;
 constexpr int BWD_IRREGULAR = 1 << 29;   // a corner on an integer pixel coordinate (or not finite): never skipped
 constexpr int BWD_BOTH = 1 << 30;        // both windings are front-facing: F + f is differentiated too
+constexpr float BWD_SMAX = 128.f;        // tasks steeper than this are enumerated from the face (see the backward kernels)
 
 struct __align__(8) FaceBox {
     short x0, y0, x1, y1;
@@ -212,6 +216,21 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
             br.slope[e][0] = (br.py[e1] - br.py[e]) / (br.px[e1] - br.px[e]);
             br.slope[e][1] = (br.px[e1] - br.px[e]) / (br.py[e1] - br.py[e]);
         }
+#pragma unroll
+        for (int e = 0; e < 3; ++e) {
+            const int e1 = e == 2 ? 0 : e + 1;
+#pragma unroll
+            for (int axis = 0; axis < 2; ++axis) {   // the scan-line range and direction backward_pixel_map derives
+                const float p0 = axis ? br.py[e] : br.px[e], p1 = axis ? br.py[e1] : br.px[e1];
+                int from = __float2int_rz(fmaxf(ceilf(fminf(p0, p1)), 0.f));
+                int to = __float2int_rz(fminf(fmaxf(p0, p1), (float)(is - 1)));
+                if (from > to) { from = 1; to = 0; }
+                const bool plus = axis == 0 ? !(p0 < p1) : (p0 < p1);
+                const bool steep = !(fabsf(br.slope[e][axis]) <= BWD_SMAX);
+                br.span[e][axis] = (unsigned)from | ((unsigned)to << 12) | (plus ? 1u << 24 : 0u) | (steep ? 1u << 25 : 0u);
+            }
+        }
+        br.pad[0] = br.pad[1] = 0u;
         br.meta = fn < 0 ? -1 : (fn | (irregular ? BWD_IRREGULAR : 0) | (both ? BWD_BOTH : 0));
         brecs[i] = br;
     }
@@ -819,6 +838,7 @@ build_runs_kernel(const float *__restrict__ grad_alpha, const uint32_t *__restri
 }
 
 // ------------------------------------------------------------------------------------------ backward
+// @region eval_item
 // One MUFU.RCP (1 ulp) instead of the IEEE reciprocal sequence: the sweep sums tolerate it (parity bar 1e-4).
 __device__ __forceinline__ float rcp_fast(float x) {
     float y;
@@ -876,6 +896,7 @@ __device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, 
     a1 = has1 ? -G * h1 : 0.f;
 }
 
+// @region sweep_bits
 // Bit-line walk for lines whose run list overflowed: visits the set bits of `line` in [a, c].
 __device__ __forceinline__ void sweep_bits(const uint32_t *line, int a, int c, int axis, int d0, float d1_cross,
                                            float c0, float c1, bool has0, bool has1, const BwdCtx &ctx, float &acc0,
@@ -929,13 +950,12 @@ __device__ __forceinline__ void sweep_bits(const uint32_t *line, int a, int c, i
 //     reference does.
 // Per-crossing sums stay in registers; role A merges the crossings of one (face, edge, axis) task inside a warp
 // (match.any) before the global atomicAdd into grad_ndc (the vertices_to_faces scatter-add is fused).
-constexpr float SMAX = 128.f;
-constexpr int FIS = TILE + 4;           // row stride of the face_index tile with its one-pixel halo (ints)
+// @region geom
+constexpr float SMAX = BWD_SMAX;
+constexpr int FIS = TILE + 8;           // row stride of the face_index tile (ints): pixel (x, y) at (y + 1) * FIS + 4 + x,
+constexpr int FIX0 = 4;                 //   one-pixel halo all round, rows 16-byte aligned
 constexpr int CQCAP = 32 + 8 * TILE;    // per-warp candidate queue: a leftover batch + one tile row of candidates
-constexpr int BFACES = NTHREADS;        // faces per role-B CTA
-constexpr int TQCAP = 12 * 32;          // per-warp task list of role B (6 tasks x 2 copies x 32 faces)
-static_assert(TQCAP <= CQCAP, "role B reuses the candidate queues");
-
+constexpr int BFACES = NTHREADS;        // faces per CTA of the face kernel
 constexpr int IQCAP = 64;               // per-warp queue of (crossing, run) items
 struct ItemQueue {
     float x[IQCAP], c0[IQCAP], c1[IQCAP], G[IQCAP];   // crossing position, distance coefficients, run weight
@@ -1015,11 +1035,27 @@ struct SweepSrc {
     float inv_is2, eps;
     BwdCtx ctx;
 };
+__device__ __forceinline__ SweepSrc sweep_src(int b, int is, int aa, float eps, const float *grad_alpha,
+                                              const uint32_t *m_row, const uint32_t *m_col, const uint2 *runs,
+                                              const uint32_t *run_info) {
+    SweepSrc S;
+    const int W = is / 32;
+    S.runs = runs + (long)b * 4 * is * RCAP;
+    S.run_info = run_info + (long)b * 4 * is;
+    S.m_row = m_row + (long)b * 2 * is * W;
+    S.m_col = m_col + (long)b * 2 * is * W;
+    S.is = is; S.W = W; S.inv_is2 = 2.f / (float)is; S.eps = eps;
+    S.ctx.is = is; S.ctx.aa = aa; S.ctx.R = aa ? is / 2 : is; S.ctx.eps = eps;
+    S.ctx.grad = grad_alpha + (long)b * S.ctx.R * S.ctx.R;
+    return S;
+}
 
+// @region sweep_line
 // Sum over the pixels of list `ls` (0 mn_row, 1 mp_row, 2 mn_col, 3 mp_col) on line d0 inside [ra, rc], seen from the
 // crossing at x. `walk`: visit the bit line pixel by pixel (run list overflowed, or the sweep straddles its crossing).
-__device__ __forceinline__ void sweep_line(const SweepSrc &S, int ls, int d0, int ra, int rc, float x, float c0, float c1,
-                                           bool has0, bool has1, bool walk, float &acc0, float &acc1) {
+// The rare, lane-divergent path (in-sweeps, second edges): not inlined, the hot kernels stay small.
+__device__ __noinline__ void sweep_line(const SweepSrc &S, int ls, int d0, int ra, int rc, float x, float c0, float c1,
+                                        bool has0, bool has1, bool walk, float &acc0, float &acc1) {
     const uint32_t info = __ldg(S.run_info + ls * S.is + d0);
     const unsigned cnt = info & 15u;
     if (cnt == 0u) return;
@@ -1042,53 +1078,144 @@ __device__ __forceinline__ void sweep_line(const SweepSrc &S, int ls, int d0, in
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 4)
-raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
-                  float eps, int n_face_ctas, const int32_t *__restrict__ face_index,
-                  const float *__restrict__ grad_alpha, const uint32_t *__restrict__ cov_row,
-                  const uint32_t *__restrict__ cov_col, const uint32_t *__restrict__ m_row,
-                  const uint32_t *__restrict__ m_col, const uint2 *__restrict__ runs,
-                  const uint32_t *__restrict__ run_info, float *__restrict__ grad_ndc) {
-    __shared__ int fi[(TILE + 2) * FIS];                   // role A: face_index tile, one-pixel halo
-    __shared__ unsigned short cq[NWARPS][CQCAP];           // role A: candidates; role B: task lists (TQCAP <= CQCAP)
-    __shared__ uint32_t ext_row[TILE], ext_col[TILE];      // role A: extent of the missing-coverage list per line
-    __shared__ ItemQueue iqs[NWARPS];                      // role A: (crossing, run) items
+// @region items
+// ---- the (crossing, run) item pipeline shared by the two backward kernels: a per-warp ring of IQCAP items
+// Queues one item per lane and round (bit r of `todo` = run r of the line's list overlaps the sweep [ra, rc]; with
+// META_WALK the single item is the whole sweep, walked on the bit line). The caller drains when count >= 32.
+constexpr unsigned META_WALK = 1u << 15, META_PLANE = 1u << 16;
+__device__ __forceinline__ void push_round(ItemQueue &iq, int head, int &count, unsigned &todo, const uint2 *rl, int ra,
+                                           int rc, float x, float c0, float c1, unsigned key, unsigned meta, int lane) {
+    const bool it = todo != 0u;
+    const unsigned m = __ballot_sync(0xffffffffu, it);
+    if (it) {
+        const int r = __ffs(todo) - 1;
+        todo &= todo - 1;
+        unsigned rng = (unsigned)ra | ((unsigned)rc << 16);
+        float G = 0.f;
+        if (!(meta & META_WALK)) {
+            const uint2 run = __ldg(rl + r);
+            rng = (unsigned)max(ra, (int)(run.x & 0xffffu)) | ((unsigned)min(rc, (int)(run.x >> 16)) << 16);
+            G = __uint_as_float(run.y);
+        }
+        const int pos = (head + count + __popc(m & ((1u << lane) - 1u))) & (IQCAP - 1);
+        iq.x[pos] = x; iq.c0[pos] = c0; iq.c1[pos] = c1; iq.G[pos] = G;
+        iq.range[pos] = rng; iq.key[pos] = key; iq.meta[pos] = meta;
+    }
+    count += __popc(m);
+    __syncwarp();
+}
+
+// Bits of the runs of list `ls`, line d0 that have pixels inside [ra, rc] (clipped to the list's extent); 1 + META_WALK
+// when the run list overflowed or `walk` is set. rl receives the run list.
+__device__ __forceinline__ unsigned runs_in_sweep(const SweepSrc &S, int ls, int d0, int &ra, int &rc, bool walk,
+                                                  unsigned &meta, const uint2 *&rl) {
+    const uint32_t info = __ldg(S.run_info + ls * S.is + d0);
+    const unsigned cnt = info & 15u;
+    const int lo = (info >> 4) & 0xfffu, hi = info >> 16;
+    if (cnt == 0u || rc < lo || ra > hi) return 0u;
+    rl = S.runs + ((long)ls * S.is + d0) * RCAP;
+    if (cnt == RUN_OVERFLOW || walk) {
+        meta |= META_WALK;
+        ra = max(ra, lo); rc = min(rc, hi);
+        return 1u;
+    }
+    unsigned todo = 0;
+    for (unsigned r = 0; r < cnt; ++r) {
+        const unsigned se = __ldg(&rl[r].x);
+        if (rc >= (int)(se & 0xffffu) && ra <= (int)(se >> 16)) todo |= 1u << r;
+    }
+    return todo;
+}
+
+// Evaluates the first `n` (<= 32) queued items, one per lane. Items of one (face, edge, axis) task met in the batch are
+// summed inside the warp (match.any + pointer jumping over the peers) and leave as one atomicAdd per vertex slot.
+__device__ __forceinline__ void drain_items(ItemQueue &iq, int &head, int &count, int n, const SweepSrc &S,
+                                            const BwdRec *brecs, int F, float *grad_ndc, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    unsigned key = 0x80000000u | lane;
+    float a0 = 0.f, a1 = 0.f;
+    if (lane < n) {
+        const int s = (head + lane) & (IQCAP - 1);
+        const unsigned meta = iq.meta[s], rng = iq.range[s];
+        const int d0 = meta & 0xfffu, axis = (meta >> 12) & 1u;
+        const bool has0 = (meta >> 13) & 1u, has1 = (meta >> 14) & 1u;
+        const int ra = rng & 0xffffu, rc = rng >> 16;
+        key = iq.key[s];
+        if (meta & META_WALK) {   // run list overflowed, or the sweep straddles its crossing: walk the bit line
+            const uint32_t *line = (axis == 0 ? S.m_col : S.m_row) + ((long)((meta >> 16) & 1u) * S.is + d0) * S.W;
+            sweep_bits(line, ra, rc, axis, d0, iq.x[s], iq.c0[s], iq.c1[s], has0, has1, S.ctx, a0, a1);
+        } else {
+            eval_item(iq.x[s], iq.c0[s], iq.c1[s], iq.G[s], ra, rc, has0, has1, S.inv_is2, S.eps, a0, a1);
+        }
+    }
+    const unsigned peers = __match_any_sync(FULL, key);
+    if (__any_sync(FULL, peers & (peers - 1u))) {   // some task has several items here: suffix sums along the peers
+        const unsigned higher = lane == 31 ? 0u : peers & (0xffffffffu << (lane + 1));
+        int nxt = higher ? __ffs(higher) - 1 : -1;
+#pragma unroll
+        for (int r = 0; r < 5; ++r) {
+            const int src = nxt < 0 ? lane : nxt;
+            const float t0 = __shfl_sync(FULL, a0, src), t1 = __shfl_sync(FULL, a1, src);
+            const int tn = __shfl_sync(FULL, nxt, src);
+            if (nxt >= 0) { a0 += t0; a1 += t1; nxt = tn; }
+        }
+    }
+    if (lane < n && lane == __ffs(peers) - 1 && (a0 != 0.f || a1 != 0.f)) {
+        // key = (owner * 3 + edge) * 2 + axis: the two vertices of the edge come from the owner's record
+        const int own = (int)(key / 6u), e = (int)((key >> 1) % 3u), axis = (int)(key & 1u);
+        const int4 q3 = __ldg(reinterpret_cast<const int4 *>(brecs + (own >= F ? own - F : own)) + 3);
+        const bool rev = (q3.w & BWD_FN_MASK) != own;   // the reversed copy of a both-windings face
+        const int v0 = rev ? q3.z : q3.x, v1 = q3.y, v2 = rev ? q3.x : q3.z;
+        const int vid0 = e == 0 ? v0 : e == 1 ? v1 : v2, vid1 = e == 0 ? v1 : e == 1 ? v2 : v0;
+        // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
+        if (a0 != 0.f) atomicAdd(grad_ndc + (long)vid0 * 3 + (1 - axis), a0);
+        if (a1 != 0.f) atomicAdd(grad_ndc + (long)vid1 * 3 + (1 - axis), a1);
+    }
+    head = (head + n) & (IQCAP - 1);
+    count -= n;
+    __syncwarp();
+}
+
+// @region face_setup
+// ------------------------------------------------------------------ face side: in-sweeps and steep tasks
+// Thread per face: is it at the silhouette (an uncovered pixel in its pixel bounding box) or irregular, which of its
+// tasks are steep. Then warp per listed face: the scan-lines of its six (edge, axis) tasks are flattened over the
+// lanes, every lane tests one crossing, contributing crossings queue (crossing, run) items.
+__global__ void __launch_bounds__(NTHREADS)
+raster_bwd_face_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
+                       float eps, const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
+                       const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ cov_col,
+                       const uint32_t *__restrict__ m_row, const uint32_t *__restrict__ m_col,
+                       const uint2 *__restrict__ runs, const uint32_t *__restrict__ run_info,
+                       float *__restrict__ grad_ndc) {
+    __shared__ unsigned flist[2 * BFACES];   // face | copy << 8 | silhouette << 9 | steep tasks << 10
+    __shared__ int n_list;
+    __shared__ ItemQueue iqs[NWARPS];
     const int b = blockIdx.y;
     const int W = is / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
-    const unsigned lt_mask = (1u << lane) - 1u;
     brecs += (long)b * F;
     boxes += (long)b * F;
     grad_ndc += (long)b * V * 3;
     face_index += (long)b * is * is;
     cov_row += (long)b * is * W;
     cov_col += (long)b * is * W;
-    SweepSrc S;
-    S.runs = runs + (long)b * 4 * is * RCAP;
-    S.run_info = run_info + (long)b * 4 * is;
-    S.m_row = m_row + (long)b * 2 * is * W;
-    S.m_col = m_col + (long)b * 2 * is * W;
-    S.is = is; S.W = W; S.inv_is2 = 2.f / (float)is; S.eps = eps;
-    S.ctx.is = is; S.ctx.aa = aa; S.ctx.R = aa ? is / 2 : is; S.ctx.eps = eps;
-    S.ctx.grad = grad_alpha + (long)b * S.ctx.R * S.ctx.R;
-
-#ifdef HM_BWD_ROLE_MASK   // development: 1 = role A only, 2 = role B only
-    if (!(((int)blockIdx.x < n_face_ctas ? 2 : 1) & HM_BWD_ROLE_MASK)) return;
-#endif
-    if ((int)blockIdx.x < n_face_ctas) {
-        // =================================================================== role B: in-sweeps, steep tasks
+    const SweepSrc S = sweep_src(b, is, aa, eps, grad_alpha, m_row, m_col, runs, run_info);
+    if (threadIdx.x == 0) n_list = 0;
+    __syncthreads();
+    {
         const int f = blockIdx.x * BFACES + threadIdx.x;
-        unsigned todo = 0;  // bits 0-5: tasks (edge * 2 + axis) of the face; bits 6-11: of its reversed copy;
-                            // bit 12: the face is at the silhouette (in-sweeps on), else only steep out-sweeps
         if (f < F) {
-            const BwdFace bf = load_bwd_face(brecs + f);
-            if (bf.fn >= 0) {
+            const int4 q3 = __ldg(reinterpret_cast<const int4 *>(brecs + f) + 3);
+            if (q3.w >= 0) {
+                const uint4 s4 = __ldg(reinterpret_cast<const uint4 *>(brecs + f) + 4);
+                const uint2 s5 = __ldg(reinterpret_cast<const uint2 *>(brecs + f) + 10);
+                const unsigned sp[6] = {s4.x, s4.y, s4.z, s4.w, s5.x, s5.y};
                 unsigned steep = 0;
 #pragma unroll
-                for (int t = 0; t < 6; ++t)
-                    if (!(fabsf(bf.sl[t >> 1][t & 1]) <= SMAX)) steep |= 1u << t;
-                bool boundary = bf.irregular;
+                for (int t = 0; t < 6; ++t) steep |= ((sp[t] >> 25) & 1u) << t;
+                bool boundary = q3.w & BWD_IRREGULAR;
                 if (!boundary) {
                     const FaceBox bx = boxes[f];  // clamped pixel bbox with one pixel of slack
                     const int w0 = bx.x0 >> 5, w1 = bx.x1 >> 5;
@@ -1099,99 +1226,144 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ 
                             if (~__ldg(cov_row + (long)y * W + w) & m) { boundary = true; break; }
                         }
                 }
-                todo = boundary ? (0x3fu | (1u << 12)) : steep;
-                if (bf.both) {   // both windings front-facing: the reversed copy F + f is differentiated too
-                    const unsigned steep_rev = ((steep >> 2) & 3u) | ((steep & 3u) << 2) | (steep & 0x30u);
-                    todo |= (boundary ? 0x3fu : steep_rev) << 6;
+                if (boundary || steep) {
+                    const unsigned ent = (unsigned)threadIdx.x | (boundary ? 1u << 9 : 0u);
+                    const int both = (q3.w & BWD_BOTH) ? 1 : 0;
+                    const int at = atomicAdd(&n_list, 1 + both);
+                    flist[at] = ent | (steep << 10);
+                    // the reversed copy F + f of a both-windings face: edges 0 and 1 trade places
+                    if (both) flist[at + 1] = ent | (1u << 8) | ((((steep >> 2) & 3u) | ((steep & 3u) << 2) | (steep & 0x30u)) << 10);
                 }
             }
         }
-        // ---- the warp's tasks, compacted: lane | task << 5 | copy << 8 | boundary << 9
-        unsigned short *tq = cq[warp];
-        int nt = 0;
-        {
-            const unsigned tasks = todo & 0xfffu;
-            int mine = __popc(tasks), incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += v;
-            }
-            nt = __shfl_sync(FULL, incl, 31);
-            int pos = incl - mine;
-            unsigned m = tasks;
-            while (m) {
-                const int t = __ffs(m) - 1;
-                m &= m - 1;
-                tq[pos++] = (unsigned short)(lane | ((t % 6) << 5) | ((t / 6) << 8) | (((todo >> 12) & 1u) << 9));
-            }
+    }
+    __syncthreads();
+// @region face_tasks
+    ItemQueue &iq = iqs[warp];
+    int head = 0, count = 0;
+    const int nl = n_list;
+    for (int j = warp; j < nl; j += NWARPS) {
+        const unsigned ent = flist[j];
+        const bool copy = (ent >> 8) & 1u, boundary = (ent >> 9) & 1u;
+        const unsigned steep_mask = (ent >> 10) & 0x3fu;
+        const BwdRec *rp = brecs + blockIdx.x * BFACES + (ent & 0xffu);
+        BwdFace bf = load_bwd_face(rp);   // (warp-uniform address: one broadcast load)
+        const uint4 s4 = __ldg(reinterpret_cast<const uint4 *>(rp) + 4);
+        const uint2 s5 = __ldg(reinterpret_cast<const uint2 *>(rp) + 10);
+        unsigned sp[6] = {s4.x, s4.y, s4.z, s4.w, s5.x, s5.y};
+        if (copy) {
+            reverse_bwd_face(bf, F);
+            unsigned t = sp[0]; sp[0] = sp[2]; sp[2] = t;
+            t = sp[1]; sp[1] = sp[3]; sp[3] = t;
         }
-        __syncwarp();
-        for (int i = lane; i < nt; i += 32) {
-            const unsigned ent = tq[i];
-            const int fl = ent & 31, task = (ent >> 5) & 7, copy = (ent >> 8) & 1;
-            const bool boundary = (ent >> 9) & 1u;
-            BwdFace bf = load_bwd_face(brecs + blockIdx.x * BFACES + (warp << 5) + fl);
-            if (copy) reverse_bwd_face(bf, F);
-            const int e = task >> 1, axis = task & 1;
-            const TaskGeom g = task_geom(bf, e, axis, is);
-            const bool steep = !(fabsf(g.slope) <= SMAX);
-            const int lN = axis == 0 ? 2 : 0, lP = lN + 1;
-            const uint32_t *cov = axis == 0 ? cov_col : cov_row;   // coverage words of line d0 along d1
-            float acc0 = 0.f, acc1 = 0.f;
-            for (int d0 = g.d0_from; d0 <= g.d0_to; ++d0) {
+        // scan-lines of the six tasks (in-sweeps: all tasks of a silhouette face; otherwise only the steep tasks)
+        int from[6], pre[7];
+        pre[0] = 0;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+            from[t] = sp[t] & 0xfffu;
+            const int len = (int)((sp[t] >> 12) & 0xfffu) - from[t] + 1;
+            pre[t + 1] = pre[t] + ((boundary || ((steep_mask >> t) & 1u)) ? max(len, 0) : 0);
+        }
+        const int N = pre[6];
+        for (int base = 0; base < N; base += 32) {
+            const int i = base + lane;
+            unsigned todo_in = 0, todo_out = 0, key = 0, meta_in = 0, meta_out = 0;
+            const uint2 *rl_in = S.runs, *rl_out = S.runs;
+            float x = 0.f, c0 = 0.f, c1 = 0.f;
+            int ra_in = 0, rc_in = 0, ra_out = 0, rc_out = 0;
+            if (i < N) {
+                const int t = (i >= pre[1]) + (i >= pre[2]) + (i >= pre[3]) + (i >= pre[4]) + (i >= pre[5]);
+                const int tf = t == 0 ? from[0] : t == 1 ? from[1] : t == 2 ? from[2] : t == 3 ? from[3] : t == 4 ? from[4] : from[5];
+                const int tp = t == 0 ? pre[0] : t == 1 ? pre[1] : t == 2 ? pre[2] : t == 3 ? pre[3] : t == 4 ? pre[4] : pre[5];
+                const int d0 = tf + (i - tp), e = t >> 1, axis = t & 1;
+                const TaskGeom g = task_geom(bf, e, axis, is);
                 const float fd0 = (float)d0;
-                const float x = g.slope * (fd0 - g.p0d0) + g.p0d1;
+                x = g.slope * (fd0 - g.p0d0) + g.p0d1;
                 const int d1_in = __float2int_rz(g.dir > 0 ? floorf(x) : ceilf(x));
                 const int d1_out = d1_in + g.dir;
-                if (d1_in < 0 || d1_in >= is || d1_out < 0 || d1_out >= is) continue;
-                const bool has0 = g.p1d0 != fd0, has1 = g.p0d0 != fd0;
-                const float c0 = __fdividef(g.ka, g.p1d0 - fd0), c1 = __fdividef(g.ka, fd0 - g.p0d0);
-                if (steep) {   // out-sweep of a steep task: the reference's own ownership test
-                    const int own = axis == 0 ? __ldg(face_index + (long)d1_in * is + d0)
-                                              : __ldg(face_index + (long)d0 * is + d1_in);
-                    if (own == bf.fn) {
-                        const int lim = g.dir > 0 ? is - 1 : 0;
-                        sweep_line(S, lN, d0, min(d1_out, lim), max(d1_out, lim), x, c0, c1, has0, has1, false, acc0, acc1);
+                if ((unsigned)d1_in < (unsigned)is && (unsigned)d1_out < (unsigned)is) {
+                    const int lN = axis == 0 ? 2 : 0;
+                    const unsigned meta = (unsigned)d0 | ((unsigned)axis << 12) | (g.p1d0 != fd0 ? 1u << 13 : 0u) |
+                                          (g.p0d0 != fd0 ? 1u << 14 : 0u);
+                    key = (unsigned)((bf.fn * 3 + e) * 2 + axis);
+                    if ((steep_mask >> t) & 1u) {   // out-sweep of a steep task: the reference's own ownership test
+                        const int own = axis == 0 ? __ldg(face_index + (long)d1_in * is + d0)
+                                                  : __ldg(face_index + (long)d0 * is + d1_in);
+                        if (own == bf.fn) {
+                            const int lim = g.dir > 0 ? is - 1 : 0;
+                            ra_out = min(d1_out, lim); rc_out = max(d1_out, lim);
+                            meta_out = meta;
+                            todo_out = runs_in_sweep(S, lN, d0, ra_out, rc_out, false, meta_out, rl_out);
+                        }
                     }
+                    if (boundary) {
+                        // in-sweep: from the in-pixel to the opposite edge of the triangle; most find nothing to sweep
+                        const uint32_t *cov = axis == 0 ? cov_col : cov_row;   // coverage words of line d0 along d1
+                        const bool alpha_out = (__ldg(cov + (long)d0 * W + (d1_out >> 5)) >> (d1_out & 31)) & 1u;
+                        const int ls = alpha_out ? lN : lN + 1;
+                        if ((__ldg(S.run_info + ls * is + d0) & 15u) != 0u) {
+                            float c2;
+                            if ((fd0 - g.p0d0) * (fd0 - g.p2d0) < 0.f) c2 = g.s02 * (fd0 - g.p0d0) + g.p0d1;
+                            else c2 = g.s21 * (fd0 - g.p2d0) + g.p2d1;
+                            const int lim = __float2int_rz(g.dir > 0 ? ceilf(c2) : floorf(c2));
+                            ra_in = max(min(d1_in, lim), 0); rc_in = min(max(d1_in, lim), is - 1);
+                            if (ra_in <= rc_in) {
+                                // an in-sweep can straddle its crossing: by a pixel when the triangle is thinner than a
+                                // pixel there (eval_item copes with NEAR_N - 1 pixels on the near side), by many when
+                                // its far end is extrapolated (irregular faces): the closed form assumes one side, such
+                                // a sweep walks the bit line
+                                const bool walk = (float)ra_in < x - (float)(NEAR_N - 1) && (float)rc_in > x;
+                                meta_in = meta | (alpha_out ? 0u : META_PLANE);
+                                todo_in = runs_in_sweep(S, ls, d0, ra_in, rc_in, walk, meta_in, rl_in);
+                            }
+                        }
+                    }
+                    if (todo_in | todo_out) { c0 = __fdividef(g.ka, g.p1d0 - fd0); c1 = __fdividef(g.ka, fd0 - g.p0d0); }
                 }
-                if (!boundary) continue;
-                // in-sweep: from the in-pixel to the opposite edge of the triangle
-                const bool alpha_out = (__ldg(cov + (long)d0 * W + (d1_out >> 5)) >> (d1_out & 31)) & 1u;
-                const int ls = alpha_out ? lN : lP;
-                if ((__ldg(S.run_info + ls * is + d0) & 15u) == 0u) continue;
-                float c2;
-                if ((fd0 - g.p0d0) * (fd0 - g.p2d0) < 0.f) c2 = g.s02 * (fd0 - g.p0d0) + g.p0d1;
-                else c2 = g.s21 * (fd0 - g.p2d0) + g.p2d1;
-                const int lim = __float2int_rz(g.dir > 0 ? ceilf(c2) : floorf(c2));
-                const int ra = max(min(d1_in, lim), 0), rc = min(max(d1_in, lim), is - 1);
-                if (ra > rc) continue;
-                // an in-sweep can straddle its crossing: by a pixel when the triangle is thinner than a pixel there
-                // (eval_item copes with NEAR_N - 1 pixels on the near side), by many when its far end is
-                // extrapolated (irregular faces): the closed form assumes one side, such a sweep walks the bit line
-                const bool walk = (float)ra < x - (float)(NEAR_N - 1) && (float)rc > x;
-                sweep_line(S, ls, d0, ra, rc, x, c0, c1, has0, has1, walk, acc0, acc1);
             }
-            // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
-            if (acc0 != 0.f) atomicAdd(grad_ndc + (long)g.vid0 * 3 + (1 - axis), acc0);
-            if (acc1 != 0.f) atomicAdd(grad_ndc + (long)g.vid1 * 3 + (1 - axis), acc1);
+            while (__any_sync(FULL, todo_in != 0u)) {
+                push_round(iq, head, count, todo_in, rl_in, ra_in, rc_in, x, c0, c1, key, meta_in, lane);
+                if (count >= 32) drain_items(iq, head, count, 32, S, brecs, F, grad_ndc, lane);
+            }
+            while (__any_sync(FULL, todo_out != 0u)) {
+                push_round(iq, head, count, todo_out, rl_out, ra_out, rc_out, x, c0, c1, key, meta_out, lane);
+                if (count >= 32) drain_items(iq, head, count, 32, S, brecs, F, grad_ndc, lane);
+            }
         }
-        return;
     }
+    if (count > 0) drain_items(iq, head, count, count, S, brecs, F, grad_ndc, lane);
+}
 
-    // ======================================================================= role A: out-sweeps from the pixels
-    const int tile = blockIdx.x - n_face_ctas;
+// @region pix_prologue
+// ------------------------------------------------------------------ pixel side: out-sweeps
+#ifndef HM_BWD_MINB
+#define HM_BWD_MINB 4
+#endif
+__global__ void __launch_bounds__(NTHREADS, HM_BWD_MINB)
+raster_bwd_kernel(const BwdRec *__restrict__ brecs, int F, int V, int is, int aa, float eps,
+                  const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
+                  const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ m_row,
+                  const uint32_t *__restrict__ m_col, const uint2 *__restrict__ runs,
+                  const uint32_t *__restrict__ run_info, float *__restrict__ grad_ndc) {
+    __shared__ __align__(16) int fi[(TILE + 2) * FIS];     // face_index tile, one-pixel halo
+    __shared__ unsigned short cq[NWARPS][CQCAP];           // candidates (span ends)
+    __shared__ uint32_t ext_row[TILE], ext_col[TILE];      // extent of the missing-coverage list per line
+    __shared__ ItemQueue iqs[NWARPS];                      // (crossing, run) items
+    const int b = blockIdx.y;
+    const int W = is / 32;
     const int tiles_x = is / TILE;
-    const int tx0 = (tile % tiles_x) * TILE, ty0 = (tile / tiles_x) * TILE;
+    const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
     // ---- nothing to do when the tile is empty or no line through it has missing coverage
     {
         bool any_cov = false, any_miss = false;
         if (threadIdx.x < 2 * TILE) {
             const int r = threadIdx.x >> 1, w = threadIdx.x & 1;
-            any_cov = __ldg(cov_row + (long)(ty0 + r) * W + (tx0 >> 5) + w) != 0u;
+            any_cov = __ldg(cov_row + ((long)b * is + ty0 + r) * W + (tx0 >> 5) + w) != 0u;
         }
         if (threadIdx.x < TILE) {
-            const uint32_t er = __ldg(S.run_info + 0 * is + ty0 + threadIdx.x), ec = __ldg(S.run_info + 2 * is + tx0 + threadIdx.x);
+            const uint32_t *ri = run_info + (long)b * 4 * is;
+            const uint32_t er = __ldg(ri + ty0 + threadIdx.x), ec = __ldg(ri + 2 * is + tx0 + threadIdx.x);
             ext_row[threadIdx.x] = (er & 15u) ? er : 0x0000fff0u;   // empty list: lo = 4095, hi = 0
             ext_col[threadIdx.x] = (ec & 15u) ? ec : 0x0000fff0u;
             any_miss = ((er | ec) & 15u) != 0u;
@@ -1200,82 +1372,36 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ 
         const int miss_any = __syncthreads_or(any_miss);
         if (!cov_any || !miss_any) return;
     }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    brecs += (long)b * F;
+    grad_ndc += (long)b * V * 3;
+    face_index += (long)b * is * is;
+    const SweepSrc S = sweep_src(b, is, aa, eps, grad_alpha, m_row, m_col, runs, run_info);
+// @region pix_load
     // ---- face_index tile with a one-pixel halo (-2 outside the image: never equal to an owner)
     for (int i = threadIdx.x; i < TILE * TILE / 4; i += NTHREADS) {
         const int r = i / (TILE / 4), c4 = i % (TILE / 4);
         const int4 v = __ldg(reinterpret_cast<const int4 *>(face_index + (long)(ty0 + r) * is + tx0) + c4);
-        int *dst = fi + (r + 1) * FIS + 1 + 4 * c4;
-        dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+        *reinterpret_cast<int4 *>(fi + (r + 1) * FIS + FIX0 + 4 * c4) = v;
     }
     {
-        const int t = threadIdx.x;   // 4 x 66 halo pixels: rows above / below, columns left / right
-        const int side = t >> 6, k = t & 63;
+        const int side = threadIdx.x >> 6, k = threadIdx.x & 63;   // rows above / below, columns left / right
         int yy, xx;
         if (side == 0) { yy = -1; xx = k; } else if (side == 1) { yy = TILE; xx = k; }
         else if (side == 2) { yy = k; xx = -1; } else { yy = k; xx = TILE; }
         const int gy = ty0 + yy, gx = tx0 + xx;
-        fi[(yy + 1) * FIS + xx + 1] = (gy >= 0 && gy < is && gx >= 0 && gx < is) ? __ldg(face_index + (long)gy * is + gx) : -2;
-        if (t < 4) fi[(t & 1 ? TILE + 1 : 0) * FIS + (t & 2 ? TILE + 1 : 0)] = -2;   // corners (never read as neighbours)
+        fi[(yy + 1) * FIS + FIX0 + xx] = ((unsigned)gy < (unsigned)is && (unsigned)gx < (unsigned)is)
+                                            ? __ldg(face_index + (long)gy * is + gx) : -2;
     }
     __syncthreads();
 
     unsigned short *q = cq[warp];
     ItemQueue &iq = iqs[warp];
-    int qn = 0, ni = 0;   // queued candidates, queued items
+    int qn = 0, head = 0, count = 0;   // queued candidates; ring of queued items
 
-    // Evaluates the first `n` (<= 32) queued items, one per lane; items of one (face, edge, axis) task met in the
-    // batch are merged (match.any) and leave as one atomicAdd per vertex slot. Then the rest of the queue moves up.
-    auto drain = [&](int n) {
-        unsigned key = 0x80000000u | lane;
-        float a0 = 0.f, a1 = 0.f;
-        if (lane < n) {
-            const unsigned meta = iq.meta[lane], rng = iq.range[lane];
-            const int d0 = meta & 0xfffu, axis = (meta >> 12) & 1u;
-            const bool has0 = (meta >> 13) & 1u, has1 = (meta >> 14) & 1u;
-            const int ra = rng & 0xffffu, rc = rng >> 16;
-            key = iq.key[lane];
-            if ((meta >> 15) & 1u) {   // run list overflowed: walk the bit line
-                const uint32_t *line = (axis == 0 ? S.m_col : S.m_row) + (long)d0 * W;
-                sweep_bits(line, ra, rc, axis, d0, iq.x[lane], iq.c0[lane], iq.c1[lane], has0, has1, S.ctx, a0, a1);
-            } else {
-                eval_item(iq.x[lane], iq.c0[lane], iq.c1[lane], iq.G[lane], ra, rc, has0, has1, S.inv_is2, eps, a0, a1);
-            }
-        }
-        const unsigned peers = __match_any_sync(FULL, key);
-        const int leader = __ffs(peers) - 1;
-        unsigned others = lane == leader ? peers & ~(1u << lane) : 0u;
-        const unsigned rounds = __reduce_max_sync(FULL, (unsigned)__popc(others));
-        for (unsigned r = 0; r < rounds; ++r) {
-            const int src = others ? __ffs(others) - 1 : lane;
-            const float t0 = __shfl_sync(FULL, a0, src), t1 = __shfl_sync(FULL, a1, src);
-            if (others) { a0 += t0; a1 += t1; others &= others - 1; }
-        }
-        if (lane < n && lane == leader && (a0 != 0.f || a1 != 0.f)) {
-            // key = (owner * 3 + edge) * 2 + axis: the two vertices of the edge come from the owner's record
-            const int own = (int)(key / 6u), e = (int)((key >> 1) % 3u), axis = (int)(key & 1u);
-            const int4 q3 = __ldg(reinterpret_cast<const int4 *>(brecs + (own >= F ? own - F : own)) + 3);
-            const bool rev = (q3.w & BWD_FN_MASK) != own;   // the reversed copy of a both-windings face
-            const int v0 = rev ? q3.z : q3.x, v1 = q3.y, v2 = rev ? q3.x : q3.z;
-            const int vid0 = e == 0 ? v0 : e == 1 ? v1 : v2, vid1 = e == 0 ? v1 : e == 1 ? v2 : v0;
-            if (a0 != 0.f) atomicAdd(grad_ndc + (long)vid0 * 3 + (1 - axis), a0);
-            if (a1 != 0.f) atomicAdd(grad_ndc + (long)vid1 * 3 + (1 - axis), a1);
-        }
-        const int rem = ni - n;   // > 0 only when n == 32
-        float mx = 0.f, mc0 = 0.f, mc1 = 0.f, mg = 0.f;
-        unsigned mr = 0, mk = 0, mm = 0;
-        if (lane < rem) {
-            mx = iq.x[32 + lane]; mc0 = iq.c0[32 + lane]; mc1 = iq.c1[32 + lane]; mg = iq.G[32 + lane];
-            mr = iq.range[32 + lane]; mk = iq.key[32 + lane]; mm = iq.meta[32 + lane];
-        }
-        __syncwarp();
-        if (lane < rem) {
-            iq.x[lane] = mx; iq.c0[lane] = mc0; iq.c1[lane] = mc1; iq.G[lane] = mg;
-            iq.range[lane] = mr; iq.key[lane] = mk; iq.meta[lane] = mm;
-        }
-        ni = max(rem, 0);
-        __syncwarp();
-    };
-
+// @region pix_process
     // Turns `n` (<= 32) queued candidates, one per lane, into (crossing, run) items.
     auto process = [&](int n) {
         bool matched = false;
@@ -1284,23 +1410,41 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ 
         int ra = 0, rc = 0;
         if (lane < n) {
             const unsigned c = q[lane];
-            const int xl = c & 63, yl = (c >> 6) & 63, axis = (c >> 12) & 1, dir = (c >> 13) & 1 ? 1 : -1;
-            const int own = fi[(yl + 1) * FIS + xl + 1];
-            BwdFace bf = load_bwd_face(brecs + (own >= F ? own - F : own));
-            if (bf.fn != own && bf.both && bf.fn + F == own) reverse_bwd_face(bf, F);
-            if (bf.fn == own) {
-                const int d0 = axis == 0 ? tx0 + xl : ty0 + yl, q0 = axis == 0 ? ty0 + yl : tx0 + xl;
+            const int xl = c & 63, yl = (c >> 6) & 63, axis = (c >> 12) & 1, dirbit = (c >> 13) & 1;
+            const int dir = dirbit ? 1 : -1;
+            const int own = fi[(yl + 1) * FIS + FIX0 + xl];
+            const BwdRec *rp = brecs + (own >= F ? own - F : own);
+            // per-edge scan-line spans of this axis: d0_from | d0_to << 12 | dir > 0 << 24 | steep << 25
+            const uint4 s4 = __ldg(reinterpret_cast<const uint4 *>(rp) + 4);
+            const uint2 s5 = __ldg(reinterpret_cast<const uint2 *>(rp) + 10);
+            const int meta_fn = __ldg(reinterpret_cast<const int *>(rp) + 15);
+            const bool rev = (meta_fn & BWD_FN_MASK) != own;   // the reversed copy F + f of a both-windings face
+            unsigned sp[3] = {axis ? s4.y : s4.x, axis ? s4.w : s4.z, axis ? s5.y : s5.x};
+            if (rev) {   // edges 0 and 1 trade places and every edge is walked backwards
+                const unsigned t = sp[0]; sp[0] = sp[1]; sp[1] = t;
+                sp[0] ^= 1u << 24; sp[1] ^= 1u << 24; sp[2] ^= 1u << 24;
+            }
+            const int d0 = axis == 0 ? tx0 + xl : ty0 + yl, q0 = axis == 0 ? ty0 + yl : tx0 + xl;
+            unsigned edges = 0;
+#pragma unroll
+            for (int e = 0; e < 3; ++e) {
+                const int from = sp[e] & 0xfffu, to = (sp[e] >> 12) & 0xfffu;
+                if (((sp[e] >> 24) & 3u) == (unsigned)dirbit && d0 >= from && d0 <= to) edges |= 1u << e;   // dir, !steep
+            }
+            if (meta_fn >= 0 && edges && (!rev || ((meta_fn & BWD_BOTH) && (meta_fn & BWD_FN_MASK) + F == own))) {
+                BwdFace bf = load_bwd_face(rp);
+                if (rev) reverse_bwd_face(bf, F);
                 const float fd0 = (float)d0;
                 // the pixel one step back along the sweep (in the tile or its halo)
-                const int prev_own = axis == 0 ? fi[(yl + 1 - dir) * FIS + xl + 1] : fi[(yl + 1) * FIS + xl + 1 - dir];
-#pragma unroll
-                for (int e = 0; e < 3; ++e) {
+                const int prev_own = axis == 0 ? fi[(yl + 1 - dir) * FIS + FIX0 + xl] : fi[(yl + 1) * FIS + FIX0 + xl - dir];
+                while (edges) {
+                    const int e = __ffs(edges) - 1;
+                    edges &= edges - 1;
                     const TaskGeom g = task_geom(bf, e, axis, is);
-                    if (g.dir != dir || d0 < g.d0_from || d0 > g.d0_to || !(fabsf(g.slope) <= SMAX)) continue;
                     const float xe = g.slope * (fd0 - g.p0d0) + g.p0d1;
                     const int d1_in = __float2int_rz(dir > 0 ? floorf(xe) : ceilf(xe));
                     const int d1_out = d1_in + dir;
-                    if (d1_in < 0 || d1_in >= is || d1_out < 0 || d1_out >= is) continue;
+                    if ((unsigned)d1_in >= (unsigned)is || (unsigned)d1_out >= (unsigned)is) continue;
                     if (d1_in != q0 && !(d1_in == q0 - dir && prev_own == own)) continue;
                     const bool has0 = g.p1d0 != fd0, has1 = g.p0d0 != fd0;
                     const float e0 = __fdividef(g.ka, g.p1d0 - fd0), e1 = __fdividef(g.ka, fd0 - g.p0d0);
@@ -1321,109 +1465,84 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ 
                 }
             }
         }
-        // ---- runs of the missing-coverage list inside the sweep: bit r = run r (bit 0 alone + walk flag on overflow)
+// @region pix_items
+        // ---- runs of the missing-coverage list inside the sweep; one item per lane and round, 32 evaluated at a time
         unsigned todo = 0;
         const uint2 *rl = S.runs;
-        if (matched) {
-            const int ls = (meta >> 12) & 1u ? 0 : 2, d0 = meta & 0xfffu;
-            const uint32_t info = __ldg(S.run_info + ls * is + d0);
-            const unsigned cnt = info & 15u;
-            const int lo = (info >> 4) & 0xfffu, hi = info >> 16;
-            if (cnt != 0u && rc >= lo && ra <= hi) {
-                rl += ((long)ls * is + d0) * RCAP;
-                if (cnt == RUN_OVERFLOW) {
-                    todo = 1u;
-                    meta |= 1u << 15;
-                    ra = max(ra, lo); rc = min(rc, hi);
-                } else {
-                    for (unsigned r = 0; r < cnt; ++r) {
-                        const unsigned se = __ldg(&rl[r].x);
-                        if (rc >= (int)(se & 0xffffu) && ra <= (int)(se >> 16)) todo |= 1u << r;
-                    }
-                }
-            }
-        }
-        // ---- one item per lane and round into the warp's queue; 32 queued items are evaluated at a time
+        if (matched) todo = runs_in_sweep(S, (meta >> 12) & 1u ? 0 : 2, meta & 0xfffu, ra, rc, false, meta, rl);
         while (__any_sync(FULL, todo != 0u)) {
-            const bool it = todo != 0u;
-            const unsigned m = __ballot_sync(FULL, it);
-            if (it) {
-                const int r = __ffs(todo) - 1;
-                todo &= todo - 1;
-                unsigned rng = (unsigned)ra | ((unsigned)rc << 16);
-                float G = 0.f;
-                if (!((meta >> 15) & 1u)) {
-                    const uint2 run = __ldg(rl + r);
-                    rng = (unsigned)max(ra, (int)(run.x & 0xffffu)) | ((unsigned)min(rc, (int)(run.x >> 16)) << 16);
-                    G = __uint_as_float(run.y);
-                }
-                const int pos = ni + __popc(m & lt_mask);
-                iq.x[pos] = x; iq.c0[pos] = c0; iq.c1[pos] = c1; iq.G[pos] = G;
-                iq.range[pos] = rng; iq.key[pos] = key; iq.meta[pos] = meta;
-            }
-            ni += __popc(m);
-            __syncwarp();
-            if (ni >= 32) drain(32);
+            push_round(iq, head, count, todo, rl, ra, rc, x, c0, c1, key, meta, lane);
+            if (count >= 32) drain_items(iq, head, count, 32, S, brecs, F, grad_ndc, lane);
         }
     };
 
-    // ---- each warp scans 8 rows of the tile; lane = column (two halves)
-    uint32_t ecol[2];
-    ecol[0] = ext_col[lane]; ecol[1] = ext_col[lane + 32];
-    for (int rr = 0; rr < TILE / NWARPS; ++rr) {
-        const int yl = warp * (TILE / NWARPS) + rr;
-        const int Y = ty0 + yl;
-        const uint32_t er = ext_row[yl];
-        const int row_lo = (er >> 4) & 0xfff, row_hi = er >> 16;
-        const int *rowp = fi + (yl + 1) * FIS + 1;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const int xl = lane + 32 * half, X = tx0 + xl;
-            const int c = rowp[xl];
-            const bool cov = c >= 0;
-            if (!__any_sync(FULL, cov)) continue;
-            const int col_lo = (ecol[half] >> 4) & 0xfff, col_hi = ecol[half] >> 16;
-            // span ends with missing coverage beyond them: axis 1 sweeps along x (row lists), axis 0 along y
-            const bool cand[4] = {cov && rowp[xl + 1] != c && row_hi > X,        // axis 1, dir +1
-                                  cov && rowp[xl - 1] != c && row_lo < X,        // axis 1, dir -1
-                                  cov && rowp[xl + FIS] != c && col_hi > Y,      // axis 0, dir +1
-                                  cov && rowp[xl - FIS] != c && col_lo < Y};     // axis 0, dir -1
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const unsigned m = __ballot_sync(FULL, cand[k]);
-                if (cand[k]) {
-                    const int axis = k < 2 ? 1 : 0, dirbit = (k & 1) ? 0 : 1;
-                    q[qn + __popc(m & lt_mask)] = (unsigned short)(xl | (yl << 6) | (axis << 12) | (dirbit << 13));
+// @region pix_scan
+    // ---- each warp scans 8 rows of the tile, lane = column (two halves); the three rows around a pixel stay in registers
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+        const int xl = lane + 32 * half, X = tx0 + xl;
+        const uint32_t ec = ext_col[xl];
+        const int col_lo = (ec >> 4) & 0xfff, col_hi = ec >> 16;
+        const int *colp = fi + (warp * (TILE / NWARPS)) * FIS + FIX0 + xl;   // row above the warp's first row
+        int up = colp[0], cur = colp[FIS];
+#pragma unroll 1
+        for (int rr = 0; rr < TILE / NWARPS; ++rr) {
+            const int yl = warp * (TILE / NWARPS) + rr, Y = ty0 + yl;
+            const int *p = colp + (rr + 1) * FIS;
+            const int down = p[FIS];
+            const bool cov = cur >= 0;
+            if (__any_sync(FULL, cov)) {
+                const uint32_t er = ext_row[yl];
+                const int row_lo = (er >> 4) & 0xfff, row_hi = er >> 16;
+                // span ends with missing coverage beyond them: axis 1 sweeps along x (row lists), axis 0 along y
+                const bool c0 = cov && p[1] != cur && row_hi > X;     // axis 1, dir +1
+                const bool c1 = cov && p[-1] != cur && row_lo < X;    // axis 1, dir -1
+                const bool c2 = cov && down != cur && col_hi > Y;     // axis 0, dir +1
+                const bool c3 = cov && up != cur && col_lo < Y;       // axis 0, dir -1
+                // exclusive prefix of the per-lane candidate count (0..4) from three ballots of its binary digits
+                const int mine = (int)c0 + (int)c1 + (int)c2 + (int)c3;
+                const unsigned b0 = __ballot_sync(FULL, mine & 1), b1 = __ballot_sync(FULL, mine & 2),
+                               b2 = __ballot_sync(FULL, mine & 4);
+                if (b0 | b1 | b2) {
+                    int at = qn + __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+                    const unsigned code = (unsigned)(xl | (yl << 6));
+                    if (c0) q[at++] = (unsigned short)(code | (1u << 12) | (1u << 13));
+                    if (c1) q[at++] = (unsigned short)(code | (1u << 12));
+                    if (c2) q[at++] = (unsigned short)(code | (1u << 13));
+                    if (c3) q[at] = (unsigned short)code;
+                    qn += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
+                    __syncwarp();
+                    int qh = 0;
+                    while (qn - qh >= 32) {
+                        if (qh) {   // (process reads q[lane])
+                            const unsigned short v = q[qh + lane];
+                            __syncwarp();
+                            q[lane] = v;
+                            __syncwarp();
+                        }
+                        process(32);
+                        qh += 32;
+                    }
+                    if (qh) {   // move the leftover to the front
+                        const int rem = qn - qh;
+                        unsigned short v = 0;
+                        if (lane < rem) v = q[qh + lane];
+                        __syncwarp();
+                        if (lane < rem) q[lane] = v;
+                        qn = rem;
+                        __syncwarp();
+                    }
                 }
-                qn += __popc(m);
             }
-        }
-        __syncwarp();
-        int head = 0;
-        while (qn - head >= 32) {
-            if (head) {   // (process reads q[lane])
-                const unsigned short v = q[head + lane];
-                __syncwarp();
-                q[lane] = v;
-                __syncwarp();
-            }
-            process(32);
-            head += 32;
-        }
-        if (head) {   // move the leftover to the front
-            const int rem = qn - head;
-            unsigned short v = 0;
-            if (lane < rem) v = q[head + lane];
-            __syncwarp();
-            if (lane < rem) q[lane] = v;
-            qn = rem;
-            __syncwarp();
+            up = cur;
+            cur = down;
         }
     }
     if (qn > 0) process(qn);
-    if (ni > 0) drain(ni);
+    if (count > 0) drain_items(iq, head, count, count, S, brecs, F, grad_ndc, lane);
 }
 
+// @region after
 // ------------------------------------------------------------------------------------------ RGB / depth (visualisation)
 // Forward of nr.rasterize_rgbad for texture_size 1 on top of the face_index map: a covered raster sample takes the
 // lit colour of its face (doubled numbering: f or F + f) and the reference's interpolated depth (same arithmetic
@@ -1616,12 +1735,16 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
                "hm_raster_sil_bwd: null pointer");
     HM_REQUIRE(V > 0, "hm_raster_sil_bwd: bad sizes");
     HM_UNSUPPORTED(is > 1024, "hm_raster_sil_bwd: raster size %d > 1024 is not supported", is);
-    const int n_face_ctas = (F + BFACES - 1) / BFACES;
-    dim3 grid(n_face_ctas + (is / TILE) * (is / TILE), B);
-    raster_bwd_kernel<<<grid, NTHREADS, 0, hm_stream(stream)>>>(
-        reinterpret_cast<const BwdRec *>(static_cast<const FaceRec *>(records) + (long)B * F),
-        static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, n_face_ctas, face_index, grad_alpha, cov_row,
+    const BwdRec *brecs = reinterpret_cast<const BwdRec *>(static_cast<const FaceRec *>(records) + (long)B * F);
+    dim3 grid_f((F + BFACES - 1) / BFACES, B);
+    raster_bwd_face_kernel<<<grid_f, NTHREADS, 0, hm_stream(stream)>>>(
+        brecs, static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, face_index, grad_alpha, cov_row,
         cov_col, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
+    HM_CHECK_LAUNCH("hm_raster_sil_bwd(faces)");
+    dim3 grid((is / TILE) * (is / TILE), B);
+    raster_bwd_kernel<<<grid, NTHREADS, 0, hm_stream(stream)>>>(
+        brecs, F, V, is, anti_aliasing, eps, face_index, grad_alpha, cov_row, m_row, m_col,
+        static_cast<const uint2 *>(runs), run_counts, grad_ndc);
     HM_CHECK_LAUNCH("hm_raster_sil_bwd");
     return HM_OK;
 }

@@ -66,7 +66,7 @@ class RasterBuffers:
         self.B, self.V, self.F, self.image_size, self.aa = B, V, F, image_size, bool(anti_aliasing)
         S = image_size * 2 if anti_aliasing else image_size
         self.S = S
-        self.records = torch.empty(B * F * 192, dtype=torch.uint8, device=device)   # HM_FACE_RECORD_BYTES
+        self.records = torch.empty(B * F * 224, dtype=torch.uint8, device=device)   # HM_FACE_RECORD_BYTES
         self.bboxes = torch.empty(B * F * 8, dtype=torch.uint8, device=device)
         self.face_index = torch.empty(B, S, S, dtype=torch.int32, device=device)
         self.alpha = torch.empty(B, image_size, image_size, dtype=torch.float32, device=device)

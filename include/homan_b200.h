@@ -53,10 +53,10 @@ int hm_project_bwd(const float *verts, const float *K, int K_batch, const float 
  * (z-buffered nearest front face, vertical flip, 2x2 average pool when anti-aliasing) and its
  * hand-crafted backward (backward_pixel_map).  image_size is the OUTPUT size R; the raster size is
  * S = 2R with anti-aliasing.  S must be a multiple of 64. */
-#define HM_FACE_RECORD_BYTES 192
+#define HM_FACE_RECORD_BYTES 224
 #define HM_FACE_BBOX_BYTES 8
 /* ndc [B,V,3], faces [faces_batch,F,3] -> records (B*F*HM_FACE_RECORD_BYTES bytes: a plane of 128-byte forward
- * records followed by a plane of 64-byte backward records) + bboxes [B,F,8 B] (front-facing winding of every face;
+ * records followed by a plane of 96-byte backward records) + bboxes [B,F,8 B] (front-facing winding of every face;
  * never materialises the doubled face array). */
 int hm_raster_setup(const float *ndc, const int32_t *faces, int faces_batch, int B, int V, int F,
                     int image_size, int anti_aliasing, int fill_back, void *records, void *bboxes,
