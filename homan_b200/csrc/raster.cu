@@ -898,7 +898,7 @@ __device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, 
 
 // @region sweep_bits
 // Bit-line walk for lines whose run list overflowed: visits the set bits of `line` in [a, c].
-__device__ __forceinline__ void sweep_bits(const uint32_t *line, int a, int c, int axis, int d0, float d1_cross,
+__device__ __noinline__ void sweep_bits(const uint32_t *line, int a, int c, int axis, int d0, float d1_cross,
                                            float c0, float c1, bool has0, bool has1, const BwdCtx &ctx, float &acc0,
                                            float &acc1) {
     if (a > c) return;
@@ -1083,6 +1083,7 @@ __device__ __noinline__ void sweep_line(const SweepSrc &S, int ls, int d0, int r
 // Queues one item per lane and round (bit r of `todo` = run r of the line's list overlaps the sweep [ra, rc]; with
 // META_WALK the single item is the whole sweep, walked on the bit line). The caller drains when count >= 32.
 constexpr unsigned META_WALK = 1u << 15, META_PLANE = 1u << 16;
+template <bool SH>
 __device__ __forceinline__ void push_round(ItemQueue &iq, int head, int &count, unsigned &todo, const uint2 *rl, int ra,
                                            int rc, float x, float c0, float c1, unsigned key, unsigned meta, int lane) {
     const bool it = todo != 0u;
@@ -1093,7 +1094,7 @@ __device__ __forceinline__ void push_round(ItemQueue &iq, int head, int &count, 
         unsigned rng = (unsigned)ra | ((unsigned)rc << 16);
         float G = 0.f;
         if (!(meta & META_WALK)) {
-            const uint2 run = __ldg(rl + r);
+            const uint2 run = SH ? rl[r] : __ldg(rl + r);
             rng = (unsigned)max(ra, (int)(run.x & 0xffffu)) | ((unsigned)min(rc, (int)(run.x >> 16)) << 16);
             G = __uint_as_float(run.y);
         }
@@ -1105,15 +1106,14 @@ __device__ __forceinline__ void push_round(ItemQueue &iq, int head, int &count, 
     __syncwarp();
 }
 
-// Bits of the runs of list `ls`, line d0 that have pixels inside [ra, rc] (clipped to the list's extent); 1 + META_WALK
-// when the run list overflowed or `walk` is set. rl receives the run list.
-__device__ __forceinline__ unsigned runs_in_sweep(const SweepSrc &S, int ls, int d0, int &ra, int &rc, bool walk,
-                                                  unsigned &meta, const uint2 *&rl) {
-    const uint32_t info = __ldg(S.run_info + ls * S.is + d0);
+// Bits of the runs of a line's list (`info` = its run_counts word, rl = its runs, in shared or global memory) that have
+// pixels inside [ra, rc] (clipped to the list's extent); 1 + META_WALK when the list overflowed or `walk` is set.
+template <bool SH>
+__device__ __forceinline__ unsigned runs_in_sweep_of(uint32_t info, const uint2 *rl, int &ra, int &rc, bool walk,
+                                                     unsigned &meta) {
     const unsigned cnt = info & 15u;
     const int lo = (info >> 4) & 0xfffu, hi = info >> 16;
     if (cnt == 0u || rc < lo || ra > hi) return 0u;
-    rl = S.runs + ((long)ls * S.is + d0) * RCAP;
     if (cnt == RUN_OVERFLOW || walk) {
         meta |= META_WALK;
         ra = max(ra, lo); rc = min(rc, hi);
@@ -1121,17 +1121,27 @@ __device__ __forceinline__ unsigned runs_in_sweep(const SweepSrc &S, int ls, int
     }
     unsigned todo = 0;
     for (unsigned r = 0; r < cnt; ++r) {
-        const unsigned se = __ldg(&rl[r].x);
+        const unsigned se = SH ? rl[r].x : __ldg(&rl[r].x);
         if (rc >= (int)(se & 0xffffu) && ra <= (int)(se >> 16)) todo |= 1u << r;
     }
     return todo;
 }
+// The same for list `ls`, line d0 of the image (global memory); rl receives the run list.
+__device__ __forceinline__ unsigned runs_in_sweep(const SweepSrc &S, int ls, int d0, int &ra, int &rc, bool walk,
+                                                  unsigned &meta, const uint2 *&rl) {
+    rl = S.runs + ((long)ls * S.is + d0) * RCAP;
+    return runs_in_sweep_of<false>(__ldg(S.run_info + ls * S.is + d0), rl, ra, rc, walk, meta);
+}
 
 // Evaluates the first `n` (<= 32) queued items, one per lane. Items of one (face, edge, axis) task met in the batch are
 // summed inside the warp (match.any + pointer jumping over the peers) and leave as one atomicAdd per vertex slot.
-__device__ __forceinline__ void drain_items(ItemQueue &iq, int &head, int &count, int n, const SweepSrc &S,
-                                            const BwdRec *brecs, int F, float *grad_ndc, int lane) {
+// Not inlined: one copy of the evaluation code per kernel (the backward is bound by instruction fetch otherwise); the
+// caller advances head / count by n.
+__device__ __noinline__ void drain_items(const ItemQueue &iq, int head, int n, const SweepSrc *Sp, const BwdRec *brecs,
+                                         int F, float *grad_ndc) {
     const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const SweepSrc &S = *Sp;
     unsigned key = 0x80000000u | lane;
     float a0 = 0.f, a1 = 0.f;
     if (lane < n) {
@@ -1171,26 +1181,28 @@ __device__ __forceinline__ void drain_items(ItemQueue &iq, int &head, int &count
         if (a0 != 0.f) atomicAdd(grad_ndc + (long)vid0 * 3 + (1 - axis), a0);
         if (a1 != 0.f) atomicAdd(grad_ndc + (long)vid1 * 3 + (1 - axis), a1);
     }
-    head = (head + n) & (IQCAP - 1);
-    count -= n;
     __syncwarp();
 }
+#define DRAIN(n_)                                                         \
+    do {                                                                  \
+        const int dn__ = (n_);                                            \
+        drain_items(iq, head, dn__, &S, brecs, F, grad_ndc);              \
+        head = (head + dn__) & (IQCAP - 1);                               \
+        count -= dn__;                                                    \
+    } while (0)
 
 // @region face_setup
 // ------------------------------------------------------------------ face side: in-sweeps and steep tasks
 // Thread per face: is it at the silhouette (an uncovered pixel in its pixel bounding box) or irregular, which of its
 // tasks are steep. Then warp per listed face: the scan-lines of its six (edge, axis) tasks are flattened over the
 // lanes, every lane tests one crossing, contributing crossings queue (crossing, run) items.
-__global__ void __launch_bounds__(NTHREADS)
-raster_bwd_face_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
-                       float eps, const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
-                       const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ cov_col,
-                       const uint32_t *__restrict__ m_row, const uint32_t *__restrict__ m_col,
-                       const uint2 *__restrict__ runs, const uint32_t *__restrict__ run_info,
-                       float *__restrict__ grad_ndc) {
-    __shared__ unsigned flist[2 * BFACES];   // face | copy << 8 | silhouette << 9 | steep tasks << 10
-    __shared__ int n_list;
-    __shared__ ItemQueue iqs[NWARPS];
+__device__ __forceinline__ void
+raster_bwd_face_role(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
+                     float eps, const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
+                     const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ cov_col,
+                     const uint32_t *__restrict__ m_row, const uint32_t *__restrict__ m_col,
+                     const uint2 *__restrict__ runs, const uint32_t *__restrict__ run_info,
+                     float *__restrict__ grad_ndc, unsigned *flist, int &n_list, ItemQueue *iqs, SweepSrc &S) {
     const int b = blockIdx.y;
     const int W = is / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1201,8 +1213,10 @@ raster_bwd_face_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restri
     face_index += (long)b * is * is;
     cov_row += (long)b * is * W;
     cov_col += (long)b * is * W;
-    const SweepSrc S = sweep_src(b, is, aa, eps, grad_alpha, m_row, m_col, runs, run_info);
-    if (threadIdx.x == 0) n_list = 0;
+    if (threadIdx.x == 0) {
+        S = sweep_src(b, is, aa, eps, grad_alpha, m_row, m_col, runs, run_info);
+        n_list = 0;
+    }
     __syncthreads();
     {
         const int f = blockIdx.x * BFACES + threadIdx.x;
@@ -1323,37 +1337,32 @@ raster_bwd_face_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restri
                 }
             }
             while (__any_sync(FULL, todo_in != 0u)) {
-                push_round(iq, head, count, todo_in, rl_in, ra_in, rc_in, x, c0, c1, key, meta_in, lane);
-                if (count >= 32) drain_items(iq, head, count, 32, S, brecs, F, grad_ndc, lane);
+                push_round<false>(iq, head, count, todo_in, rl_in, ra_in, rc_in, x, c0, c1, key, meta_in, lane);
+                if (count >= 32) DRAIN(32);
             }
             while (__any_sync(FULL, todo_out != 0u)) {
-                push_round(iq, head, count, todo_out, rl_out, ra_out, rc_out, x, c0, c1, key, meta_out, lane);
-                if (count >= 32) drain_items(iq, head, count, 32, S, brecs, F, grad_ndc, lane);
+                push_round<false>(iq, head, count, todo_out, rl_out, ra_out, rc_out, x, c0, c1, key, meta_out, lane);
+                if (count >= 32) DRAIN(32);
             }
         }
     }
-    if (count > 0) drain_items(iq, head, count, count, S, brecs, F, grad_ndc, lane);
+    if (count > 0) DRAIN(count);
 }
 
 // @region pix_prologue
 // ------------------------------------------------------------------ pixel side: out-sweeps
-#ifndef HM_BWD_MINB
-#define HM_BWD_MINB 4
-#endif
-__global__ void __launch_bounds__(NTHREADS, HM_BWD_MINB)
-raster_bwd_kernel(const BwdRec *__restrict__ brecs, int F, int V, int is, int aa, float eps,
-                  const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
-                  const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ m_row,
-                  const uint32_t *__restrict__ m_col, const uint2 *__restrict__ runs,
-                  const uint32_t *__restrict__ run_info, float *__restrict__ grad_ndc) {
-    __shared__ __align__(16) int fi[(TILE + 2) * FIS];     // face_index tile, one-pixel halo
-    __shared__ unsigned short cq[NWARPS][CQCAP];           // candidates (span ends)
-    __shared__ uint32_t ext_row[TILE], ext_col[TILE];      // extent of the missing-coverage list per line
-    __shared__ ItemQueue iqs[NWARPS];                      // (crossing, run) items
+__device__ __forceinline__ void
+raster_bwd_tile_role(int tile, const BwdRec *__restrict__ brecs, int F, int V, int is, int aa, float eps,
+                     const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
+                     const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ m_row,
+                     const uint32_t *__restrict__ m_col, const uint2 *__restrict__ runs,
+                     const uint32_t *__restrict__ run_info, float *__restrict__ grad_ndc, int *fi,
+                     unsigned short (*cq)[CQCAP], uint32_t *ext_row, uint32_t *ext_col, ItemQueue *iqs, SweepSrc &S,
+                     uint2 *sruns, uint64_t *bar) {
     const int b = blockIdx.y;
     const int W = is / 32;
     const int tiles_x = is / TILE;
-    const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
+    const int tx0 = (tile % tiles_x) * TILE, ty0 = (tile / tiles_x) * TILE;
     // ---- nothing to do when the tile is empty or no line through it has missing coverage
     {
         bool any_cov = false, any_miss = false;
@@ -1378,7 +1387,15 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, int F, int V, int is, int aa
     brecs += (long)b * F;
     grad_ndc += (long)b * V * 3;
     face_index += (long)b * is * is;
-    const SweepSrc S = sweep_src(b, is, aa, eps, grad_alpha, m_row, m_col, runs, run_info);
+    if (threadIdx.x == 0) {   // (barrier below)
+        S = sweep_src(b, is, aa, eps, grad_alpha, m_row, m_col, runs, run_info);
+        // the missing-coverage run lists of the tile's 64 rows and 64 columns: two contiguous 4 KB blocks (TMA bulk copies)
+        mbar_init(bar, 1);
+        mbar_fence_init();
+        mbar_expect_tx(bar, (uint32_t)(2 * TILE * RCAP * sizeof(uint2)));
+        tma_bulk_g2s(sruns, runs + (((long)b * 4 + 0) * is + ty0) * RCAP, TILE * RCAP * sizeof(uint2), bar);
+        tma_bulk_g2s(sruns + TILE * RCAP, runs + (((long)b * 4 + 2) * is + tx0) * RCAP, TILE * RCAP * sizeof(uint2), bar);
+    }
 // @region pix_load
     // ---- face_index tile with a one-pixel halo (-2 outside the image: never equal to an owner)
     for (int i = threadIdx.x; i < TILE * TILE / 4; i += NTHREADS) {
@@ -1396,6 +1413,7 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, int F, int V, int is, int aa
                                             ? __ldg(face_index + (long)gy * is + gx) : -2;
     }
     __syncthreads();
+    mbar_wait(bar, 0);
 
     unsigned short *q = cq[warp];
     ItemQueue &iq = iqs[warp];
@@ -1468,78 +1486,125 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, int F, int V, int is, int aa
 // @region pix_items
         // ---- runs of the missing-coverage list inside the sweep; one item per lane and round, 32 evaluated at a time
         unsigned todo = 0;
-        const uint2 *rl = S.runs;
-        if (matched) todo = runs_in_sweep(S, (meta >> 12) & 1u ? 0 : 2, meta & 0xfffu, ra, rc, false, meta, rl);
+        const uint2 *rl = sruns;
+        if (matched) {   // (the tile's run lists and their info words were staged in shared memory)
+            const int axis = (meta >> 12) & 1u, l0 = (int)(meta & 0xfffu) - (axis ? ty0 : tx0);
+            rl = sruns + ((axis ? 0 : TILE) + l0) * RCAP;
+            todo = runs_in_sweep_of<true>(axis ? ext_row[l0] : ext_col[l0], rl, ra, rc, false, meta);
+        }
         while (__any_sync(FULL, todo != 0u)) {
-            push_round(iq, head, count, todo, rl, ra, rc, x, c0, c1, key, meta, lane);
-            if (count >= 32) drain_items(iq, head, count, 32, S, brecs, F, grad_ndc, lane);
+            push_round<true>(iq, head, count, todo, rl, ra, rc, x, c0, c1, key, meta, lane);
+            if (count >= 32) DRAIN(32);
         }
     };
 
 // @region pix_scan
-    // ---- each warp scans 8 rows of the tile, lane = column (two halves); the three rows around a pixel stay in registers
+    // ---- span ends: a warp takes two rows of the tile per step, a lane four consecutive pixels of one row (the rows
+    //      above and below and the two pixels beside them in registers): 16 flags per lane, queued with one prefix sum
+    {
+        const int x4 = (lane & 15) * 4;
+        const uint4 ec4 = *reinterpret_cast<const uint4 *>(ext_col + x4);
+        const unsigned ecol[4] = {ec4.x, ec4.y, ec4.z, ec4.w};
 #pragma unroll 1
-    for (int half = 0; half < 2; ++half) {
-        const int xl = lane + 32 * half, X = tx0 + xl;
-        const uint32_t ec = ext_col[xl];
-        const int col_lo = (ec >> 4) & 0xfff, col_hi = ec >> 16;
-        const int *colp = fi + (warp * (TILE / NWARPS)) * FIS + FIX0 + xl;   // row above the warp's first row
-        int up = colp[0], cur = colp[FIS];
-#pragma unroll 1
-        for (int rr = 0; rr < TILE / NWARPS; ++rr) {
-            const int yl = warp * (TILE / NWARPS) + rr, Y = ty0 + yl;
-            const int *p = colp + (rr + 1) * FIS;
-            const int down = p[FIS];
-            const bool cov = cur >= 0;
-            if (__any_sync(FULL, cov)) {
+        for (int it = 0; it <= TILE / NWARPS / 2; ++it) {
+            const bool flush = it == TILE / NWARPS / 2;   // extra step: the candidates left in the queue
+            const int yl = warp * (TILE / NWARPS) + 2 * min(it, TILE / NWARPS / 2 - 1) + (lane >> 4), Y = ty0 + yl;
+            const int *p = fi + (yl + 1) * FIS + FIX0 + x4;
+            const int4 c4 = *reinterpret_cast<const int4 *>(p);
+            const int cur[4] = {c4.x, c4.y, c4.z, c4.w};
+            unsigned mask = 0;
+            if (!flush && (c4.x & c4.y & c4.z & c4.w) >= 0) {   // some pixel of the four is covered (-1: all bits set)
+                const int4 u4 = *reinterpret_cast<const int4 *>(p - FIS), d4 = *reinterpret_cast<const int4 *>(p + FIS);
+                const int up[4] = {u4.x, u4.y, u4.z, u4.w}, down[4] = {d4.x, d4.y, d4.z, d4.w};
+                const int nb[6] = {p[-1], c4.x, c4.y, c4.z, c4.w, p[4]};
                 const uint32_t er = ext_row[yl];
                 const int row_lo = (er >> 4) & 0xfff, row_hi = er >> 16;
-                // span ends with missing coverage beyond them: axis 1 sweeps along x (row lists), axis 0 along y
-                const bool c0 = cov && p[1] != cur && row_hi > X;     // axis 1, dir +1
-                const bool c1 = cov && p[-1] != cur && row_lo < X;    // axis 1, dir -1
-                const bool c2 = cov && down != cur && col_hi > Y;     // axis 0, dir +1
-                const bool c3 = cov && up != cur && col_lo < Y;       // axis 0, dir -1
-                // exclusive prefix of the per-lane candidate count (0..4) from three ballots of its binary digits
-                const int mine = (int)c0 + (int)c1 + (int)c2 + (int)c3;
-                const unsigned b0 = __ballot_sync(FULL, mine & 1), b1 = __ballot_sync(FULL, mine & 2),
-                               b2 = __ballot_sync(FULL, mine & 4);
-                if (b0 | b1 | b2) {
-                    int at = qn + __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
-                    const unsigned code = (unsigned)(xl | (yl << 6));
-                    if (c0) q[at++] = (unsigned short)(code | (1u << 12) | (1u << 13));
-                    if (c1) q[at++] = (unsigned short)(code | (1u << 12));
-                    if (c2) q[at++] = (unsigned short)(code | (1u << 13));
-                    if (c3) q[at] = (unsigned short)code;
-                    qn += __popc(b0) + 2 * __popc(b1) + 4 * __popc(b2);
-                    __syncwarp();
-                    int qh = 0;
-                    while (qn - qh >= 32) {
-                        if (qh) {   // (process reads q[lane])
-                            const unsigned short v = q[qh + lane];
-                            __syncwarp();
-                            q[lane] = v;
-                            __syncwarp();
-                        }
-                        process(32);
-                        qh += 32;
-                    }
-                    if (qh) {   // move the leftover to the front
-                        const int rem = qn - qh;
-                        unsigned short v = 0;
-                        if (lane < rem) v = q[qh + lane];
-                        __syncwarp();
-                        if (lane < rem) q[lane] = v;
-                        qn = rem;
-                        __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int X = tx0 + x4 + j;
+                    const int col_lo = (ecol[j] >> 4) & 0xfff, col_hi = ecol[j] >> 16;
+                    if (cur[j] >= 0) {
+                        // span ends with missing coverage beyond them: axis 1 sweeps along x (row lists), axis 0 along y
+                        if (nb[j + 2] != cur[j] && row_hi > X) mask |= 1u << (4 * j);        // axis 1, dir +1
+                        if (nb[j] != cur[j] && row_lo < X) mask |= 2u << (4 * j);            // axis 1, dir -1
+                        if (down[j] != cur[j] && col_hi > Y) mask |= 4u << (4 * j);          // axis 0, dir +1
+                        if (up[j] != cur[j] && col_lo < Y) mask |= 8u << (4 * j);            // axis 0, dir -1
                     }
                 }
             }
-            up = cur;
-            cur = down;
+            if (flush || __any_sync(FULL, mask != 0u)) {
+                const int mine = __popc(mask);
+                int incl = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
+                }
+                int at = qn + incl - mine;
+                while (mask) {
+                    const int bit = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const int k = bit & 3;   // 0: axis 1 dir +, 1: axis 1 dir -, 2: axis 0 dir +, 3: axis 0 dir -
+                    q[at++] = (unsigned short)((x4 + (bit >> 2)) | (yl << 6) | (k < 2 ? 1u << 12 : 0u) | ((k & 1) ? 0u : 1u << 13));
+                }
+                qn += __shfl_sync(FULL, incl, 31);
+                __syncwarp();
+                int qh = 0;
+                while (qn - qh >= 32 || (flush && qn - qh > 0)) {
+                    if (qh) {   // (process reads q[lane])
+                        const unsigned short v = q[qh + lane];
+                        __syncwarp();
+                        q[lane] = v;
+                        __syncwarp();
+                    }
+                    process(min(32, qn - qh));
+                    qh += 32;
+                }
+                if (qh && !flush) {   // move the leftover to the front
+                    const int rem = qn - qh;
+                    unsigned short v = 0;
+                    if (lane < rem) v = q[qh + lane];
+                    __syncwarp();
+                    if (lane < rem) q[lane] = v;
+                    qn = rem;
+                    __syncwarp();
+                }
+            }
         }
     }
-    if (qn > 0) process(qn);
-    if (count > 0) drain_items(iq, head, count, count, S, brecs, F, grad_ndc, lane);
+    if (count > 0) DRAIN(count);
+}
+
+// One launch, two kinds of CTA: the first n_face_ctas blocks of an image take the faces (in-sweeps, steep tasks), the
+// others one tile each (out-sweeps); the few long face CTAs start first and overlap the many tile CTAs.
+#ifndef HM_BWD_MINB
+#define HM_BWD_MINB 3
+#endif
+__global__ void __launch_bounds__(NTHREADS, HM_BWD_MINB)
+raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
+                  float eps, int n_face_ctas, const int32_t *__restrict__ face_index,
+                  const float *__restrict__ grad_alpha, const uint32_t *__restrict__ cov_row,
+                  const uint32_t *__restrict__ cov_col, const uint32_t *__restrict__ m_row,
+                  const uint32_t *__restrict__ m_col, const uint2 *__restrict__ runs,
+                  const uint32_t *__restrict__ run_info, float *__restrict__ grad_ndc) {
+    __shared__ __align__(16) int fi[(TILE + 2) * FIS];     // tiles: face_index tile, one-pixel halo
+    __shared__ __align__(16) unsigned short cq[NWARPS][CQCAP];   // tiles: candidates (span ends); faces: the face list
+    __shared__ __align__(16) uint32_t ext_row[TILE], ext_col[TILE];   // tiles: extent of the missing-coverage list per line
+    __shared__ ItemQueue iqs[NWARPS];                      // (crossing, run) items
+    __shared__ int n_list;
+    __shared__ SweepSrc S;
+    __shared__ __align__(8) uint64_t bar;
+    extern __shared__ __align__(128) uint2 sruns[];          // tiles: run lists of the tile's rows and columns [2][TILE][RCAP]
+    static_assert(sizeof(cq) >= 2 * BFACES * sizeof(unsigned), "face list fits the candidate queues");
+#ifdef HM_BWD_ROLE_MASK   // development: 1 = tiles only, 2 = faces only
+    if (!(((int)blockIdx.x < n_face_ctas ? 2 : 1) & HM_BWD_ROLE_MASK)) return;
+#endif
+    if ((int)blockIdx.x < n_face_ctas)
+        raster_bwd_face_role(brecs, boxes, F, V, is, aa, eps, face_index, grad_alpha, cov_row, cov_col, m_row, m_col, runs,
+                             run_info, grad_ndc, reinterpret_cast<unsigned *>(&cq[0][0]), n_list, iqs, S);
+    else
+        raster_bwd_tile_role((int)blockIdx.x - n_face_ctas, brecs, F, V, is, aa, eps, face_index, grad_alpha, cov_row,
+                             m_row, m_col, runs, run_info, grad_ndc, fi, cq, ext_row, ext_col, iqs, S, sruns, &bar);
 }
 
 // @region after
@@ -1736,15 +1801,23 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
     HM_REQUIRE(V > 0, "hm_raster_sil_bwd: bad sizes");
     HM_UNSUPPORTED(is > 1024, "hm_raster_sil_bwd: raster size %d > 1024 is not supported", is);
     const BwdRec *brecs = reinterpret_cast<const BwdRec *>(static_cast<const FaceRec *>(records) + (long)B * F);
-    dim3 grid_f((F + BFACES - 1) / BFACES, B);
-    raster_bwd_face_kernel<<<grid_f, NTHREADS, 0, hm_stream(stream)>>>(
-        brecs, static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, face_index, grad_alpha, cov_row,
-        cov_col, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
-    HM_CHECK_LAUNCH("hm_raster_sil_bwd(faces)");
-    dim3 grid((is / TILE) * (is / TILE), B);
-    raster_bwd_kernel<<<grid, NTHREADS, 0, hm_stream(stream)>>>(
-        brecs, F, V, is, anti_aliasing, eps, face_index, grad_alpha, cov_row, m_row, m_col,
-        static_cast<const uint2 *>(runs), run_counts, grad_ndc);
+    const int n_face_ctas = (F + BFACES - 1) / BFACES;
+    const int n_tiles = (is / TILE) * (is / TILE);
+    const size_t smem = 2 * TILE * RCAP * sizeof(uint2);   // staged run lists (static + dynamic exceeds the 48 KB default)
+    static HmSmemOptIn opt_in;
+    if (int rc = hm_smem_opt_in(raster_bwd_kernel, smem, opt_in, "hm_raster_sil_bwd")) return rc;
+#ifdef HM_BWD_SPLIT   // development: the two kinds of CTA in two launches instead of one
+    raster_bwd_kernel<<<dim3(n_face_ctas, B), NTHREADS, smem, hm_stream(stream)>>>(
+        brecs, static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, n_face_ctas, face_index, grad_alpha,
+        cov_row, cov_col, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
+    raster_bwd_kernel<<<dim3(n_tiles, B), NTHREADS, smem, hm_stream(stream)>>>(
+        brecs, static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, 0, face_index, grad_alpha,
+        cov_row, cov_col, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
+#else
+    raster_bwd_kernel<<<dim3(n_face_ctas + n_tiles, B), NTHREADS, smem, hm_stream(stream)>>>(
+        brecs, static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, n_face_ctas, face_index, grad_alpha,
+        cov_row, cov_col, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
+#endif
     HM_CHECK_LAUNCH("hm_raster_sil_bwd");
     return HM_OK;
 }
