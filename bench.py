@@ -122,7 +122,7 @@ def run_reference(args):
     from homan_b200 import synth
     from homan_b200.workload import CONFIGS, loss_weights
     cfg = CONFIGS[args.workload]
-    asset = synth.make_mano_asset(0, "right")
+    asset = synth.make_mano_asset(0, "right", mesh=args.hand_mesh)
     from oracle import build as obuild, nmr
     obuild.build()
 
@@ -145,7 +145,7 @@ def run_reference(args):
         "steps": steps, "warmup": warmup, "ms_per_step": sec * P * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "inits": P, "frames": cfg["T"], "object": cfg["obj"],
-                   "losses": cfg["lw"], "render": "256^2 (512^2 raster, AA)"},
+                   "hand_mesh": args.hand_mesh, "losses": cfg["lw"], "render": "256^2 (512^2 raster, AA)"},
         "cpu_baseline": {"value": value, "unit": "iters/s", "cores": os.cpu_count(), "kind": "port",
                          "sample": f"{steps} timed iteration(s) of 1 of the {P} inits ({cfg['T']} frames), "
                                    f"time x {P} = one whole-batch iteration; oracle/homan_ref.py (torch CPU + OpenMP C)"},
@@ -198,7 +198,7 @@ def run_ours(args):
     from homan_b200.engine import FitEngine, NPART
     from homan_b200.workload import CONFIGS, make_workload
     cfg = CONFIGS[args.workload]
-    asset = synth.make_mano_asset(0, "right")
+    asset = synth.make_mano_asset(0, "right", mesh=args.hand_mesh)
     # weak scaling: every rank fits the same clip from its own block of P random initialisations (equal work per
     # GPU); the job's answer is the argmin over all N*P inits, gathered once at the end
     batch, lw = make_workload(args.workload, clip_index=0, init_shard=rank, mano_asset=asset)
@@ -294,7 +294,8 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "inits": eng.P, "frames": eng.T, "images_per_step_per_gpu": eng.B,
-                   "object": cfg["obj"], "faces": [int(eng.faces_hand.shape[1]), int(eng.faces_obj.shape[1])],
+                   "object": cfg["obj"], "hand_mesh": args.hand_mesh,
+                   "faces": [int(eng.faces_hand.shape[1]), int(eng.faces_obj.shape[1])],
                    "losses": cfg["lw"], "render": "256^2 (512^2 raster, AA)", "cuda_graph": True,
                    "sharding": "inits: every rank fits the clip from its own block of P random inits, one all_gather of the best init at the end",
                    "l2": "inputs larger than L2 (face_index maps alone are %d MB per step)" %
@@ -320,6 +321,8 @@ def main():
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hand-mesh", default="delaunay", choices=["delaunay", "polar"],
+                    help="triangulation of the synthetic hand: well-shaped faces (default) or the round-1 polar slivers")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

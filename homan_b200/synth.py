@@ -89,32 +89,57 @@ def _hand_outline(phi):
     return r
 
 
-def make_mano_asset(seed=0, side="right"):
+_TEMPLATE_CACHE = {}
+
+
+def _hand_template(mesh):
+    """(verts [778,3] float64, closed faces [1552,3]; the first 1538 are the open raster mesh) of the synthetic hand.
+
+    "delaunay" (default): well-shaped faces, homan_b200/data/hand_template.npz made by scripts/make_hand_template.py
+    (planar Delaunay pillow of the mitten outline; longest / shortest edge of a face: median 1.07, worst 3.4).
+    "polar": the round-1 surface, a 97 x 8 polar triangulation of the same outline (many sliver faces: about three times
+    the scan-line crossings per face of a well-shaped mesh); kept so that earlier measurements stay comparable."""
+    if mesh in _TEMPLATE_CACHE:
+        return _TEMPLATE_CACHE[mesh]
+    if mesh == "delaunay":
+        import os
+        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "hand_template.npz"))
+        verts, closed = z["verts"].astype(np.float64), z["closed_faces"].astype(np.int32)
+    elif mesh == "polar":
+        L, K = 97, 8
+        closed = _uv_sphere_topology(L, K)
+        # geometry: flat star-shaped pillow, pole axis = palm normal (z)
+        verts = np.zeros((N_HAND_VERTS, 3), dtype=np.float64)
+        thick = 0.011
+        verts[0] = (0, 0, thick)
+        for j in range(K):
+            th = math.pi * (j + 1) / (K + 1)
+            for i in range(L):
+                ph = 2 * math.pi * i / L
+                r = _hand_outline(np.array([ph]))[0] * math.sin(th) ** 0.6
+                verts[1 + j * L + i] = (r * math.cos(ph), r * math.sin(ph), thick * math.cos(th))
+        verts[-1] = (0, 0, -thick)
+        # the 14 cap faces (a strip of 7 quads at the wrist side, phi ~ pi, between rings 3 and 4) go last
+        cap = []
+        i0 = L // 2 - 3
+        base = L + 2 * L * 3  # faces before band j=3
+        for i in range(i0, i0 + 7):
+            cap += [base + 2 * i, base + 2 * i + 1]
+        keep = np.ones(len(closed), dtype=bool)
+        keep[cap] = False
+        closed = np.concatenate([closed[keep], closed[~keep]], 0)
+    else:
+        raise ValueError(mesh)
+    assert verts.shape == (N_HAND_VERTS, 3) and closed.shape == (N_HAND_FACES_CLOSED, 3)
+    _TEMPLATE_CACHE[mesh] = (verts, closed)
+    return verts, closed
+
+
+def make_mano_asset(seed=0, side="right", mesh="delaunay"):
     """Seeded synthetic MANO-shaped asset. Returns a dict of float32 / int32 numpy arrays."""
     rng = np.random.default_rng(seed)
-    L, K = 97, 8
-    closed = _uv_sphere_topology(L, K)
-    assert closed.shape[0] == N_HAND_FACES_CLOSED
-    # geometry: flat star-shaped pillow, pole axis = palm normal (z)
-    verts = np.zeros((N_HAND_VERTS, 3), dtype=np.float64)
-    thick = 0.011
-    verts[0] = (0, 0, thick)
-    for j in range(K):
-        th = math.pi * (j + 1) / (K + 1)
-        for i in range(L):
-            ph = 2 * math.pi * i / L
-            r = _hand_outline(np.array([ph]))[0] * math.sin(th) ** 0.6
-            verts[1 + j * L + i] = (r * math.cos(ph), r * math.sin(ph), thick * math.cos(th))
-    verts[-1] = (0, 0, -thick)
-    # the 14 cap faces (a strip of 7 quads at the wrist side, phi ~ pi, between rings 3 and 4) go last
-    cap = []
-    i0 = L // 2 - 3
-    base = L + 2 * L * 3  # faces before band j=3
-    for i in range(i0, i0 + 7):
-        cap += [base + 2 * i, base + 2 * i + 1]
-    keep = np.ones(len(closed), dtype=bool)
-    keep[cap] = False
-    closed = np.concatenate([closed[keep], closed[~keep]], 0)
+    verts, closed = _hand_template(mesh)
+    verts, closed = verts.copy(), closed.copy()
     faces_open = closed[:N_HAND_FACES]
     # joints: wrist + 3 per finger (index, middle, pinky, ring, thumb)
     targets = [(-0.025, 0.0, 0.0)]

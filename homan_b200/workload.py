@@ -38,11 +38,12 @@ def gpu_render_fn(device="cuda"):
     return render
 
 
-def make_workload(name, clip_index=0, device="cuda", mano_asset=None, init_shard=0):
+def make_workload(name, clip_index=0, device="cuda", mano_asset=None, init_shard=0, hand_mesh="delaunay"):
     """-> (batch dict of numpy arrays [P,T,...], loss weights). `clip_index` selects the synthetic clip (ground-truth
-    trajectory and target masks), `init_shard` the block of P random initialisations of that clip."""
+    trajectory and target masks), `init_shard` the block of P random initialisations of that clip, `hand_mesh` the
+    triangulation of the synthetic hand when no asset is passed (synth._hand_template)."""
     cfg = CONFIGS[name]
-    asset = mano_asset if mano_asset is not None else synth.make_mano_asset(0, "right")
+    asset = mano_asset if mano_asset is not None else synth.make_mano_asset(0, "right", mesh=hand_mesh)
     seed = cfg["seed"] + clip_index
     clip = synth.make_clip(cfg["T"], cfg["obj"], seed=seed, mano_asset=asset, render_fn=gpu_render_fn(device))
     inits = synth.make_inits(clip, cfg["P"], seed=seed + 7919 * init_shard)
