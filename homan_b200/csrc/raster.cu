@@ -11,6 +11,7 @@
 // The file is compiled with -fmad=false: coverage / ownership predicates are evaluated with the same
 // individually rounded fp32 operations as the CPU oracle so that face_index maps agree bit for bit.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -372,7 +373,8 @@ __device__ __forceinline__ void clip_edge(const RowCtx &rc, float A, float xk, f
 __global__ void __launch_bounds__(NTHREADS)
 raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ boxes, int F, int is, int aa,
                   float near_, float far_, int32_t *__restrict__ face_index, float *__restrict__ alpha,
-                  uint32_t *__restrict__ cov_row, uint32_t *__restrict__ cov_col) {
+                  uint32_t *__restrict__ cov_row, uint32_t *__restrict__ cov_col, uint32_t *__restrict__ face_vis,
+                  unsigned char *__restrict__ cov_blocks) {
     extern __shared__ __align__(16) unsigned long long keys[];  // [TILE * TILE] z-buffer (dynamic: static + this > 48 KB)
     __shared__ int list[LISTCAP];
     __shared__ int cnt, next;
@@ -618,13 +620,35 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     }
     __syncthreads();
 
-    // ---- write-out: face_index rows (four pixels per thread, 16-byte stores), coverage words
+    // ---- write-out: face_index rows (four pixels per thread, 16-byte stores), coverage words, and the faces that own
+    //      a pixel (face_vis: one bit per face of the doubled numbering; collected in shared memory - the face list
+    //      is free now - when it fits, one global atomicOr per non-zero word and tile)
+    const int nvw = (2 * F + 31) / 32;
+    const bool vis_shared = nvw <= LISTCAP;
+    uint32_t *vis_out = face_vis ? face_vis + (long)b * nvw : nullptr;
+    if (vis_out && vis_shared) {
+        for (int i = threadIdx.x; i < nvw; i += NTHREADS) list[i] = 0;
+        __syncthreads();
+    }
     for (int i = threadIdx.x; i < TILE * TILE / 4; i += NTHREADS) {
         const int yl = i / (TILE / 4), x4 = i % (TILE / 4);  // a warp covers two rows of the tile
         const ulonglong2 k01 = *reinterpret_cast<const ulonglong2 *>(&keys[4 * i]);
         const ulonglong2 k23 = *reinterpret_cast<const ulonglong2 *>(&keys[4 * i + 2]);
         const int4 fi4 = make_int4((int)(unsigned)k01.x, (int)(unsigned)k01.y, (int)(unsigned)k23.x, (int)(unsigned)k23.y);
         *reinterpret_cast<int4 *>(face_index + ((long)b * is + (ty0 + yl)) * is + tx0 + 4 * x4) = fi4;  // empty = -1
+        if (vis_out) {   // one mark per run of equal owners along the row
+            int prev = __shfl_up_sync(0xffffffffu, fi4.w, 1);
+            if ((lane & 15) == 0) prev = -1;
+            const int o[4] = {fi4.x, fi4.y, fi4.z, fi4.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                if (o[k] >= 0 && o[k] != prev) {
+                    if (vis_shared) atomicOr(reinterpret_cast<unsigned *>(&list[o[k] >> 5]), 1u << (o[k] & 31));
+                    else atomicOr(&vis_out[o[k] >> 5], 1u << (o[k] & 31));
+                }
+                prev = o[k];
+            }
+        }
         unsigned nib = (fi4.x != -1 ? 1u : 0u) | (fi4.y != -1 ? 2u : 0u) | (fi4.z != -1 ? 4u : 0u) | (fi4.w != -1 ? 8u : 0u);
         nib <<= 4 * (lane & 7);  // eight consecutive lanes make one 32-pixel word
         nib |= __shfl_xor_sync(0xffffffffu, nib, 1);
@@ -637,6 +661,23 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
         }
     }
     __syncthreads();
+    if (vis_out && vis_shared)
+        for (int i = threadIdx.x; i < nvw; i += NTHREADS) {
+            const unsigned w = (unsigned)list[i];
+            if (w) atomicOr(&vis_out[i], w);
+        }
+    if (cov_blocks && threadIdx.x < 2 * (TILE / 8)) {
+        // 8x8-block summary of the coverage: bit j of cov_blocks[band][w] = block 4w + j of the 8-row band has an
+        // uncovered pixel (the backward's test for faces that can have in-sweeps)
+        const int band = threadIdx.x >> 1, w = threadIdx.x & 1;
+        unsigned a = 0xffffffffu;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) a &= roww[band * 8 + r][w];
+        a = ~a;
+        cov_blocks[((long)b * (is / 8) + (ty0 >> 3) + band) * (is / 32) + (tx0 >> 5) + w] =
+            (unsigned char)(((a & 0xffu) ? 1u : 0u) | ((a & 0xff00u) ? 2u : 0u) | ((a & 0xff0000u) ? 4u : 0u) |
+                            ((a & 0xff000000u) ? 8u : 0u));
+    }
     if (aa) {
         const int R = is / 2;
         const int rtop = R - 1 - (ty0 >> 1);
@@ -894,6 +935,12 @@ __device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, 
     h1 += sgn * harmonic_span(zf + del1, nf) * rK1;
     a0 = has0 ? -G * h0 : 0.f;
     a1 = has1 ? -G * h1 : 0.f;
+}
+
+// eval_item with the 2 / is scale already in the coefficients.
+__device__ __forceinline__ void eval_item_k(float x, float K0, float K1, float G, int s, int e, bool has0, bool has1,
+                                            float eps, float &a0, float &a1) {
+    eval_item(x, K0, K1, G, s, e, has0, has1, 1.f, eps, a0, a1);
 }
 
 // @region sweep_bits
@@ -1575,6 +1622,391 @@ raster_bwd_tile_role(int tile, const BwdRec *__restrict__ brecs, int F, int V, i
     if (count > 0) DRAIN(count);
 }
 
+// @region bwd2
+// ------------------------------------------------------------------------------------------ backward, segment kernel
+// backward_pixel_map as the reference organises it - a walk over the scan-lines of every (face, edge, axis) task with
+// the ownership test on face_index - cut into units that fill a GPU: one THREAD per segment of <= B2_SEG consecutive
+// scan-lines of one task. A CTA takes rounds of NTHREADS faces of one image: (1) a thread per face counts the segments
+// of its six tasks (both copies of a both-windings face) and decides whether the face can have in-sweeps at all (an
+// uncovered pixel near its pixel bounding box, looked up in an 8x8-block summary of the coverage built once per CTA,
+// or a corner on an integer pixel coordinate); a block scan turns the counts into a shared work list; (2) a thread per
+// list entry: the face_index reads of its scan-lines are issued together, then each crossing that owns its in-pixel
+// sweeps the missing-coverage runs of its line beyond the crossing, and crossings of silhouette faces sweep the span of
+// the triangle; (crossing, run) items are evaluated in place (eval_item_fast), sums stay in two registers and leave as
+// one atomicAdd per segment and edge vertex into grad_ndc (the vertices_to_faces scatter-add is fused).
+constexpr int B2_SEG = 8;
+constexpr int B2_CAP = 2048;            // list entries per slice
+constexpr int B2_MAXW = 32;             // coverage words per raster row (is <= 1024)
+
+// (crossing, run) item with the cheap cases branched out: no term-by-term part when the run starts >= NEAR_N pixels
+// from the crossing (the closed form holds from distance 4), no closed form for runs of <= NEAR_N pixels.
+__device__ __forceinline__ void eval_item_fast(float x, float c0, float c1, float G, int s, int e, bool has0, bool has1,
+                                               float inv_is2, float eps, float &acc0, float &acc1) {
+    const float K0 = c0 * inv_is2, K1 = c1 * inv_is2;
+    const float rK0 = rcp_fast(K0), rK1 = rcp_fast(K1);
+    const bool left = (float)e <= x;
+    const float sgn = left ? -1.f : 1.f;
+    float z = left ? x - (float)e : (float)s - x;  // distance of the item's nearest pixel
+    int n = e - s + 1;
+    float h0 = 0.f, h1 = 0.f;
+    if (z < (float)NEAR_N) {
+#pragma unroll
+        for (int k = 0; k < NEAR_N; ++k) {
+            const float dd = sgn * (z + (float)k);
+            float dist0 = K0 * dd, dist1 = K1 * dd;
+            dist0 = (0.f < dist0) ? dist0 + eps : dist0 - eps;
+            dist1 = (0.f < dist1) ? dist1 + eps : dist1 - eps;
+            const float t0 = rcp_fast(dist0), t1 = rcp_fast(dist1);
+            if (k < n) { h0 += t0; h1 += t1; }
+        }
+        n -= NEAR_N;
+        z += (float)NEAR_N;
+    }
+    if (n > 0) {
+        const float nf = (float)n;
+        h0 += sgn * harmonic_span(z + eps * fabsf(rK0), nf) * rK0;
+        h1 += sgn * harmonic_span(z + eps * fabsf(rK1), nf) * rK1;
+    }
+    if (has0) acc0 -= G * h0;
+    if (has1) acc1 -= G * h1;
+}
+
+// Runs of list `ls` on line d0 (info = its run_counts word) with pixels inside [ra, rc]: bit r = run r; SWEEP_WALK
+// when the list overflowed or the sweep must walk the bit line.
+constexpr unsigned SWEEP_WALK = 1u << 31;
+__device__ __forceinline__ unsigned sweep_todo(const SweepSrc &S, int ls, int d0, uint32_t info, int ra, int rc, bool walk) {
+    const unsigned cnt = info & 15u;
+    if (cnt == 0u || rc < (int)((info >> 4) & 0xfffu) || ra > (int)(info >> 16)) return 0u;
+    if (cnt == RUN_OVERFLOW || walk) return SWEEP_WALK;
+    const uint2 *rl = S.runs + ((long)ls * S.is + d0) * RCAP;
+    unsigned todo = 0;
+    for (unsigned r = 0; r < cnt; ++r) {
+        const unsigned se = __ldg(&rl[r].x);
+        if (rc >= (int)(se & 0xffffu) && ra <= (int)(se >> 16)) todo |= 1u << r;
+    }
+    return todo;
+}
+__device__ __noinline__ void sweep_walk(const SweepSrc &S, int ls, int d0, int ra, int rc, float x, float K0, float K1,
+                                        unsigned flags, float &a0, float &a1) {
+    const int col = ls >> 1;
+    const uint32_t *line = (col ? S.m_col : S.m_row) + ((long)(ls & 1) * S.is + d0) * S.W;
+    const float is2 = 0.5f * (float)S.is;   // sweep_bits takes the coefficients before the 2 / is scale
+    sweep_bits(line, ra, rc, col ? 0 : 1, d0, x, K0 * is2, K1 * is2, flags & 1u, flags & 2u, S.ctx, a0, a1);
+}
+
+// Per-warp queue of (crossing, run) items: x, K0, K1 (distance coefficients, 2 / is included), G (run weight),
+// range = s | e << 12 | has0 << 24 | has1 << 25 | owner lane << 26.
+constexpr int B2_QCAP = 64;
+struct ItemQueue2 {
+    float x[B2_QCAP], K0[B2_QCAP], K1[B2_QCAP], G[B2_QCAP];
+    unsigned range[B2_QCAP];
+};
+// One push round: every lane with runs left queues its next run.
+__device__ __forceinline__ void b2_push(ItemQueue2 &iq, int &count, unsigned &todo, const uint2 *rl, int ra, int rc, float x,
+                                        float K0, float K1, unsigned flags, int owner) {
+    const int lane = threadIdx.x & 31;
+    const bool it = todo != 0u;
+    const unsigned m = __ballot_sync(0xffffffffu, it);
+    if (it) {
+        const int r = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint2 run = __ldg(rl + r);
+        const int s = max(ra, (int)(run.x & 0xffffu)), e = min(rc, (int)(run.x >> 16));
+        const int pos = count + __popc(m & ((1u << lane) - 1u));
+        iq.x[pos] = x; iq.K0[pos] = K0; iq.K1[pos] = K1; iq.G[pos] = __uint_as_float(run.y);
+        iq.range[pos] = (unsigned)s | ((unsigned)e << 12) | (flags << 24) | ((unsigned)owner << 26);
+    }
+    count += __popc(m);
+    __syncwarp();
+}
+// Evaluates items [first, first + n) (n <= 32, one per lane) and adds the results to the owners' accumulators. The
+// leftover of the queue ([0, first)) stays in place: the caller drains from the top.
+__device__ __noinline__ void b2_drain(const ItemQueue2 &iq, int first, int n, float eps, float (*sacc)[2]) {
+    const int lane = threadIdx.x & 31;
+    if (lane < n) {
+        const int s_ = first + lane;
+        const unsigned rng = iq.range[s_];
+        float a0, a1;
+        eval_item_k(iq.x[s_], iq.K0[s_], iq.K1[s_], iq.G[s_], rng & 0xfffu, (rng >> 12) & 0xfffu, (rng >> 24) & 1u,
+                    (rng >> 25) & 1u, eps, a0, a1);
+        const int owner = rng >> 26;
+        if (a0 != 0.f) atomicAdd(&sacc[owner][0], a0);
+        if (a1 != 0.f) atomicAdd(&sacc[owner][1], a1);
+    }
+    __syncwarp();
+}
+
+#ifndef HM_BWD2_MINB
+#define HM_BWD2_MINB 4
+#endif
+// Geometry of the 32 tasks a warp is working on, by lane (structure of arrays: the consumer of a crossing reads the
+// fields of the lane that produced it).
+struct TaskStash {
+    float slope[32], p0d0[32], p0d1[32], p1d0[32], p2d0[32], p2d1[32], s02[32], s21[32];
+    int misc[32];   // d0a | axis << 12 | dir > 0 << 13
+};
+constexpr int B2_PAIRS = 32 * 2 * B2_SEG;   // (lane, scan-line, kind) of the crossings worth a sweep: at most two per line
+
+__global__ void __launch_bounds__(NTHREADS, HM_BWD2_MINB)
+raster_bwd2_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
+                   float eps, const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
+                   const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ cov_col,
+                   const uint32_t *__restrict__ face_vis, const unsigned char *__restrict__ cov_blocks,
+                   const uint32_t *__restrict__ m_row, const uint32_t *__restrict__ m_col,
+                   const uint2 *__restrict__ runs, const uint32_t *__restrict__ run_info, float *__restrict__ grad_ndc) {
+    __shared__ uint32_t list[B2_CAP];
+    __shared__ int wsum[NWARPS];
+    __shared__ SweepSrc S;
+    __shared__ ItemQueue2 iq2[NWARPS];
+    __shared__ float sacc[NWARPS][32][2];
+    __shared__ TaskStash stash[NWARPS];
+    __shared__ unsigned short pairs[NWARPS][B2_PAIRS];
+    const int b = blockIdx.y;
+    const int W = is / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
+    int qcount = 0;
+    brecs += (long)b * F;
+    boxes += (long)b * F;
+    grad_ndc += (long)b * V * 3;
+    face_index += (long)b * is * is;
+    cov_row += (long)b * is * W;
+    cov_col += (long)b * is * W;
+    face_vis += (long)b * HM_FACE_VIS_WORDS(F);
+    cov_blocks += (long)b * (is / 8) * W;
+    if (threadIdx.x == 0) S = sweep_src(b, is, aa, eps, grad_alpha, m_row, m_col, runs, run_info);
+    const int n_rounds = (F + NTHREADS - 1) / NTHREADS;
+    for (int round = blockIdx.x; round < n_rounds; round += gridDim.x) {
+        // ---- (1) thread per face: is it visible (owns a pixel: out-sweeps), can it have in-sweeps (an uncovered pixel
+        //      in the 8x8 blocks its pixel bounding box touches, or irregular), how many segments do its tasks have
+        const int f = round * NTHREADS + threadIdx.x;
+        unsigned ns = 0, ns_hi = 0;   // segments per task, 8 bits each
+        int n_f = 0;
+        unsigned fflags = 0;          // 1: boundary, 2: first copy visible, 4: there is a second copy, 8: second copy visible
+        if (f < F) {
+            const int4 q3 = __ldg(reinterpret_cast<const int4 *>(brecs + f) + 3);
+            if (q3.w >= 0) {
+                const int fn = q3.w & BWD_FN_MASK;
+                bool boundary = q3.w & BWD_IRREGULAR;
+                if (!boundary) {
+                    const FaceBox bx = boxes[f];   // clamped pixel bbox with one pixel of slack
+                    const int w0 = bx.x0 >> 5, w1 = bx.x1 >> 5;
+                    for (int band = bx.y0 >> 3; band <= (bx.y1 >> 3) && !boundary; ++band)
+                        for (int w = w0; w <= w1; ++w) {
+                            const int lo = max((bx.x0 >> 3) - 4 * w, 0), hi = min((bx.x1 >> 3) - 4 * w, 3);
+                            if (__ldg(cov_blocks + band * W + w) & ((0xfu >> (3 - hi)) & (0xfu << lo))) { boundary = true; break; }
+                        }
+                }
+                const bool vis0 = (__ldg(face_vis + (fn >> 5)) >> (fn & 31)) & 1u;
+                const bool both = q3.w & BWD_BOTH;
+                const bool vis1 = both && ((__ldg(face_vis + ((fn + F) >> 5)) >> ((fn + F) & 31)) & 1u);
+                fflags = (boundary ? 1u : 0u) | (vis0 ? 2u : 0u) | (both ? 4u : 0u) | (vis1 ? 8u : 0u);
+                const int copies = ((boundary || vis0) ? 1 : 0) + ((both && (boundary || vis1)) ? 1 : 0);
+                if (copies) {
+                    const uint4 s4 = __ldg(reinterpret_cast<const uint4 *>(brecs + f) + 4);
+                    const uint2 s5 = __ldg(reinterpret_cast<const uint2 *>(brecs + f) + 10);
+                    const unsigned sp[6] = {s4.x, s4.y, s4.z, s4.w, s5.x, s5.y};
+                    int tot = 0;
+#pragma unroll
+                    for (int t = 0; t < 6; ++t) {
+                        const int len = (int)((sp[t] >> 12) & 0xfffu) - (int)(sp[t] & 0xfffu) + 1;
+                        const int n = len > 0 ? (len + B2_SEG - 1) / B2_SEG : 0;   // <= 128
+                        if (t < 4) ns |= (unsigned)n << (8 * t); else ns_hi |= (unsigned)n << (8 * (t - 4));
+                        tot += n;
+                    }
+                    n_f = tot * copies;
+                }
+            }
+        }
+        // block-wide exclusive scan of n_f
+        int incl = n_f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        __syncthreads();   // previous round's list fully consumed, wsum free
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        int base = incl - n_f, total = 0;
+#pragma unroll
+        for (int w = 0; w < NWARPS; ++w) {
+            const int v = wsum[w];
+            if (w < warp) base += v;
+            total += v;
+        }
+        for (int lo = 0; lo < total; lo += B2_CAP) {
+            if (lo) __syncthreads();
+            // ---- entries of this slice: face (local) | task << 8 | copy << 11 | boundary << 12 | visible << 13 | segment << 14
+            if (n_f && base < lo + B2_CAP && base + n_f > lo) {
+                int idx = base;
+                for (int copy = 0; copy < 2; ++copy) {
+                    const bool vis = copy ? (fflags & 8u) : (fflags & 2u);
+                    if (copy && !(fflags & 4u)) break;
+                    if (!vis && !(fflags & 1u)) continue;
+#pragma unroll
+                    for (int t = 0; t < 6; ++t) {
+                        // the reversed copy swaps edges 0 and 1: its task t has the scan-lines of task t ^ 2 (t < 4)
+                        const int ts = (copy && t < 4) ? (t ^ 2) : t;
+                        const int n = (ts < 4 ? ns >> (8 * ts) : ns_hi >> (8 * (ts - 4))) & 0xff;
+                        for (int k = 0; k < n; ++k, ++idx)
+                            if (idx >= lo && idx < lo + B2_CAP)
+                                list[idx - lo] = (unsigned)threadIdx.x | ((unsigned)t << 8) | ((unsigned)copy << 11) |
+                                                 ((fflags & 1u) << 12) | (vis ? 1u << 13 : 0u) | ((unsigned)k << 14);
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- (2) a warp takes 32 segments. (a) thread per segment: ownership of the in-pixels (loads issued
+            //      together), which crossings are worth a sweep; (b) those crossings are compacted over the lanes,
+            //      thread per crossing: sweep range, runs inside it -> (crossing, run) items in the warp's queue;
+            //      (c) 32 items are evaluated at a time, one per lane, straight-line code; results return to the
+            //      segment's accumulators in shared memory.
+            const int n_here = min(B2_CAP, total - lo);
+            TaskStash &st = stash[warp];
+            unsigned short *pr = pairs[warp];
+            for (int j0 = warp * 32; j0 < n_here; j0 += NTHREADS) {
+                const int j = j0 + lane;
+                const bool valid = j < n_here;
+                const unsigned ent = valid ? list[j] : 0u;
+                const int t = (ent >> 8) & 7, e = t >> 1, axis = t & 1, k = ent >> 14;
+                const bool bnd = (ent >> 12) & 1u, vis = (ent >> 13) & 1u;
+                BwdFace bf = load_bwd_face(brecs + (valid ? round * NTHREADS + (int)(ent & 0xffu) : 0));
+                if ((ent >> 11) & 1u) reverse_bwd_face(bf, F);
+                const TaskGeom g = task_geom(bf, e, axis, is);
+                const int d0a = g.d0_from + k * B2_SEG;
+                const int d0b = valid ? min(g.d0_to, d0a + B2_SEG - 1) : d0a - 1;
+                const int lN = axis == 0 ? 2 : 0;
+                st.slope[lane] = g.slope; st.p0d0[lane] = g.p0d0; st.p0d1[lane] = g.p0d1; st.p1d0[lane] = g.p1d0;
+                st.p2d0[lane] = g.p2d0; st.p2d1[lane] = g.p2d1; st.s02[lane] = g.s02; st.s21[lane] = g.s21;
+                st.misc[lane] = d0a | (axis << 12) | (g.dir > 0 ? 1 << 13 : 0);
+                sacc[warp][lane][0] = 0.f;
+                sacc[warp][lane][1] = 0.f;
+                // (a) bit q of `out`: the face owns the in-pixel of scan-line d0a + q and the line has missing coverage
+                //     beyond the out-pixel; bit q of `in`: a crossing of a face that can have in-sweeps
+                unsigned out = 0, in = 0;
+                {
+                    int own[B2_SEG];
+                    uint32_t inf[B2_SEG];
+                    int d1o[B2_SEG];
+#pragma unroll
+                    for (int q = 0; q < B2_SEG; ++q) {
+                        const int d0 = d0a + q;
+                        own[q] = -3; inf[q] = 0u; d1o[q] = 0;
+                        if (d0 <= d0b) {
+                            const float x = g.slope * ((float)d0 - g.p0d0) + g.p0d1;
+                            const int d1_in = __float2int_rz(g.dir > 0 ? floorf(x) : ceilf(x));
+                            const int d1_out = d1_in + g.dir;
+                            if ((unsigned)d1_in < (unsigned)is && (unsigned)d1_out < (unsigned)is) {
+                                if (bnd) in |= 1u << q;
+                                if (vis) {
+                                    own[q] = __ldg(face_index + (axis == 0 ? d1_in * is + d0 : d0 * is + d1_in));
+                                    inf[q] = __ldg(S.run_info + lN * is + d0);
+                                    d1o[q] = d1_out;
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int q = 0; q < B2_SEG; ++q) {
+                        // extent of the line's missing-coverage list against the sweep [d1_out, border]
+                        const int lo_ = (inf[q] >> 4) & 0xfffu, hi_ = inf[q] >> 16;
+                        const bool beyond = g.dir > 0 ? hi_ >= d1o[q] : lo_ <= d1o[q];
+                        if (own[q] == bf.fn && (inf[q] & 15u) && beyond) out |= 1u << q;
+                    }
+                }
+                // (b) compaction: pair = lane | q << 5 | in-sweep << 8
+                const int mine = __popc(out) + __popc(in);
+                int pre = mine;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, pre, o);
+                    if (lane >= o) pre += v;
+                }
+                const int npairs = __shfl_sync(FULL, pre, 31);
+                if (npairs == 0) continue;   // (warp-uniform)
+                {
+                    int at = pre - mine;
+                    unsigned m = out;
+                    while (m) { const int q = __ffs(m) - 1; m &= m - 1; pr[at++] = (unsigned short)(lane | (q << 5)); }
+                    m = in;
+                    while (m) { const int q = __ffs(m) - 1; m &= m - 1; pr[at++] = (unsigned short)(lane | (q << 5) | 256); }
+                }
+                __syncwarp();
+                for (int i0 = 0; i0 < npairs; i0 += 32) {
+                    unsigned todo = 0, flags = 0;
+                    int ra = 0, rc = 0, ls = 0, d0 = 0, owner = 0;
+                    float x = 0.f, K0 = 0.f, K1 = 0.f;
+                    if (i0 + lane < npairs) {
+                        const unsigned pw = pr[i0 + lane];
+                        owner = pw & 31;
+                        const int q = (pw >> 5) & 7;
+                        const int misc = st.misc[owner];
+                        const int ax = (misc >> 12) & 1, dir = (misc >> 13) & 1 ? 1 : -1, lNo = ax == 0 ? 2 : 0;
+                        d0 = (misc & 0xfff) + q;
+                        const float fd0 = (float)d0, p0d0 = st.p0d0[owner], p0d1 = st.p0d1[owner], p1d0 = st.p1d0[owner];
+                        x = st.slope[owner] * (fd0 - p0d0) + p0d1;
+                        const int d1_in = __float2int_rz(dir > 0 ? floorf(x) : ceilf(x));
+                        const int d1_out = d1_in + dir;
+                        flags = (p1d0 != fd0 ? 1u : 0u) | (p0d0 != fd0 ? 2u : 0u);
+                        bool walk = false;
+                        uint32_t info = 0;
+                        if (!(pw & 256u)) {   // out-sweep: from the out-pixel to the image border
+                            const int lim = dir > 0 ? is - 1 : 0;
+                            ra = min(d1_out, lim); rc = max(d1_out, lim);
+                            ls = lNo;
+                            info = __ldg(S.run_info + ls * is + d0);
+                        } else {              // in-sweep: from the in-pixel to the opposite edge of the triangle
+                            const uint32_t *cov = ax == 0 ? cov_col : cov_row;   // coverage of line d0 along d1
+                            const bool alpha_out = (__ldg(cov + d0 * W + (d1_out >> 5)) >> (d1_out & 31)) & 1u;
+                            ls = alpha_out ? lNo : lNo + 1;
+                            info = __ldg(S.run_info + ls * is + d0);
+                            if ((info & 15u) != 0u) {
+                                const float p2d0 = st.p2d0[owner];
+                                float c2;
+                                if ((fd0 - p0d0) * (fd0 - p2d0) < 0.f) c2 = st.s02[owner] * (fd0 - p0d0) + p0d1;
+                                else c2 = st.s21[owner] * (fd0 - p2d0) + st.p2d1[owner];
+                                const int lim = __float2int_rz(dir > 0 ? ceilf(c2) : floorf(c2));
+                                ra = max(min(d1_in, lim), 0); rc = min(max(d1_in, lim), is - 1);
+                                // an in-sweep can straddle its crossing: by a pixel when the triangle is thinner than a
+                                // pixel there (eval_item copes with NEAR_N - 1 pixels on the near side), by many when its
+                                // far end is extrapolated (irregular faces): those walk the bit line
+                                walk = (float)ra < x - (float)(NEAR_N - 1) && (float)rc > x;
+                                if (ra > rc) info = 0u;
+                            }
+                        }
+                        todo = sweep_todo(S, ls, d0, info, ra, rc, walk);
+                        if (todo) {
+                            const float ka = p1d0 - p0d0;
+                            K0 = __fdividef(ka, p1d0 - fd0) * S.inv_is2;
+                            K1 = __fdividef(ka, fd0 - p0d0) * S.inv_is2;
+                        }
+                        if (todo & SWEEP_WALK) {   // rare: in place
+                            float a0 = 0.f, a1 = 0.f;
+                            sweep_walk(S, ls, d0, ra, rc, x, K0, K1, flags, a0, a1);
+                            if (a0 != 0.f) atomicAdd(&sacc[warp][owner][0], a0);
+                            if (a1 != 0.f) atomicAdd(&sacc[warp][owner][1], a1);
+                            todo = 0;
+                        }
+                    }
+                    __syncwarp();
+                    while (__any_sync(FULL, todo != 0u)) {
+                        b2_push(iq2[warp], qcount, todo, S.runs + ((long)ls * is + d0) * RCAP, ra, rc, x, K0, K1, flags, owner);
+                        if (qcount >= 32) { b2_drain(iq2[warp], qcount - 32, 32, S.eps, sacc[warp]); qcount -= 32; }
+                    }
+                }
+                if (qcount > 0) { b2_drain(iq2[warp], 0, qcount, S.eps, sacc[warp]); qcount = 0; }
+                __syncwarp();
+                // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
+                const float acc0 = sacc[warp][lane][0], acc1 = sacc[warp][lane][1];
+                if (acc0 != 0.f) atomicAdd(grad_ndc + g.vid0 * 3 + (1 - axis), acc0);
+                if (acc1 != 0.f) atomicAdd(grad_ndc + g.vid1 * 3 + (1 - axis), acc1);
+                __syncwarp();
+            }
+        }
+    }
+}
+
 // One launch, two kinds of CTA: the first n_face_ctas blocks of an image take the faces (in-sweeps, steep tasks), the
 // others one tile each (out-sweeps); the few long face CTAs start first and overlap the many tile CTAs.
 #ifndef HM_BWD_MINB
@@ -1745,7 +2177,7 @@ int hm_raster_setup(const float *ndc, const int32_t *faces, int faces_batch, int
 
 int hm_raster_sil_fwd(const void *records, const void *bboxes, int B, int F, int image_size,
                       int anti_aliasing, float near_, float far_, int32_t *face_index, float *alpha,
-                      uint32_t *cov_row, uint32_t *cov_col, void *stream) {
+                      uint32_t *cov_row, uint32_t *cov_col, uint32_t *face_vis, uint8_t *cov_blocks, void *stream) {
     HM_REQUIRE(B >= 0 && F >= 0 && B <= 65535, "hm_raster_sil_fwd: bad sizes (B <= 65535)");
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
@@ -1755,9 +2187,16 @@ int hm_raster_sil_fwd(const void *records, const void *bboxes, int B, int F, int
     const int fwd_smem = TILE * TILE * (int)sizeof(unsigned long long);
     static HmSmemOptIn opt_in;  // static + dynamic shared memory exceeds the 48 KB default
     if (int rc = hm_smem_opt_in(raster_fwd_kernel, fwd_smem, opt_in, "hm_raster_sil_fwd")) return rc;
+    if (face_vis && F > 0) {   // the tiles OR into it (a memset node when the stream is being captured)
+        const cudaError_t e = cudaMemsetAsync(face_vis, 0, (size_t)B * HM_FACE_VIS_WORDS(F) * sizeof(uint32_t), hm_stream(stream));
+        if (e != cudaSuccess) {
+            hm_set_error("hm_raster_sil_fwd: cudaMemsetAsync: %s", cudaGetErrorString(e));
+            return HM_ERR_CUDA;
+        }
+    }
     raster_fwd_kernel<<<grid, NTHREADS, fwd_smem, hm_stream(stream)>>>(
         static_cast<const FaceRec *>(records), static_cast<const FaceBox *>(bboxes), F, is, anti_aliasing, near_, far_,
-        face_index, alpha, cov_row, cov_col);
+        face_index, alpha, cov_row, cov_col, face_vis, cov_blocks);
     HM_CHECK_LAUNCH("hm_raster_sil_fwd");
     return HM_OK;
 }
@@ -1788,6 +2227,7 @@ int hm_raster_grad_prep(const float *grad_alpha, const uint32_t *cov_row, const 
 
 int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *face_index,
                       const float *grad_alpha, const uint32_t *cov_row, const uint32_t *cov_col,
+                      const uint32_t *face_vis, const uint8_t *cov_blocks,
                       const uint32_t *m_row, const uint32_t *m_col, const void *runs, const uint32_t *run_counts,
                       int B, int V, int F, int image_size, int anti_aliasing, float eps, float *grad_ndc,
                       void *stream) {
@@ -1795,8 +2235,8 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
     if (B == 0 || F == 0) return HM_OK;
-    HM_REQUIRE(records && bboxes && face_index && grad_alpha && cov_row && cov_col && m_row && m_col && runs &&
-                   run_counts && grad_ndc,
+    HM_REQUIRE(records && bboxes && face_index && grad_alpha && cov_row && cov_col && face_vis && cov_blocks && m_row &&
+                   m_col && runs && run_counts && grad_ndc,
                "hm_raster_sil_bwd: null pointer");
     HM_REQUIRE(V > 0, "hm_raster_sil_bwd: bad sizes");
     HM_UNSUPPORTED(is > 1024, "hm_raster_sil_bwd: raster size %d > 1024 is not supported", is);
@@ -1806,6 +2246,15 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
     const size_t smem = 2 * TILE * RCAP * sizeof(uint2);   // staged run lists (static + dynamic exceeds the 48 KB default)
     static HmSmemOptIn opt_in;
     if (int rc = hm_smem_opt_in(raster_bwd_kernel, smem, opt_in, "hm_raster_sil_bwd")) return rc;
+    static const bool use_old = getenv("HOMAN_B200_BWD_OLD") != nullptr;   // development switch
+    if (!use_old) {
+        const int n_rounds = (F + NTHREADS - 1) / NTHREADS;
+        raster_bwd2_kernel<<<dim3(min(n_rounds, 8), B), NTHREADS, 0, hm_stream(stream)>>>(
+            brecs, static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, face_index, grad_alpha, cov_row,
+            cov_col, face_vis, cov_blocks, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
+        HM_CHECK_LAUNCH("hm_raster_sil_bwd");
+        return HM_OK;
+    }
 #ifdef HM_BWD_SPLIT   // development: the two kinds of CTA in two launches instead of one
     raster_bwd_kernel<<<dim3(n_face_ctas, B), NTHREADS, smem, hm_stream(stream)>>>(
         brecs, static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, n_face_ctas, face_index, grad_alpha,

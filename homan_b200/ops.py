@@ -76,6 +76,8 @@ class RasterBuffers:
         self.m_col = torch.empty(B, 2, S, S // 32, dtype=torch.int32, device=device)
         self.runs = torch.empty(B, 4, S, 8, 2, dtype=torch.int32, device=device)   # HM_RASTER_RUN_CAP = 8
         self.run_counts = torch.empty(B, 4, S, dtype=torch.int32, device=device)
+        self.face_vis = torch.empty(B, (2 * F + 31) // 32, dtype=torch.int32, device=device)   # HM_FACE_VIS_WORDS(F)
+        self.cov_blocks = torch.empty(B, S // 8, S // 32, dtype=torch.uint8, device=device)
 
 
 def raster_forward(buf, ndc, faces, fill_back=True, near=NEAR, far=FAR):
@@ -84,7 +86,8 @@ def raster_forward(buf, ndc, faces, fill_back=True, near=NEAR, far=FAR):
     call("hm_raster_setup", ptr(ndc), ptr(faces), faces.shape[0], buf.B, buf.V, buf.F, buf.image_size, int(buf.aa),
          int(fill_back), ptr(buf.records), ptr(buf.bboxes), s)
     call("hm_raster_sil_fwd", ptr(buf.records), ptr(buf.bboxes), buf.B, buf.F, buf.image_size, int(buf.aa),
-         float(near), float(far), ptr(buf.face_index), ptr(buf.alpha), ptr(buf.cov_row), ptr(buf.cov_col), s)
+         float(near), float(far), ptr(buf.face_index), ptr(buf.alpha), ptr(buf.cov_row), ptr(buf.cov_col),
+         ptr(buf.face_vis), ptr(buf.cov_blocks), s)
     return buf.alpha
 
 
@@ -94,7 +97,8 @@ def raster_backward(buf, grad_alpha, grad_ndc, eps=RASTER_EPS):
     call("hm_raster_grad_prep", ptr(grad_alpha), ptr(buf.cov_row), ptr(buf.cov_col), buf.B, buf.image_size,
          int(buf.aa), ptr(buf.m_row), ptr(buf.m_col), ptr(buf.runs), ptr(buf.run_counts), s)
     call("hm_raster_sil_bwd", ptr(buf.records), ptr(buf.bboxes), ptr(buf.face_index), ptr(grad_alpha),
-         ptr(buf.cov_row), ptr(buf.cov_col), ptr(buf.m_row), ptr(buf.m_col), ptr(buf.runs), ptr(buf.run_counts),
+         ptr(buf.cov_row), ptr(buf.cov_col), ptr(buf.face_vis), ptr(buf.cov_blocks), ptr(buf.m_row), ptr(buf.m_col),
+         ptr(buf.runs), ptr(buf.run_counts),
          buf.B, buf.V, buf.F, buf.image_size,
          int(buf.aa), float(eps), ptr(grad_ndc), s)
     return grad_ndc

@@ -62,10 +62,14 @@ int hm_raster_setup(const float *ndc, const int32_t *faces, int faces_batch, int
                     int image_size, int anti_aliasing, int fill_back, void *records, void *bboxes,
                     void *stream);
 /* -> face_index [B,S,S] (doubled numbering: f or F+f, -1 background; raster frame, row 0 = y -1),
- *    alpha [B,R,R] (after flip + pool), coverage bitmaps cov_row / cov_col [B,S,S/32] (may be NULL). */
+ *    alpha [B,R,R] (after flip + pool), coverage bitmaps cov_row / cov_col [B,S,S/32] (may be NULL),
+ *    face_vis [B,HM_FACE_VIS_WORDS(F)] (may be NULL): bit fn set iff face fn of the doubled numbering owns a pixel,
+ *    cov_blocks [B,S/8,S/32] bytes (may be NULL): bit j of [band][w] set iff the 8x8 block 4w + j of the 8-row band has
+ *    an uncovered pixel.  The last two are what hm_raster_sil_bwd culls hidden faces and in-sweeps with. */
+#define HM_FACE_VIS_WORDS(F) ((2 * (F) + 31) / 32)
 int hm_raster_sil_fwd(const void *records, const void *bboxes, int B, int F, int image_size,
                       int anti_aliasing, float near_, float far_, int32_t *face_index, float *alpha,
-                      uint32_t *cov_row, uint32_t *cov_col, void *stream);
+                      uint32_t *cov_row, uint32_t *cov_col, uint32_t *face_vis, uint8_t *cov_blocks, void *stream);
 /* grad_alpha [B,R,R] + coverage -> sweep masks m_row / m_col [B,2,S,S/32]
  * (0: uncovered & grad<0, 1: covered & grad>0) and their run-length form:
  * runs [B,4,S,HM_RASTER_RUN_CAP] (8 B each), run_counts [B,4,S] (count | first pixel << 4 | last pixel << 16). */
@@ -77,6 +81,7 @@ int hm_raster_grad_prep(const float *grad_alpha, const uint32_t *cov_row, const 
  * grad_ndc [B,V,3] += d loss / d (u, v) of every vertex (z receives nothing in silhouette mode). */
 int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *face_index,
                       const float *grad_alpha, const uint32_t *cov_row, const uint32_t *cov_col,
+                      const uint32_t *face_vis, const uint8_t *cov_blocks,
                       const uint32_t *m_row, const uint32_t *m_col, const void *runs, const uint32_t *run_counts,
                       int B, int V, int F, int image_size, int anti_aliasing, float eps, float *grad_ndc,
                       void *stream);
