@@ -1671,21 +1671,6 @@ __device__ __forceinline__ void eval_item_fast(float x, float c0, float c1, floa
     if (has1) acc1 -= G * h1;
 }
 
-// Runs of list `ls` on line d0 (info = its run_counts word) with pixels inside [ra, rc]: bit r = run r; SWEEP_WALK
-// when the list overflowed or the sweep must walk the bit line.
-constexpr unsigned SWEEP_WALK = 1u << 31;
-__device__ __forceinline__ unsigned sweep_todo(const SweepSrc &S, int ls, int d0, uint32_t info, int ra, int rc, bool walk) {
-    const unsigned cnt = info & 15u;
-    if (cnt == 0u || rc < (int)((info >> 4) & 0xfffu) || ra > (int)(info >> 16)) return 0u;
-    if (cnt == RUN_OVERFLOW || walk) return SWEEP_WALK;
-    const uint2 *rl = S.runs + ((long)ls * S.is + d0) * RCAP;
-    unsigned todo = 0;
-    for (unsigned r = 0; r < cnt; ++r) {
-        const unsigned se = __ldg(&rl[r].x);
-        if (rc >= (int)(se & 0xffffu) && ra <= (int)(se >> 16)) todo |= 1u << r;
-    }
-    return todo;
-}
 __device__ __noinline__ void sweep_walk(const SweepSrc &S, int ls, int d0, int ra, int rc, float x, float K0, float K1,
                                         unsigned flags, float &a0, float &a1) {
     const int col = ls >> 1;
@@ -1694,44 +1679,54 @@ __device__ __noinline__ void sweep_walk(const SweepSrc &S, int ls, int d0, int r
     sweep_bits(line, ra, rc, col ? 0 : 1, d0, x, K0 * is2, K1 * is2, flags & 1u, flags & 2u, S.ctx, a0, a1);
 }
 
-// Per-warp queue of (crossing, run) items: x, K0, K1 (distance coefficients, 2 / is included), G (run weight),
-// range = s | e << 12 | has0 << 24 | has1 << 25 | owner lane << 26.
-constexpr int B2_QCAP = 64;
-struct ItemQueue2 {
-    float x[B2_QCAP], K0[B2_QCAP], K1[B2_QCAP], G[B2_QCAP];
-    unsigned range[B2_QCAP];
+// Per-warp queue of the sweeps that found runs, in pair order: x, K0, K1 (crossing position, distance coefficients
+// with 2 / is included), meta = has0 | has1 << 1 | segment (lane of the warp pass) << 2 | first run << 7 | runs << 10,
+// where = ra | rc << 10 | (list * is + scan-line) << 20.
+constexpr int B2_QCAP = 64;   // ring: a leftover of < 32 plus one push of <= 32
+struct SweepQueue2 {
+    float x[B2_QCAP], K0[B2_QCAP], K1[B2_QCAP];
+    unsigned meta[B2_QCAP], where[B2_QCAP];
 };
-// One push round: every lane with runs left queues its next run.
-__device__ __forceinline__ void b2_push(ItemQueue2 &iq, int &count, unsigned &todo, const uint2 *rl, int ra, int rc, float x,
-                                        float K0, float K1, unsigned flags, int owner) {
+// Evaluates sweeps [head, head + n) of the ring (n <= 32, one per lane): the runs of a sweep one after the other
+// (straight-line item code; the queue holds sweeps with runs only, most have one or two). The sweeps of one segment
+// are neighbours: segmented sum over the lanes, the first lane of every group adds to the segment's accumulator
+// (batches run one after the other: a plain read-modify-write, and the order of the sum is fixed).
+__device__ __noinline__ void b2_drain(const SweepQueue2 &sq, int head, int n, const uint2 *__restrict__ runs, float eps,
+                                      float (*sacc)[2]) {
+    const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const bool it = todo != 0u;
-    const unsigned m = __ballot_sync(0xffffffffu, it);
-    if (it) {
-        const int r = __ffs(todo) - 1;
-        todo &= todo - 1;
-        const uint2 run = __ldg(rl + r);
-        const int s = max(ra, (int)(run.x & 0xffffu)), e = min(rc, (int)(run.x >> 16));
-        const int pos = count + __popc(m & ((1u << lane) - 1u));
-        iq.x[pos] = x; iq.K0[pos] = K0; iq.K1[pos] = K1; iq.G[pos] = __uint_as_float(run.y);
-        iq.range[pos] = (unsigned)s | ((unsigned)e << 12) | (flags << 24) | ((unsigned)owner << 26);
-    }
-    count += __popc(m);
-    __syncwarp();
-}
-// Evaluates items [first, first + n) (n <= 32, one per lane) and adds the results to the owners' accumulators. The
-// leftover of the queue ([0, first)) stays in place: the caller drains from the top.
-__device__ __noinline__ void b2_drain(const ItemQueue2 &iq, int first, int n, float eps, float (*sacc)[2]) {
-    const int lane = threadIdx.x & 31;
+    float a0 = 0.f, a1 = 0.f;
+    int owner = 32 + lane, nr = 0;
+    float x = 0.f, K0 = 0.f, K1 = 0.f;
+    unsigned meta = 0, where = 0;
     if (lane < n) {
-        const int s_ = first + lane;
-        const unsigned rng = iq.range[s_];
-        float a0, a1;
-        eval_item_k(iq.x[s_], iq.K0[s_], iq.K1[s_], iq.G[s_], rng & 0xfffu, (rng >> 12) & 0xfffu, (rng >> 24) & 1u,
-                    (rng >> 25) & 1u, eps, a0, a1);
-        const int owner = rng >> 26;
-        if (a0 != 0.f) atomicAdd(&sacc[owner][0], a0);
-        if (a1 != 0.f) atomicAdd(&sacc[owner][1], a1);
+        const int s_ = (head + lane) & (B2_QCAP - 1);
+        x = sq.x[s_]; K0 = sq.K0[s_]; K1 = sq.K1[s_]; meta = sq.meta[s_]; where = sq.where[s_];
+        owner = (meta >> 2) & 31;
+        nr = meta >> 10;
+    }
+    const uint2 *rl = runs + (long)(where >> 20) * RCAP + ((meta >> 7) & 7u);
+    const int ra = where & 0x3ffu, rc = (where >> 10) & 0x3ffu;
+    const int rounds = __reduce_max_sync(FULL, nr);
+    for (int k = 0; k < rounds; ++k) {
+        if (k < nr) {
+            const uint2 run = __ldg(rl + k);
+            float t0, t1;
+            eval_item(x, K0, K1, __uint_as_float(run.y), max(ra, (int)(run.x & 0xffffu)), min(rc, (int)(run.x >> 16)),
+                      meta & 1u, meta & 2u, 1.f, eps, t0, t1);
+            a0 += t0; a1 += t1;
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float v0 = __shfl_down_sync(FULL, a0, o), v1 = __shfl_down_sync(FULL, a1, o);
+        const int ow = __shfl_down_sync(FULL, owner, o);
+        if (lane + o < 32 && ow == owner) { a0 += v0; a1 += v1; }
+    }
+    const int prev_owner = __shfl_up_sync(FULL, owner, 1);
+    if (owner < 32 && (lane == 0 || prev_owner != owner)) {
+        sacc[owner][0] += a0;
+        sacc[owner][1] += a1;
     }
     __syncwarp();
 }
@@ -1757,15 +1752,14 @@ raster_bwd2_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__
     __shared__ uint32_t list[B2_CAP];
     __shared__ int wsum[NWARPS];
     __shared__ SweepSrc S;
-    __shared__ ItemQueue2 iq2[NWARPS];
     __shared__ float sacc[NWARPS][32][2];
+    __shared__ SweepQueue2 sq2[NWARPS];
     __shared__ TaskStash stash[NWARPS];
     __shared__ unsigned short pairs[NWARPS][B2_PAIRS];
     const int b = blockIdx.y;
     const int W = is / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned FULL = 0xffffffffu;
-    int qcount = 0;
     brecs += (long)b * F;
     boxes += (long)b * F;
     grad_ndc += (long)b * V * 3;
@@ -1787,7 +1781,10 @@ raster_bwd2_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__
             const int4 q3 = __ldg(reinterpret_cast<const int4 *>(brecs + f) + 3);
             if (q3.w >= 0) {
                 const int fn = q3.w & BWD_FN_MASK;
-                bool boundary = q3.w & BWD_IRREGULAR;
+                const uint4 s4 = __ldg(reinterpret_cast<const uint4 *>(brecs + f) + 4);
+                const uint2 s5 = __ldg(reinterpret_cast<const uint2 *>(brecs + f) + 10);
+                // irregular faces and faces with a steep task (sweep ends extrapolated with large slopes) always sweep
+                bool boundary = (q3.w & BWD_IRREGULAR) || ((s4.x | s4.y | s4.z | s4.w | s5.x | s5.y) & (1u << 25));
                 if (!boundary) {
                     const FaceBox bx = boxes[f];   // clamped pixel bbox with one pixel of slack
                     const int w0 = bx.x0 >> 5, w1 = bx.x1 >> 5;
@@ -1796,6 +1793,14 @@ raster_bwd2_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__
                             const int lo = max((bx.x0 >> 3) - 4 * w, 0), hi = min((bx.x1 >> 3) - 4 * w, 3);
                             if (__ldg(cov_blocks + band * W + w) & ((0xfu >> (3 - hi)) & (0xfu << lo))) { boundary = true; break; }
                         }
+                    if (boundary) {   // some 8x8 block the box touches has a hole: look at the box itself
+                        boundary = false;
+                        for (int y = bx.y0; y <= bx.y1 && !boundary; ++y)
+                            for (int w = w0; w <= w1; ++w) {
+                                const int lo = max(bx.x0 - 32 * w, 0), hi = min(bx.x1 - 32 * w, 31);
+                                if (~__ldg(cov_row + y * W + w) & ((0xffffffffu >> (31 - hi)) & (0xffffffffu << lo))) { boundary = true; break; }
+                            }
+                    }
                 }
                 const bool vis0 = (__ldg(face_vis + (fn >> 5)) >> (fn & 31)) & 1u;
                 const bool both = q3.w & BWD_BOTH;
@@ -1803,8 +1808,6 @@ raster_bwd2_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__
                 fflags = (boundary ? 1u : 0u) | (vis0 ? 2u : 0u) | (both ? 4u : 0u) | (vis1 ? 8u : 0u);
                 const int copies = ((boundary || vis0) ? 1 : 0) + ((both && (boundary || vis1)) ? 1 : 0);
                 if (copies) {
-                    const uint4 s4 = __ldg(reinterpret_cast<const uint4 *>(brecs + f) + 4);
-                    const uint2 s5 = __ldg(reinterpret_cast<const uint2 *>(brecs + f) + 10);
                     const unsigned sp[6] = {s4.x, s4.y, s4.z, s4.w, s5.x, s5.y};
                     int tot = 0;
 #pragma unroll
@@ -1864,6 +1867,8 @@ raster_bwd2_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__
             //      segment's accumulators in shared memory.
             const int n_here = min(B2_CAP, total - lo);
             TaskStash &st = stash[warp];
+            SweepQueue2 &sq = sq2[warp];
+            int qhead = 0, qtail = 0;
             unsigned short *pr = pairs[warp];
             for (int j0 = warp * 32; j0 < n_here; j0 += NTHREADS) {
                 const int j = j0 + lane;
@@ -1885,14 +1890,16 @@ raster_bwd2_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__
                 // (a) bit q of `out`: the face owns the in-pixel of scan-line d0a + q and the line has missing coverage
                 //     beyond the out-pixel; bit q of `in`: a crossing of a face that can have in-sweeps
                 unsigned out = 0, in = 0;
-                {
-                    int own[B2_SEG];
-                    uint32_t inf[B2_SEG];
-                    int d1o[B2_SEG];
 #pragma unroll
-                    for (int q = 0; q < B2_SEG; ++q) {
-                        const int d0 = d0a + q;
-                        own[q] = -3; inf[q] = 0u; d1o[q] = 0;
+                for (int half = 0; half < B2_SEG / 4; ++half) {   // four scan-lines at a time; short segments stop early
+                    if (half > 0 && !__any_sync(FULL, d0b >= d0a + 4 * half)) break;
+                    int own[4];
+                    uint32_t inf[4];
+                    int d1o[4];
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int q = 4 * half + q4, d0 = d0a + q;
+                        own[q4] = -3; inf[q4] = 0u; d1o[q4] = 0;
                         if (d0 <= d0b) {
                             const float x = g.slope * ((float)d0 - g.p0d0) + g.p0d1;
                             const int d1_in = __float2int_rz(g.dir > 0 ? floorf(x) : ceilf(x));
@@ -1900,19 +1907,19 @@ raster_bwd2_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__
                             if ((unsigned)d1_in < (unsigned)is && (unsigned)d1_out < (unsigned)is) {
                                 if (bnd) in |= 1u << q;
                                 if (vis) {
-                                    own[q] = __ldg(face_index + (axis == 0 ? d1_in * is + d0 : d0 * is + d1_in));
-                                    inf[q] = __ldg(S.run_info + lN * is + d0);
-                                    d1o[q] = d1_out;
+                                    own[q4] = __ldg(face_index + (axis == 0 ? d1_in * is + d0 : d0 * is + d1_in));
+                                    inf[q4] = __ldg(S.run_info + lN * is + d0);
+                                    d1o[q4] = d1_out;
                                 }
                             }
                         }
                     }
 #pragma unroll
-                    for (int q = 0; q < B2_SEG; ++q) {
+                    for (int q4 = 0; q4 < 4; ++q4) {
                         // extent of the line's missing-coverage list against the sweep [d1_out, border]
-                        const int lo_ = (inf[q] >> 4) & 0xfffu, hi_ = inf[q] >> 16;
-                        const bool beyond = g.dir > 0 ? hi_ >= d1o[q] : lo_ <= d1o[q];
-                        if (own[q] == bf.fn && (inf[q] & 15u) && beyond) out |= 1u << q;
+                        const int lo_ = (inf[q4] >> 4) & 0xfffu, hi_ = inf[q4] >> 16;
+                        const bool beyond = g.dir > 0 ? hi_ >= d1o[q4] : lo_ <= d1o[q4];
+                        if (own[q4] == bf.fn && (inf[q4] & 15u) && beyond) out |= 1u << (4 * half + q4);
                     }
                 }
                 // (b) compaction: pair = lane | q << 5 | in-sweep << 8
@@ -1934,8 +1941,8 @@ raster_bwd2_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__
                 }
                 __syncwarp();
                 for (int i0 = 0; i0 < npairs; i0 += 32) {
-                    unsigned todo = 0, flags = 0;
-                    int ra = 0, rc = 0, ls = 0, d0 = 0, owner = 0;
+                    unsigned flags = 0;
+                    int ra = 0, rc = 0, ls = 0, d0 = 0, owner = 0, r0 = 0, nr = 0;
                     float x = 0.f, K0 = 0.f, K1 = 0.f;
                     if (i0 + lane < npairs) {
                         const unsigned pw = pr[i0 + lane];
@@ -1975,27 +1982,52 @@ raster_bwd2_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__
                                 if (ra > rc) info = 0u;
                             }
                         }
-                        todo = sweep_todo(S, ls, d0, info, ra, rc, walk);
-                        if (todo) {
+                        // runs of the line's list with pixels inside [ra, rc]: the lists are sorted, so they are
+                        // neighbours [r0, r0 + nr)
+                        const unsigned cnt = info & 15u;
+                        if (cnt != 0u && rc >= (int)((info >> 4) & 0xfffu) && ra <= (int)(info >> 16)) {
+                            const uint2 *rl = S.runs + (ls * is + d0) * RCAP;
+                            if (cnt == RUN_OVERFLOW || walk) {
+                                nr = -1;
+                            } else {
+                                for (unsigned r = 0; r < cnt; ++r) {
+                                    const unsigned se = __ldg(&rl[r].x);
+                                    if (rc >= (int)(se & 0xffffu) && ra <= (int)(se >> 16)) {
+                                        if (nr == 0) r0 = r;
+                                        ++nr;
+                                    }
+                                }
+                            }
+                        }
+                        if (nr) {
                             const float ka = p1d0 - p0d0;
                             K0 = __fdividef(ka, p1d0 - fd0) * S.inv_is2;
                             K1 = __fdividef(ka, fd0 - p0d0) * S.inv_is2;
                         }
-                        if (todo & SWEEP_WALK) {   // rare: in place
+                        if (nr < 0) {   // rare: run list overflowed or straddling sweep, walk the bit line in place
                             float a0 = 0.f, a1 = 0.f;
                             sweep_walk(S, ls, d0, ra, rc, x, K0, K1, flags, a0, a1);
                             if (a0 != 0.f) atomicAdd(&sacc[warp][owner][0], a0);
                             if (a1 != 0.f) atomicAdd(&sacc[warp][owner][1], a1);
-                            todo = 0;
+                            nr = 0;
                         }
                     }
-                    __syncwarp();
-                    while (__any_sync(FULL, todo != 0u)) {
-                        b2_push(iq2[warp], qcount, todo, S.runs + ((long)ls * is + d0) * RCAP, ra, rc, x, K0, K1, flags, owner);
-                        if (qcount >= 32) { b2_drain(iq2[warp], qcount - 32, 32, S.eps, sacc[warp]); qcount -= 32; }
+                    // (c) sweeps with runs go to the warp's queue in pair order (the sweeps of one segment stay
+                    //     neighbours); 32 are evaluated at a time
+                    {
+                        const unsigned m = __ballot_sync(FULL, nr > 0);
+                        if (nr > 0) {
+                            const int at = (qtail + __popc(m & ((1u << lane) - 1u))) & (B2_QCAP - 1);
+                            sq.x[at] = x; sq.K0[at] = K0; sq.K1[at] = K1;
+                            sq.meta[at] = flags | ((unsigned)owner << 2) | ((unsigned)r0 << 7) | ((unsigned)nr << 10);
+                            sq.where[at] = (unsigned)ra | ((unsigned)rc << 10) | ((unsigned)(ls * is + d0) << 20);
+                        }
+                        qtail += __popc(m);
+                        __syncwarp();
+                        if (qtail - qhead >= 32) { b2_drain(sq, qhead, 32, S.runs, S.eps, sacc[warp]); qhead += 32; }
                     }
                 }
-                if (qcount > 0) { b2_drain(iq2[warp], 0, qcount, S.eps, sacc[warp]); qcount = 0; }
+                if (qtail > qhead) { b2_drain(sq, qhead, qtail - qhead, S.runs, S.eps, sacc[warp]); qhead = qtail; }
                 __syncwarp();
                 // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
                 const float acc0 = sacc[warp][lane][0], acc1 = sacc[warp][lane][1];
