@@ -11,7 +11,6 @@
 // The file is compiled with -fmad=false: coverage / ownership predicates are evaluated with the same
 // individually rounded fp32 operations as the CPU oracle so that face_index maps agree bit for bit.
 #include "common.cuh"
-#include <stdlib.h>
 
 namespace {
 
@@ -937,12 +936,6 @@ __device__ __forceinline__ void eval_item(float x, float c0, float c1, float G, 
     a1 = has1 ? -G * h1 : 0.f;
 }
 
-// eval_item with the 2 / is scale already in the coefficients.
-__device__ __forceinline__ void eval_item_k(float x, float K0, float K1, float G, int s, int e, bool has0, bool has1,
-                                            float eps, float &a0, float &a1) {
-    eval_item(x, K0, K1, G, s, e, has0, has1, 1.f, eps, a0, a1);
-}
-
 // @region sweep_bits
 // Bit-line walk for lines whose run list overflowed: visits the set bits of `line` in [a, c].
 __device__ __noinline__ void sweep_bits(const uint32_t *line, int a, int c, int axis, int d0, float d1_cross,
@@ -975,42 +968,8 @@ __device__ __noinline__ void sweep_bits(const uint32_t *line, int a, int c, int 
     }
 }
 
-// ------------------------------------------------------------------------------------------ backward kernel
-// backward_pixel_map visits, per (face, edge, axis, scan-line) crossing, an out-sweep (only when the face owns the
-// in-pixel) and an in-sweep (always). Enumerating every crossing costs far more than the sweeps that contribute, so
-// the kernel finds the contributing crossings from the data instead (scripts/proto/bwd_proto.c is the scalar model
-// of this enumeration, checked against the oracle on the adversarial inputs):
-//
-//  role A, CTA per (image, 64x64 tile) - OUT-SWEEPS FROM THE PIXELS. The in-pixel of an out-sweep is owned by the
-//     face and sits at most one pixel before the end of a span of the face_index map along the sweep direction (the
-//     pixel two steps further lies more than a pixel outside the edge, and the coverage predicate and the crossing
-//     arithmetic agree to ~1e-2 px when |slope| <= SMAX). So every span end (owner changes between neighbouring
-//     pixels: one ballot per row and direction) that has missing-coverage pixels beyond it looks up the three edges
-//     of its owner; the edge whose crossing has this in-pixel sweeps the run list of the line. ~1 candidate per real
-//     out-sweep instead of ~8 enumerated crossings.
-//  role B, thread per face - IN-SWEEPS AND STEEP TASKS. An in-sweep reads alpha at the out-pixel and mismatch pixels
-//     inside the triangle's span: a face whose pixel bounding box is fully covered cannot contribute (alpha_out = 1
-//     selects the missing-coverage list, which is empty on covered pixels), unless a corner sits exactly on an integer
-//     pixel coordinate (the reference then extrapolates the far end of the sweep from an edge that does not span the
-//     line: "irregular" faces are never skipped). Only faces at the silhouette are enumerated. Tasks with
-//     |slope| > SMAX (at most a few lines long) take their out-sweeps here too, tested with face_index as the
-//     reference does.
-// Per-crossing sums stay in registers; role A merges the crossings of one (face, edge, axis) task inside a warp
-// (match.any) before the global atomicAdd into grad_ndc (the vertices_to_faces scatter-add is fused).
+// ------------------------------------------------------------------------------------------ backward geometry
 // @region geom
-constexpr float SMAX = BWD_SMAX;
-constexpr int FIS = TILE + 8;           // row stride of the face_index tile (ints): pixel (x, y) at (y + 1) * FIS + 4 + x,
-constexpr int FIX0 = 4;                 //   one-pixel halo all round, rows 16-byte aligned
-constexpr int CQCAP = 32 + 8 * TILE;    // per-warp candidate queue: a leftover batch + one tile row of candidates
-constexpr int BFACES = NTHREADS;        // faces per CTA of the face kernel
-constexpr int IQCAP = 64;               // per-warp queue of (crossing, run) items
-struct ItemQueue {
-    float x[IQCAP], c0[IQCAP], c1[IQCAP], G[IQCAP];   // crossing position, distance coefficients, run weight
-    unsigned range[IQCAP];                            // pixels of the run inside the sweep: s | e << 16
-    unsigned key[IQCAP];                              // (owner * 3 + edge) * 2 + axis
-    unsigned meta[IQCAP];                             // d0 | axis << 12 | has0 << 13 | has1 << 14 | walk << 15
-};
-
 struct TaskGeom {
     float p0d0, p0d1, p1d0, p2d0, p2d1, slope, s02, s21, ka;
     int dir, d0_from, d0_to, vid0, vid1;
@@ -1097,531 +1056,6 @@ __device__ __forceinline__ SweepSrc sweep_src(int b, int is, int aa, float eps, 
     return S;
 }
 
-// @region sweep_line
-// Sum over the pixels of list `ls` (0 mn_row, 1 mp_row, 2 mn_col, 3 mp_col) on line d0 inside [ra, rc], seen from the
-// crossing at x. `walk`: visit the bit line pixel by pixel (run list overflowed, or the sweep straddles its crossing).
-// The rare, lane-divergent path (in-sweeps, second edges): not inlined, the hot kernels stay small.
-__device__ __noinline__ void sweep_line(const SweepSrc &S, int ls, int d0, int ra, int rc, float x, float c0, float c1,
-                                        bool has0, bool has1, bool walk, float &acc0, float &acc1) {
-    const uint32_t info = __ldg(S.run_info + ls * S.is + d0);
-    const unsigned cnt = info & 15u;
-    if (cnt == 0u) return;
-    if (rc < (int)((info >> 4) & 0xfffu) || ra > (int)(info >> 16)) return;  // no listed pixel inside the sweep
-    if (cnt == RUN_OVERFLOW || walk) {
-        const int col = ls >> 1;
-        const uint32_t *line = (col ? S.m_col : S.m_row) + ((long)(ls & 1) * S.is + d0) * S.W;
-        sweep_bits(line, ra, rc, col ? 0 : 1, d0, x, c0, c1, has0, has1, S.ctx, acc0, acc1);
-        return;
-    }
-    const uint2 *rl = S.runs + ((long)ls * S.is + d0) * RCAP;
-    for (unsigned r = 0; r < cnt; ++r) {
-        const uint2 run = __ldg(rl + r);
-        const int s = max(ra, (int)(run.x & 0xffffu)), e = min(rc, (int)(run.x >> 16));
-        if (s > e) continue;
-        float a0, a1;
-        eval_item(x, c0, c1, __uint_as_float(run.y), s, e, has0, has1, S.inv_is2, S.eps, a0, a1);
-        acc0 += a0;
-        acc1 += a1;
-    }
-}
-
-// @region items
-// ---- the (crossing, run) item pipeline shared by the two backward kernels: a per-warp ring of IQCAP items
-// Queues one item per lane and round (bit r of `todo` = run r of the line's list overlaps the sweep [ra, rc]; with
-// META_WALK the single item is the whole sweep, walked on the bit line). The caller drains when count >= 32.
-constexpr unsigned META_WALK = 1u << 15, META_PLANE = 1u << 16;
-template <bool SH>
-__device__ __forceinline__ void push_round(ItemQueue &iq, int head, int &count, unsigned &todo, const uint2 *rl, int ra,
-                                           int rc, float x, float c0, float c1, unsigned key, unsigned meta, int lane) {
-    const bool it = todo != 0u;
-    const unsigned m = __ballot_sync(0xffffffffu, it);
-    if (it) {
-        const int r = __ffs(todo) - 1;
-        todo &= todo - 1;
-        unsigned rng = (unsigned)ra | ((unsigned)rc << 16);
-        float G = 0.f;
-        if (!(meta & META_WALK)) {
-            const uint2 run = SH ? rl[r] : __ldg(rl + r);
-            rng = (unsigned)max(ra, (int)(run.x & 0xffffu)) | ((unsigned)min(rc, (int)(run.x >> 16)) << 16);
-            G = __uint_as_float(run.y);
-        }
-        const int pos = (head + count + __popc(m & ((1u << lane) - 1u))) & (IQCAP - 1);
-        iq.x[pos] = x; iq.c0[pos] = c0; iq.c1[pos] = c1; iq.G[pos] = G;
-        iq.range[pos] = rng; iq.key[pos] = key; iq.meta[pos] = meta;
-    }
-    count += __popc(m);
-    __syncwarp();
-}
-
-// Bits of the runs of a line's list (`info` = its run_counts word, rl = its runs, in shared or global memory) that have
-// pixels inside [ra, rc] (clipped to the list's extent); 1 + META_WALK when the list overflowed or `walk` is set.
-template <bool SH>
-__device__ __forceinline__ unsigned runs_in_sweep_of(uint32_t info, const uint2 *rl, int &ra, int &rc, bool walk,
-                                                     unsigned &meta) {
-    const unsigned cnt = info & 15u;
-    const int lo = (info >> 4) & 0xfffu, hi = info >> 16;
-    if (cnt == 0u || rc < lo || ra > hi) return 0u;
-    if (cnt == RUN_OVERFLOW || walk) {
-        meta |= META_WALK;
-        ra = max(ra, lo); rc = min(rc, hi);
-        return 1u;
-    }
-    unsigned todo = 0;
-    for (unsigned r = 0; r < cnt; ++r) {
-        const unsigned se = SH ? rl[r].x : __ldg(&rl[r].x);
-        if (rc >= (int)(se & 0xffffu) && ra <= (int)(se >> 16)) todo |= 1u << r;
-    }
-    return todo;
-}
-// The same for list `ls`, line d0 of the image (global memory); rl receives the run list.
-__device__ __forceinline__ unsigned runs_in_sweep(const SweepSrc &S, int ls, int d0, int &ra, int &rc, bool walk,
-                                                  unsigned &meta, const uint2 *&rl) {
-    rl = S.runs + ((long)ls * S.is + d0) * RCAP;
-    return runs_in_sweep_of<false>(__ldg(S.run_info + ls * S.is + d0), rl, ra, rc, walk, meta);
-}
-
-// Evaluates the first `n` (<= 32) queued items, one per lane. Items of one (face, edge, axis) task met in the batch are
-// summed inside the warp (match.any + pointer jumping over the peers) and leave as one atomicAdd per vertex slot.
-// Not inlined: one copy of the evaluation code per kernel (the backward is bound by instruction fetch otherwise); the
-// caller advances head / count by n.
-__device__ __noinline__ void drain_items(const ItemQueue &iq, int head, int n, const SweepSrc *Sp, const BwdRec *brecs,
-                                         int F, float *grad_ndc) {
-    const unsigned FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const SweepSrc &S = *Sp;
-    unsigned key = 0x80000000u | lane;
-    float a0 = 0.f, a1 = 0.f;
-    if (lane < n) {
-        const int s = (head + lane) & (IQCAP - 1);
-        const unsigned meta = iq.meta[s], rng = iq.range[s];
-        const int d0 = meta & 0xfffu, axis = (meta >> 12) & 1u;
-        const bool has0 = (meta >> 13) & 1u, has1 = (meta >> 14) & 1u;
-        const int ra = rng & 0xffffu, rc = rng >> 16;
-        key = iq.key[s];
-        if (meta & META_WALK) {   // run list overflowed, or the sweep straddles its crossing: walk the bit line
-            const uint32_t *line = (axis == 0 ? S.m_col : S.m_row) + ((long)((meta >> 16) & 1u) * S.is + d0) * S.W;
-            sweep_bits(line, ra, rc, axis, d0, iq.x[s], iq.c0[s], iq.c1[s], has0, has1, S.ctx, a0, a1);
-        } else {
-            eval_item(iq.x[s], iq.c0[s], iq.c1[s], iq.G[s], ra, rc, has0, has1, S.inv_is2, S.eps, a0, a1);
-        }
-    }
-    const unsigned peers = __match_any_sync(FULL, key);
-    if (__any_sync(FULL, peers & (peers - 1u))) {   // some task has several items here: suffix sums along the peers
-        const unsigned higher = lane == 31 ? 0u : peers & (0xffffffffu << (lane + 1));
-        int nxt = higher ? __ffs(higher) - 1 : -1;
-#pragma unroll
-        for (int r = 0; r < 5; ++r) {
-            const int src = nxt < 0 ? lane : nxt;
-            const float t0 = __shfl_sync(FULL, a0, src), t1 = __shfl_sync(FULL, a1, src);
-            const int tn = __shfl_sync(FULL, nxt, src);
-            if (nxt >= 0) { a0 += t0; a1 += t1; nxt = tn; }
-        }
-    }
-    if (lane < n && lane == __ffs(peers) - 1 && (a0 != 0.f || a1 != 0.f)) {
-        // key = (owner * 3 + edge) * 2 + axis: the two vertices of the edge come from the owner's record
-        const int own = (int)(key / 6u), e = (int)((key >> 1) % 3u), axis = (int)(key & 1u);
-        const int4 q3 = __ldg(reinterpret_cast<const int4 *>(brecs + (own >= F ? own - F : own)) + 3);
-        const bool rev = (q3.w & BWD_FN_MASK) != own;   // the reversed copy of a both-windings face
-        const int v0 = rev ? q3.z : q3.x, v1 = q3.y, v2 = rev ? q3.x : q3.z;
-        const int vid0 = e == 0 ? v0 : e == 1 ? v1 : v2, vid1 = e == 0 ? v1 : e == 1 ? v2 : v0;
-        // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
-        if (a0 != 0.f) atomicAdd(grad_ndc + (long)vid0 * 3 + (1 - axis), a0);
-        if (a1 != 0.f) atomicAdd(grad_ndc + (long)vid1 * 3 + (1 - axis), a1);
-    }
-    __syncwarp();
-}
-#define DRAIN(n_)                                                         \
-    do {                                                                  \
-        const int dn__ = (n_);                                            \
-        drain_items(iq, head, dn__, &S, brecs, F, grad_ndc);              \
-        head = (head + dn__) & (IQCAP - 1);                               \
-        count -= dn__;                                                    \
-    } while (0)
-
-// @region face_setup
-// ------------------------------------------------------------------ face side: in-sweeps and steep tasks
-// Thread per face: is it at the silhouette (an uncovered pixel in its pixel bounding box) or irregular, which of its
-// tasks are steep. Then warp per listed face: the scan-lines of its six (edge, axis) tasks are flattened over the
-// lanes, every lane tests one crossing, contributing crossings queue (crossing, run) items.
-__device__ __forceinline__ void
-raster_bwd_face_role(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
-                     float eps, const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
-                     const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ cov_col,
-                     const uint32_t *__restrict__ m_row, const uint32_t *__restrict__ m_col,
-                     const uint2 *__restrict__ runs, const uint32_t *__restrict__ run_info,
-                     float *__restrict__ grad_ndc, unsigned *flist, int &n_list, ItemQueue *iqs, SweepSrc &S) {
-    const int b = blockIdx.y;
-    const int W = is / 32;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned FULL = 0xffffffffu;
-    brecs += (long)b * F;
-    boxes += (long)b * F;
-    grad_ndc += (long)b * V * 3;
-    face_index += (long)b * is * is;
-    cov_row += (long)b * is * W;
-    cov_col += (long)b * is * W;
-    if (threadIdx.x == 0) {
-        S = sweep_src(b, is, aa, eps, grad_alpha, m_row, m_col, runs, run_info);
-        n_list = 0;
-    }
-    __syncthreads();
-    {
-        const int f = blockIdx.x * BFACES + threadIdx.x;
-        if (f < F) {
-            const int4 q3 = __ldg(reinterpret_cast<const int4 *>(brecs + f) + 3);
-            if (q3.w >= 0) {
-                const uint4 s4 = __ldg(reinterpret_cast<const uint4 *>(brecs + f) + 4);
-                const uint2 s5 = __ldg(reinterpret_cast<const uint2 *>(brecs + f) + 10);
-                const unsigned sp[6] = {s4.x, s4.y, s4.z, s4.w, s5.x, s5.y};
-                unsigned steep = 0;
-#pragma unroll
-                for (int t = 0; t < 6; ++t) steep |= ((sp[t] >> 25) & 1u) << t;
-                bool boundary = q3.w & BWD_IRREGULAR;
-                if (!boundary) {
-                    const FaceBox bx = boxes[f];  // clamped pixel bbox with one pixel of slack
-                    const int w0 = bx.x0 >> 5, w1 = bx.x1 >> 5;
-                    for (int y = bx.y0; y <= bx.y1 && !boundary; ++y)
-                        for (int w = w0; w <= w1; ++w) {
-                            const int lo = max(bx.x0 - 32 * w, 0), hi = min(bx.x1 - 32 * w, 31);
-                            const unsigned m = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
-                            if (~__ldg(cov_row + (long)y * W + w) & m) { boundary = true; break; }
-                        }
-                }
-                if (boundary || steep) {
-                    const unsigned ent = (unsigned)threadIdx.x | (boundary ? 1u << 9 : 0u);
-                    const int both = (q3.w & BWD_BOTH) ? 1 : 0;
-                    const int at = atomicAdd(&n_list, 1 + both);
-                    flist[at] = ent | (steep << 10);
-                    // the reversed copy F + f of a both-windings face: edges 0 and 1 trade places
-                    if (both) flist[at + 1] = ent | (1u << 8) | ((((steep >> 2) & 3u) | ((steep & 3u) << 2) | (steep & 0x30u)) << 10);
-                }
-            }
-        }
-    }
-    __syncthreads();
-// @region face_tasks
-    ItemQueue &iq = iqs[warp];
-    int head = 0, count = 0;
-    const int nl = n_list;
-    for (int j = warp; j < nl; j += NWARPS) {
-        const unsigned ent = flist[j];
-        const bool copy = (ent >> 8) & 1u, boundary = (ent >> 9) & 1u;
-        const unsigned steep_mask = (ent >> 10) & 0x3fu;
-        const BwdRec *rp = brecs + blockIdx.x * BFACES + (ent & 0xffu);
-        BwdFace bf = load_bwd_face(rp);   // (warp-uniform address: one broadcast load)
-        const uint4 s4 = __ldg(reinterpret_cast<const uint4 *>(rp) + 4);
-        const uint2 s5 = __ldg(reinterpret_cast<const uint2 *>(rp) + 10);
-        unsigned sp[6] = {s4.x, s4.y, s4.z, s4.w, s5.x, s5.y};
-        if (copy) {
-            reverse_bwd_face(bf, F);
-            unsigned t = sp[0]; sp[0] = sp[2]; sp[2] = t;
-            t = sp[1]; sp[1] = sp[3]; sp[3] = t;
-        }
-        // scan-lines of the six tasks (in-sweeps: all tasks of a silhouette face; otherwise only the steep tasks)
-        int from[6], pre[7];
-        pre[0] = 0;
-#pragma unroll
-        for (int t = 0; t < 6; ++t) {
-            from[t] = sp[t] & 0xfffu;
-            const int len = (int)((sp[t] >> 12) & 0xfffu) - from[t] + 1;
-            pre[t + 1] = pre[t] + ((boundary || ((steep_mask >> t) & 1u)) ? max(len, 0) : 0);
-        }
-        const int N = pre[6];
-        for (int base = 0; base < N; base += 32) {
-            const int i = base + lane;
-            unsigned todo_in = 0, todo_out = 0, key = 0, meta_in = 0, meta_out = 0;
-            const uint2 *rl_in = S.runs, *rl_out = S.runs;
-            float x = 0.f, c0 = 0.f, c1 = 0.f;
-            int ra_in = 0, rc_in = 0, ra_out = 0, rc_out = 0;
-            if (i < N) {
-                const int t = (i >= pre[1]) + (i >= pre[2]) + (i >= pre[3]) + (i >= pre[4]) + (i >= pre[5]);
-                const int tf = t == 0 ? from[0] : t == 1 ? from[1] : t == 2 ? from[2] : t == 3 ? from[3] : t == 4 ? from[4] : from[5];
-                const int tp = t == 0 ? pre[0] : t == 1 ? pre[1] : t == 2 ? pre[2] : t == 3 ? pre[3] : t == 4 ? pre[4] : pre[5];
-                const int d0 = tf + (i - tp), e = t >> 1, axis = t & 1;
-                const TaskGeom g = task_geom(bf, e, axis, is);
-                const float fd0 = (float)d0;
-                x = g.slope * (fd0 - g.p0d0) + g.p0d1;
-                const int d1_in = __float2int_rz(g.dir > 0 ? floorf(x) : ceilf(x));
-                const int d1_out = d1_in + g.dir;
-                if ((unsigned)d1_in < (unsigned)is && (unsigned)d1_out < (unsigned)is) {
-                    const int lN = axis == 0 ? 2 : 0;
-                    const unsigned meta = (unsigned)d0 | ((unsigned)axis << 12) | (g.p1d0 != fd0 ? 1u << 13 : 0u) |
-                                          (g.p0d0 != fd0 ? 1u << 14 : 0u);
-                    key = (unsigned)((bf.fn * 3 + e) * 2 + axis);
-                    if ((steep_mask >> t) & 1u) {   // out-sweep of a steep task: the reference's own ownership test
-                        const int own = axis == 0 ? __ldg(face_index + (long)d1_in * is + d0)
-                                                  : __ldg(face_index + (long)d0 * is + d1_in);
-                        if (own == bf.fn) {
-                            const int lim = g.dir > 0 ? is - 1 : 0;
-                            ra_out = min(d1_out, lim); rc_out = max(d1_out, lim);
-                            meta_out = meta;
-                            todo_out = runs_in_sweep(S, lN, d0, ra_out, rc_out, false, meta_out, rl_out);
-                        }
-                    }
-                    if (boundary) {
-                        // in-sweep: from the in-pixel to the opposite edge of the triangle; most find nothing to sweep
-                        const uint32_t *cov = axis == 0 ? cov_col : cov_row;   // coverage words of line d0 along d1
-                        const bool alpha_out = (__ldg(cov + (long)d0 * W + (d1_out >> 5)) >> (d1_out & 31)) & 1u;
-                        const int ls = alpha_out ? lN : lN + 1;
-                        if ((__ldg(S.run_info + ls * is + d0) & 15u) != 0u) {
-                            float c2;
-                            if ((fd0 - g.p0d0) * (fd0 - g.p2d0) < 0.f) c2 = g.s02 * (fd0 - g.p0d0) + g.p0d1;
-                            else c2 = g.s21 * (fd0 - g.p2d0) + g.p2d1;
-                            const int lim = __float2int_rz(g.dir > 0 ? ceilf(c2) : floorf(c2));
-                            ra_in = max(min(d1_in, lim), 0); rc_in = min(max(d1_in, lim), is - 1);
-                            if (ra_in <= rc_in) {
-                                // an in-sweep can straddle its crossing: by a pixel when the triangle is thinner than a
-                                // pixel there (eval_item copes with NEAR_N - 1 pixels on the near side), by many when
-                                // its far end is extrapolated (irregular faces): the closed form assumes one side, such
-                                // a sweep walks the bit line
-                                const bool walk = (float)ra_in < x - (float)(NEAR_N - 1) && (float)rc_in > x;
-                                meta_in = meta | (alpha_out ? 0u : META_PLANE);
-                                todo_in = runs_in_sweep(S, ls, d0, ra_in, rc_in, walk, meta_in, rl_in);
-                            }
-                        }
-                    }
-                    if (todo_in | todo_out) { c0 = __fdividef(g.ka, g.p1d0 - fd0); c1 = __fdividef(g.ka, fd0 - g.p0d0); }
-                }
-            }
-            while (__any_sync(FULL, todo_in != 0u)) {
-                push_round<false>(iq, head, count, todo_in, rl_in, ra_in, rc_in, x, c0, c1, key, meta_in, lane);
-                if (count >= 32) DRAIN(32);
-            }
-            while (__any_sync(FULL, todo_out != 0u)) {
-                push_round<false>(iq, head, count, todo_out, rl_out, ra_out, rc_out, x, c0, c1, key, meta_out, lane);
-                if (count >= 32) DRAIN(32);
-            }
-        }
-    }
-    if (count > 0) DRAIN(count);
-}
-
-// @region pix_prologue
-// ------------------------------------------------------------------ pixel side: out-sweeps
-__device__ __forceinline__ void
-raster_bwd_tile_role(int tile, const BwdRec *__restrict__ brecs, int F, int V, int is, int aa, float eps,
-                     const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
-                     const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ m_row,
-                     const uint32_t *__restrict__ m_col, const uint2 *__restrict__ runs,
-                     const uint32_t *__restrict__ run_info, float *__restrict__ grad_ndc, int *fi,
-                     unsigned short (*cq)[CQCAP], uint32_t *ext_row, uint32_t *ext_col, ItemQueue *iqs, SweepSrc &S,
-                     uint2 *sruns, uint64_t *bar) {
-    const int b = blockIdx.y;
-    const int W = is / 32;
-    const int tiles_x = is / TILE;
-    const int tx0 = (tile % tiles_x) * TILE, ty0 = (tile / tiles_x) * TILE;
-    // ---- nothing to do when the tile is empty or no line through it has missing coverage
-    {
-        bool any_cov = false, any_miss = false;
-        if (threadIdx.x < 2 * TILE) {
-            const int r = threadIdx.x >> 1, w = threadIdx.x & 1;
-            any_cov = __ldg(cov_row + ((long)b * is + ty0 + r) * W + (tx0 >> 5) + w) != 0u;
-        }
-        if (threadIdx.x < TILE) {
-            const uint32_t *ri = run_info + (long)b * 4 * is;
-            const uint32_t er = __ldg(ri + ty0 + threadIdx.x), ec = __ldg(ri + 2 * is + tx0 + threadIdx.x);
-            ext_row[threadIdx.x] = (er & 15u) ? er : 0x0000fff0u;   // empty list: lo = 4095, hi = 0
-            ext_col[threadIdx.x] = (ec & 15u) ? ec : 0x0000fff0u;
-            any_miss = ((er | ec) & 15u) != 0u;
-        }
-        const int cov_any = __syncthreads_or(any_cov);
-        const int miss_any = __syncthreads_or(any_miss);
-        if (!cov_any || !miss_any) return;
-    }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned FULL = 0xffffffffu;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    brecs += (long)b * F;
-    grad_ndc += (long)b * V * 3;
-    face_index += (long)b * is * is;
-    if (threadIdx.x == 0) {   // (barrier below)
-        S = sweep_src(b, is, aa, eps, grad_alpha, m_row, m_col, runs, run_info);
-        // the missing-coverage run lists of the tile's 64 rows and 64 columns: two contiguous 4 KB blocks (TMA bulk copies)
-        mbar_init(bar, 1);
-        mbar_fence_init();
-        mbar_expect_tx(bar, (uint32_t)(2 * TILE * RCAP * sizeof(uint2)));
-        tma_bulk_g2s(sruns, runs + (((long)b * 4 + 0) * is + ty0) * RCAP, TILE * RCAP * sizeof(uint2), bar);
-        tma_bulk_g2s(sruns + TILE * RCAP, runs + (((long)b * 4 + 2) * is + tx0) * RCAP, TILE * RCAP * sizeof(uint2), bar);
-    }
-// @region pix_load
-    // ---- face_index tile with a one-pixel halo (-2 outside the image: never equal to an owner)
-    for (int i = threadIdx.x; i < TILE * TILE / 4; i += NTHREADS) {
-        const int r = i / (TILE / 4), c4 = i % (TILE / 4);
-        const int4 v = __ldg(reinterpret_cast<const int4 *>(face_index + (long)(ty0 + r) * is + tx0) + c4);
-        *reinterpret_cast<int4 *>(fi + (r + 1) * FIS + FIX0 + 4 * c4) = v;
-    }
-    {
-        const int side = threadIdx.x >> 6, k = threadIdx.x & 63;   // rows above / below, columns left / right
-        int yy, xx;
-        if (side == 0) { yy = -1; xx = k; } else if (side == 1) { yy = TILE; xx = k; }
-        else if (side == 2) { yy = k; xx = -1; } else { yy = k; xx = TILE; }
-        const int gy = ty0 + yy, gx = tx0 + xx;
-        fi[(yy + 1) * FIS + FIX0 + xx] = ((unsigned)gy < (unsigned)is && (unsigned)gx < (unsigned)is)
-                                            ? __ldg(face_index + (long)gy * is + gx) : -2;
-    }
-    __syncthreads();
-    mbar_wait(bar, 0);
-
-    unsigned short *q = cq[warp];
-    ItemQueue &iq = iqs[warp];
-    int qn = 0, head = 0, count = 0;   // queued candidates; ring of queued items
-
-// @region pix_process
-    // Turns `n` (<= 32) queued candidates, one per lane, into (crossing, run) items.
-    auto process = [&](int n) {
-        bool matched = false;
-        float x = 0.f, c0 = 0.f, c1 = 0.f;
-        unsigned key = 0, meta = 0;
-        int ra = 0, rc = 0;
-        if (lane < n) {
-            const unsigned c = q[lane];
-            const int xl = c & 63, yl = (c >> 6) & 63, axis = (c >> 12) & 1, dirbit = (c >> 13) & 1;
-            const int dir = dirbit ? 1 : -1;
-            const int own = fi[(yl + 1) * FIS + FIX0 + xl];
-            const BwdRec *rp = brecs + (own >= F ? own - F : own);
-            // per-edge scan-line spans of this axis: d0_from | d0_to << 12 | dir > 0 << 24 | steep << 25
-            const uint4 s4 = __ldg(reinterpret_cast<const uint4 *>(rp) + 4);
-            const uint2 s5 = __ldg(reinterpret_cast<const uint2 *>(rp) + 10);
-            const int meta_fn = __ldg(reinterpret_cast<const int *>(rp) + 15);
-            const bool rev = (meta_fn & BWD_FN_MASK) != own;   // the reversed copy F + f of a both-windings face
-            unsigned sp[3] = {axis ? s4.y : s4.x, axis ? s4.w : s4.z, axis ? s5.y : s5.x};
-            if (rev) {   // edges 0 and 1 trade places and every edge is walked backwards
-                const unsigned t = sp[0]; sp[0] = sp[1]; sp[1] = t;
-                sp[0] ^= 1u << 24; sp[1] ^= 1u << 24; sp[2] ^= 1u << 24;
-            }
-            const int d0 = axis == 0 ? tx0 + xl : ty0 + yl, q0 = axis == 0 ? ty0 + yl : tx0 + xl;
-            unsigned edges = 0;
-#pragma unroll
-            for (int e = 0; e < 3; ++e) {
-                const int from = sp[e] & 0xfffu, to = (sp[e] >> 12) & 0xfffu;
-                if (((sp[e] >> 24) & 3u) == (unsigned)dirbit && d0 >= from && d0 <= to) edges |= 1u << e;   // dir, !steep
-            }
-            if (meta_fn >= 0 && edges && (!rev || ((meta_fn & BWD_BOTH) && (meta_fn & BWD_FN_MASK) + F == own))) {
-                BwdFace bf = load_bwd_face(rp);
-                if (rev) reverse_bwd_face(bf, F);
-                const float fd0 = (float)d0;
-                // the pixel one step back along the sweep (in the tile or its halo)
-                const int prev_own = axis == 0 ? fi[(yl + 1 - dir) * FIS + FIX0 + xl] : fi[(yl + 1) * FIS + FIX0 + xl - dir];
-                while (edges) {
-                    const int e = __ffs(edges) - 1;
-                    edges &= edges - 1;
-                    const TaskGeom g = task_geom(bf, e, axis, is);
-                    const float xe = g.slope * (fd0 - g.p0d0) + g.p0d1;
-                    const int d1_in = __float2int_rz(dir > 0 ? floorf(xe) : ceilf(xe));
-                    const int d1_out = d1_in + dir;
-                    if ((unsigned)d1_in >= (unsigned)is || (unsigned)d1_out >= (unsigned)is) continue;
-                    if (d1_in != q0 && !(d1_in == q0 - dir && prev_own == own)) continue;
-                    const bool has0 = g.p1d0 != fd0, has1 = g.p0d0 != fd0;
-                    const float e0 = __fdividef(g.ka, g.p1d0 - fd0), e1 = __fdividef(g.ka, fd0 - g.p0d0);
-                    const int lim = dir > 0 ? is - 1 : 0;
-                    if (!matched) {
-                        matched = true;
-                        x = xe; c0 = e0; c1 = e1;
-                        ra = min(d1_out, lim); rc = max(d1_out, lim);
-                        key = (unsigned)((own * 3 + e) * 2 + axis);
-                        meta = (unsigned)d0 | ((unsigned)axis << 12) | (has0 ? 1u << 13 : 0u) | (has1 ? 1u << 14 : 0u);
-                    } else {   // a second edge of the face through the same pixel (a corner on the line; rare): direct
-                        float a0 = 0.f, a1 = 0.f;
-                        sweep_line(S, axis == 0 ? 2 : 0, d0, min(d1_out, lim), max(d1_out, lim), xe, e0, e1, has0, has1,
-                                   false, a0, a1);
-                        if (a0 != 0.f) atomicAdd(grad_ndc + (long)g.vid0 * 3 + (1 - axis), a0);
-                        if (a1 != 0.f) atomicAdd(grad_ndc + (long)g.vid1 * 3 + (1 - axis), a1);
-                    }
-                }
-            }
-        }
-// @region pix_items
-        // ---- runs of the missing-coverage list inside the sweep; one item per lane and round, 32 evaluated at a time
-        unsigned todo = 0;
-        const uint2 *rl = sruns;
-        if (matched) {   // (the tile's run lists and their info words were staged in shared memory)
-            const int axis = (meta >> 12) & 1u, l0 = (int)(meta & 0xfffu) - (axis ? ty0 : tx0);
-            rl = sruns + ((axis ? 0 : TILE) + l0) * RCAP;
-            todo = runs_in_sweep_of<true>(axis ? ext_row[l0] : ext_col[l0], rl, ra, rc, false, meta);
-        }
-        while (__any_sync(FULL, todo != 0u)) {
-            push_round<true>(iq, head, count, todo, rl, ra, rc, x, c0, c1, key, meta, lane);
-            if (count >= 32) DRAIN(32);
-        }
-    };
-
-// @region pix_scan
-    // ---- span ends: a warp takes two rows of the tile per step, a lane four consecutive pixels of one row (the rows
-    //      above and below and the two pixels beside them in registers): 16 flags per lane, queued with one prefix sum
-    {
-        const int x4 = (lane & 15) * 4;
-        const uint4 ec4 = *reinterpret_cast<const uint4 *>(ext_col + x4);
-        const unsigned ecol[4] = {ec4.x, ec4.y, ec4.z, ec4.w};
-#pragma unroll 1
-        for (int it = 0; it <= TILE / NWARPS / 2; ++it) {
-            const bool flush = it == TILE / NWARPS / 2;   // extra step: the candidates left in the queue
-            const int yl = warp * (TILE / NWARPS) + 2 * min(it, TILE / NWARPS / 2 - 1) + (lane >> 4), Y = ty0 + yl;
-            const int *p = fi + (yl + 1) * FIS + FIX0 + x4;
-            const int4 c4 = *reinterpret_cast<const int4 *>(p);
-            const int cur[4] = {c4.x, c4.y, c4.z, c4.w};
-            unsigned mask = 0;
-            if (!flush && (c4.x & c4.y & c4.z & c4.w) >= 0) {   // some pixel of the four is covered (-1: all bits set)
-                const int4 u4 = *reinterpret_cast<const int4 *>(p - FIS), d4 = *reinterpret_cast<const int4 *>(p + FIS);
-                const int up[4] = {u4.x, u4.y, u4.z, u4.w}, down[4] = {d4.x, d4.y, d4.z, d4.w};
-                const int nb[6] = {p[-1], c4.x, c4.y, c4.z, c4.w, p[4]};
-                const uint32_t er = ext_row[yl];
-                const int row_lo = (er >> 4) & 0xfff, row_hi = er >> 16;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int X = tx0 + x4 + j;
-                    const int col_lo = (ecol[j] >> 4) & 0xfff, col_hi = ecol[j] >> 16;
-                    if (cur[j] >= 0) {
-                        // span ends with missing coverage beyond them: axis 1 sweeps along x (row lists), axis 0 along y
-                        if (nb[j + 2] != cur[j] && row_hi > X) mask |= 1u << (4 * j);        // axis 1, dir +1
-                        if (nb[j] != cur[j] && row_lo < X) mask |= 2u << (4 * j);            // axis 1, dir -1
-                        if (down[j] != cur[j] && col_hi > Y) mask |= 4u << (4 * j);          // axis 0, dir +1
-                        if (up[j] != cur[j] && col_lo < Y) mask |= 8u << (4 * j);            // axis 0, dir -1
-                    }
-                }
-            }
-            if (flush || __any_sync(FULL, mask != 0u)) {
-                const int mine = __popc(mask);
-                int incl = mine;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int v = __shfl_up_sync(FULL, incl, o);
-                    if (lane >= o) incl += v;
-                }
-                int at = qn + incl - mine;
-                while (mask) {
-                    const int bit = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const int k = bit & 3;   // 0: axis 1 dir +, 1: axis 1 dir -, 2: axis 0 dir +, 3: axis 0 dir -
-                    q[at++] = (unsigned short)((x4 + (bit >> 2)) | (yl << 6) | (k < 2 ? 1u << 12 : 0u) | ((k & 1) ? 0u : 1u << 13));
-                }
-                qn += __shfl_sync(FULL, incl, 31);
-                __syncwarp();
-                int qh = 0;
-                while (qn - qh >= 32 || (flush && qn - qh > 0)) {
-                    if (qh) {   // (process reads q[lane])
-                        const unsigned short v = q[qh + lane];
-                        __syncwarp();
-                        q[lane] = v;
-                        __syncwarp();
-                    }
-                    process(min(32, qn - qh));
-                    qh += 32;
-                }
-                if (qh && !flush) {   // move the leftover to the front
-                    const int rem = qn - qh;
-                    unsigned short v = 0;
-                    if (lane < rem) v = q[qh + lane];
-                    __syncwarp();
-                    if (lane < rem) q[lane] = v;
-                    qn = rem;
-                    __syncwarp();
-                }
-            }
-        }
-    }
-    if (count > 0) DRAIN(count);
-}
-
 // @region bwd2
 // ------------------------------------------------------------------------------------------ backward, segment kernel
 // backward_pixel_map as the reference organises it - a walk over the scan-lines of every (face, edge, axis) task with
@@ -1634,42 +1068,11 @@ raster_bwd_tile_role(int tile, const BwdRec *__restrict__ brecs, int F, int V, i
 // sweeps the missing-coverage runs of its line beyond the crossing, and crossings of silhouette faces sweep the span of
 // the triangle; (crossing, run) items are evaluated in place (eval_item_fast), sums stay in two registers and leave as
 // one atomicAdd per segment and edge vertex into grad_ndc (the vertices_to_faces scatter-add is fused).
-constexpr int B2_SEG = 8;
+#ifndef HM_BWD_SEG
+#define HM_BWD_SEG 8
+#endif
+constexpr int B2_SEG = HM_BWD_SEG;       // scan-lines per segment (a multiple of 4, <= 8)
 constexpr int B2_CAP = 2048;            // list entries per slice
-constexpr int B2_MAXW = 32;             // coverage words per raster row (is <= 1024)
-
-// (crossing, run) item with the cheap cases branched out: no term-by-term part when the run starts >= NEAR_N pixels
-// from the crossing (the closed form holds from distance 4), no closed form for runs of <= NEAR_N pixels.
-__device__ __forceinline__ void eval_item_fast(float x, float c0, float c1, float G, int s, int e, bool has0, bool has1,
-                                               float inv_is2, float eps, float &acc0, float &acc1) {
-    const float K0 = c0 * inv_is2, K1 = c1 * inv_is2;
-    const float rK0 = rcp_fast(K0), rK1 = rcp_fast(K1);
-    const bool left = (float)e <= x;
-    const float sgn = left ? -1.f : 1.f;
-    float z = left ? x - (float)e : (float)s - x;  // distance of the item's nearest pixel
-    int n = e - s + 1;
-    float h0 = 0.f, h1 = 0.f;
-    if (z < (float)NEAR_N) {
-#pragma unroll
-        for (int k = 0; k < NEAR_N; ++k) {
-            const float dd = sgn * (z + (float)k);
-            float dist0 = K0 * dd, dist1 = K1 * dd;
-            dist0 = (0.f < dist0) ? dist0 + eps : dist0 - eps;
-            dist1 = (0.f < dist1) ? dist1 + eps : dist1 - eps;
-            const float t0 = rcp_fast(dist0), t1 = rcp_fast(dist1);
-            if (k < n) { h0 += t0; h1 += t1; }
-        }
-        n -= NEAR_N;
-        z += (float)NEAR_N;
-    }
-    if (n > 0) {
-        const float nf = (float)n;
-        h0 += sgn * harmonic_span(z + eps * fabsf(rK0), nf) * rK0;
-        h1 += sgn * harmonic_span(z + eps * fabsf(rK1), nf) * rK1;
-    }
-    if (has0) acc0 -= G * h0;
-    if (has1) acc1 -= G * h1;
-}
 
 __device__ __noinline__ void sweep_walk(const SweepSrc &S, int ls, int d0, int ra, int rc, float x, float K0, float K1,
                                         unsigned flags, float &a0, float &a1) {
@@ -1731,8 +1134,8 @@ __device__ __noinline__ void b2_drain(const SweepQueue2 &sq, int head, int n, co
     __syncwarp();
 }
 
-#ifndef HM_BWD2_MINB
-#define HM_BWD2_MINB 4
+#ifndef HM_BWD_MINB
+#define HM_BWD_MINB 4
 #endif
 // Geometry of the 32 tasks a warp is working on, by lane (structure of arrays: the consumer of a crossing reads the
 // fields of the lane that produced it).
@@ -1742,8 +1145,8 @@ struct TaskStash {
 };
 constexpr int B2_PAIRS = 32 * 2 * B2_SEG;   // (lane, scan-line, kind) of the crossings worth a sweep: at most two per line
 
-__global__ void __launch_bounds__(NTHREADS, HM_BWD2_MINB)
-raster_bwd2_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
+__global__ void __launch_bounds__(NTHREADS, HM_BWD_MINB)
+raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
                    float eps, const int32_t *__restrict__ face_index, const float *__restrict__ grad_alpha,
                    const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ cov_col,
                    const uint32_t *__restrict__ face_vis, const unsigned char *__restrict__ cov_blocks,
@@ -2039,38 +1442,6 @@ raster_bwd2_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__
     }
 }
 
-// One launch, two kinds of CTA: the first n_face_ctas blocks of an image take the faces (in-sweeps, steep tasks), the
-// others one tile each (out-sweeps); the few long face CTAs start first and overlap the many tile CTAs.
-#ifndef HM_BWD_MINB
-#define HM_BWD_MINB 3
-#endif
-__global__ void __launch_bounds__(NTHREADS, HM_BWD_MINB)
-raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ boxes, int F, int V, int is, int aa,
-                  float eps, int n_face_ctas, const int32_t *__restrict__ face_index,
-                  const float *__restrict__ grad_alpha, const uint32_t *__restrict__ cov_row,
-                  const uint32_t *__restrict__ cov_col, const uint32_t *__restrict__ m_row,
-                  const uint32_t *__restrict__ m_col, const uint2 *__restrict__ runs,
-                  const uint32_t *__restrict__ run_info, float *__restrict__ grad_ndc) {
-    __shared__ __align__(16) int fi[(TILE + 2) * FIS];     // tiles: face_index tile, one-pixel halo
-    __shared__ __align__(16) unsigned short cq[NWARPS][CQCAP];   // tiles: candidates (span ends); faces: the face list
-    __shared__ __align__(16) uint32_t ext_row[TILE], ext_col[TILE];   // tiles: extent of the missing-coverage list per line
-    __shared__ ItemQueue iqs[NWARPS];                      // (crossing, run) items
-    __shared__ int n_list;
-    __shared__ SweepSrc S;
-    __shared__ __align__(8) uint64_t bar;
-    extern __shared__ __align__(128) uint2 sruns[];          // tiles: run lists of the tile's rows and columns [2][TILE][RCAP]
-    static_assert(sizeof(cq) >= 2 * BFACES * sizeof(unsigned), "face list fits the candidate queues");
-#ifdef HM_BWD_ROLE_MASK   // development: 1 = tiles only, 2 = faces only
-    if (!(((int)blockIdx.x < n_face_ctas ? 2 : 1) & HM_BWD_ROLE_MASK)) return;
-#endif
-    if ((int)blockIdx.x < n_face_ctas)
-        raster_bwd_face_role(brecs, boxes, F, V, is, aa, eps, face_index, grad_alpha, cov_row, cov_col, m_row, m_col, runs,
-                             run_info, grad_ndc, reinterpret_cast<unsigned *>(&cq[0][0]), n_list, iqs, S);
-    else
-        raster_bwd_tile_role((int)blockIdx.x - n_face_ctas, brecs, F, V, is, aa, eps, face_index, grad_alpha, cov_row,
-                             m_row, m_col, runs, run_info, grad_ndc, fi, cq, ext_row, ext_col, iqs, S, sruns, &bar);
-}
-
 // @region after
 // ------------------------------------------------------------------------------------------ RGB / depth (visualisation)
 // Forward of nr.rasterize_rgbad for texture_size 1 on top of the face_index map: a covered raster sample takes the
@@ -2273,32 +1644,10 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
     HM_REQUIRE(V > 0, "hm_raster_sil_bwd: bad sizes");
     HM_UNSUPPORTED(is > 1024, "hm_raster_sil_bwd: raster size %d > 1024 is not supported", is);
     const BwdRec *brecs = reinterpret_cast<const BwdRec *>(static_cast<const FaceRec *>(records) + (long)B * F);
-    const int n_face_ctas = (F + BFACES - 1) / BFACES;
-    const int n_tiles = (is / TILE) * (is / TILE);
-    const size_t smem = 2 * TILE * RCAP * sizeof(uint2);   // staged run lists (static + dynamic exceeds the 48 KB default)
-    static HmSmemOptIn opt_in;
-    if (int rc = hm_smem_opt_in(raster_bwd_kernel, smem, opt_in, "hm_raster_sil_bwd")) return rc;
-    static const bool use_old = getenv("HOMAN_B200_BWD_OLD") != nullptr;   // development switch
-    if (!use_old) {
-        const int n_rounds = (F + NTHREADS - 1) / NTHREADS;
-        raster_bwd2_kernel<<<dim3(min(n_rounds, 8), B), NTHREADS, 0, hm_stream(stream)>>>(
-            brecs, static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, face_index, grad_alpha, cov_row,
-            cov_col, face_vis, cov_blocks, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
-        HM_CHECK_LAUNCH("hm_raster_sil_bwd");
-        return HM_OK;
-    }
-#ifdef HM_BWD_SPLIT   // development: the two kinds of CTA in two launches instead of one
-    raster_bwd_kernel<<<dim3(n_face_ctas, B), NTHREADS, smem, hm_stream(stream)>>>(
-        brecs, static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, n_face_ctas, face_index, grad_alpha,
-        cov_row, cov_col, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
-    raster_bwd_kernel<<<dim3(n_tiles, B), NTHREADS, smem, hm_stream(stream)>>>(
-        brecs, static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, 0, face_index, grad_alpha,
-        cov_row, cov_col, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
-#else
-    raster_bwd_kernel<<<dim3(n_face_ctas + n_tiles, B), NTHREADS, smem, hm_stream(stream)>>>(
-        brecs, static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, n_face_ctas, face_index, grad_alpha,
-        cov_row, cov_col, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
-#endif
+    const int n_rounds = (F + NTHREADS - 1) / NTHREADS;
+    raster_bwd_kernel<<<dim3(min(n_rounds, 8), B), NTHREADS, 0, hm_stream(stream)>>>(
+        brecs, static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, face_index, grad_alpha, cov_row,
+        cov_col, face_vis, cov_blocks, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
     HM_CHECK_LAUNCH("hm_raster_sil_bwd");
     return HM_OK;
 }
