@@ -127,9 +127,10 @@ __device__ __forceinline__ float to_pix(float v, int is) { return 0.5f * (v * is
 
 __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *__restrict__ faces, int faces_batch,
                                   int B, int V, int F, int is, int fill_back, FaceRec *__restrict__ recs,
-                                  BwdRec *__restrict__ brecs, FaceBox *__restrict__ boxes) {
-    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (long)B * F) return;
+                                  BwdRec *__restrict__ brecs, FaceBox *__restrict__ boxes, int *__restrict__ img_box) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < (long)B * F;   // (idle threads of the last block repeat the last face: same box, same stores)
+    if (!live) i = (long)B * F - 1;
     const int b = (int)(i / F), f = (int)(i % F);
     const int32_t *fc = faces + ((faces_batch > 1 ? (long)b * F : 0) + f) * 3;
     int vi[3] = {fc[0], fc[1], fc[2]};
@@ -237,6 +238,21 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
     FaceBox bx;
     bx.x0 = (short)x0; bx.y0 = (short)y0; bx.x1 = (short)x1; bx.y1 = (short)y1;
     boxes[i] = bx;
+    // pixel box of the whole image (all its faces): {x0, y0, -x1, -y1} under atomicMin, preset to 0x7f7f7f7f. One
+    // reduction per warp over the lanes of the first lane's image, the other lanes (next image) on their own.
+    {
+        const unsigned FULL = 0xffffffffu;
+        const bool has = x0 <= x1;
+        const int b0 = __shfl_sync(FULL, b, 0);
+        int v[4] = {has ? x0 : 0x7f7f7f7f, has ? y0 : 0x7f7f7f7f, has ? -x1 : 0x7f7f7f7f, has ? -y1 : 0x7f7f7f7f};
+        const bool mine = b == b0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int m = __reduce_min_sync(FULL, mine ? v[k] : 0x7f7f7f7f);
+            if ((threadIdx.x & 31) == 0) v[k] = m;
+            if (((threadIdx.x & 31) == 0 || !mine) && v[k] != 0x7f7f7f7f && v[k] < img_box[4 * b + k]) atomicMin(&img_box[4 * b + k], v[k]);
+        }
+    }
 }
 
 constexpr int LISTCAP = 2048;  // faces of one tile processed per batch
@@ -369,11 +385,11 @@ __device__ __forceinline__ void clip_edge(const RowCtx &rc, float A, float xk, f
     }  // NaN slope: the comparison is false for every sample, all pass
 }
 
-__global__ void __launch_bounds__(NTHREADS)
+__global__ void __launch_bounds__(NTHREADS, 4)
 raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ boxes, int F, int is, int aa,
                   float near_, float far_, int32_t *__restrict__ face_index, float *__restrict__ alpha,
                   uint32_t *__restrict__ cov_row, uint32_t *__restrict__ cov_col, uint32_t *__restrict__ face_vis,
-                  unsigned char *__restrict__ cov_blocks) {
+                  unsigned char *__restrict__ cov_blocks, const int *__restrict__ img_box) {
     extern __shared__ __align__(16) unsigned long long keys[];  // [TILE * TILE] z-buffer (dynamic: static + this > 48 KB)
     __shared__ int list[LISTCAP];
     __shared__ int cnt, next;
@@ -394,15 +410,54 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     const float inv_is = rc.inv_is;
     const unsigned near_bits = __float_as_uint(near_), far_bits = __float_as_uint(far_);
     const unsigned long long empty = ((unsigned long long)far_bits << 32) | 0xffffffffull;
+    recs += (long)b * F;
+    boxes += (long)b * F;
+    // ---- tiles no face touches (outside the image's pixel box, or an empty first scan of all faces) write constants
+    bool untouched;
+    {
+        const int4 ib = __ldg(reinterpret_cast<const int4 *>(img_box) + b);   // {x0, y0, -x1, -y1}
+        untouched = F == 0 || ib.x > tx0 + TILE - 1 || -ib.z < tx0 || ib.y > ty0 + TILE - 1 || -ib.w < ty0;
+    }
+    int base = 0, n_first = 0;
+    if (!untouched) {
+        n_first = next_batch(boxes, base, F, tx0, ty0, list, &cnt, &next);
+        untouched = n_first == 0 && base >= F;
+    }
+    if (untouched) {
+        const int W = is / 32;
+        for (int i = threadIdx.x; i < TILE * TILE / 4; i += NTHREADS) {
+            const int yl = i / (TILE / 4), x4 = i % (TILE / 4);
+            *reinterpret_cast<int4 *>(face_index + ((long)b * is + (ty0 + yl)) * is + tx0 + 4 * x4) = make_int4(-1, -1, -1, -1);
+        }
+        if (threadIdx.x < 2 * TILE) {
+            const int yl = threadIdx.x >> 1, w = threadIdx.x & 1;
+            if (cov_row) cov_row[((long)b * is + (ty0 + yl)) * W + (tx0 >> 5) + w] = 0u;
+            if (cov_col) cov_col[((long)b * is + (tx0 + yl)) * W + (ty0 >> 5) + w] = 0u;
+        }
+        if (cov_blocks && threadIdx.x < 2 * (TILE / 8))
+            cov_blocks[((long)b * (is / 8) + (ty0 >> 3) + (threadIdx.x >> 1)) * W + (tx0 >> 5) + (threadIdx.x & 1)] = 0xf;
+        if (aa) {
+            const int R = is / 2, rtop = R - 1 - (ty0 >> 1);
+            for (int i = threadIdx.x; i < (TILE / 2) * (TILE / 2) / 4; i += NTHREADS) {
+                const int m = i / (TILE / 8), c4 = i % (TILE / 8);
+                *reinterpret_cast<float4 *>(alpha + ((long)b * R + (rtop - m)) * R + (tx0 >> 1) + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        } else {
+            for (int i = threadIdx.x; i < TILE * TILE / 4; i += NTHREADS) {
+                const int yl = i / (TILE / 4), x4 = i % (TILE / 4);
+                *reinterpret_cast<float4 *>(alpha + ((long)b * is + (is - 1 - ty0 - yl)) * is + tx0 + 4 * x4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < TILE * TILE / 2; i += NTHREADS)
         reinterpret_cast<ulonglong2 *>(keys)[i] = make_ulonglong2(empty, empty);
     if (threadIdx.x < 2 * TILE) (&amb[0][0])[threadIdx.x] = 0u;
-    recs += (long)b * F;
-    boxes += (long)b * F;
 
-    int base = 0;
-    while (base < F) {
-        const int n = next_batch(boxes, base, F, tx0, ty0, list, &cnt, &next);
+    bool first = true;
+    while (first || base < F) {
+        const int n = first ? n_first : next_batch(boxes, base, F, tx0, ty0, list, &cnt, &next);
+        first = false;
         // two passes: faces kept in their original winding (the outer layer of an outward-wound closed mesh)
         // first, the reversed copies second. Between them the winners are summarised per 4x4 block, so that a
         // hidden-layer face is dropped with one comparison per block instead of one per sample.
@@ -512,12 +567,16 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 inv[8] = i2.x; iz0 = i2.y; iz1 = i2.z; iz2 = i2.w;
                 exact_face = __float_as_int(rp[7].x);
             }
+            int row = 0;
             for (int i = lane; i < n_px; i += 32) {
-                int row = 0;
-                if (h > 32 && rowpre[32] <= i) row = 32;
+                if (i == lane) {   // first pixel of the lane: binary search over the rows; afterwards the row only advances
+                    if (h > 32 && rowpre[32] <= i) row = 32;
 #pragma unroll
-                for (int sft = 16; sft > 0; sft >>= 1)
-                    if (row + sft < h && rowpre[row + sft] <= i) row += sft;
+                    for (int sft = 16; sft > 0; sft >>= 1)
+                        if (row + sft < h && rowpre[row + sft] <= i) row += sft;
+                } else {
+                    while (row + 1 < h && rowpre[row + 1] <= i) ++row;
+                }
                 const int xi = rowx[row] + (i - rowpre[row]), yi = Y0 + row;
                 const int xl = xi - tx0, yl = yi - ty0;
                 unsigned long long *kp = &keys[yl * TILE + xl];
@@ -1521,6 +1580,12 @@ sil_loss_kernel(const float *__restrict__ alpha, const int8_t *__restrict__ targ
     }
 }
 
+// The per-image pixel boxes follow the face boxes in the bbox buffer (HM_FACE_BBOX_BUFFER_BYTES), 16-byte aligned.
+inline int *image_boxes(void *bboxes, int B, int F) {
+    const size_t off = ((size_t)B * F * HM_FACE_BBOX_BYTES + 15) & ~(size_t)15;
+    return reinterpret_cast<int *>(static_cast<char *>(bboxes) + off);
+}
+
 int check_raster_size(int image_size, int aa, int *is_out) {
     const int is = aa ? 2 * image_size : image_size;
     HM_REQUIRE(image_size > 0, "image_size must be positive");
@@ -1571,9 +1636,17 @@ int hm_raster_setup(const float *ndc, const int32_t *faces, int faces_batch, int
     HM_REQUIRE(V > 0, "hm_raster_setup: bad sizes");
     const long n = (long)B * F;
     HM_UNSUPPORTED(2L * F > BWD_FN_MASK, "hm_raster_setup: too many faces (%d)", F);
+    int *img_box = image_boxes(bboxes, B, F);
+    {   // preset of the per-image pixel boxes (a memset node when the stream is being captured)
+        const cudaError_t e = cudaMemsetAsync(img_box, 0x7f, (size_t)B * 16, hm_stream(stream));
+        if (e != cudaSuccess) {
+            hm_set_error("hm_raster_setup: cudaMemsetAsync: %s", cudaGetErrorString(e));
+            return HM_ERR_CUDA;
+        }
+    }
     face_setup_kernel<<<(unsigned)((n + 255) / 256), 256, 0, hm_stream(stream)>>>(
         ndc, faces, faces_batch, B, V, F, is, fill_back, static_cast<FaceRec *>(records),
-        reinterpret_cast<BwdRec *>(static_cast<FaceRec *>(records) + n), static_cast<FaceBox *>(bboxes));
+        reinterpret_cast<BwdRec *>(static_cast<FaceRec *>(records) + n), static_cast<FaceBox *>(bboxes), img_box);
     HM_CHECK_LAUNCH("hm_raster_setup");
     return HM_OK;
 }
@@ -1599,7 +1672,7 @@ int hm_raster_sil_fwd(const void *records, const void *bboxes, int B, int F, int
     }
     raster_fwd_kernel<<<grid, NTHREADS, fwd_smem, hm_stream(stream)>>>(
         static_cast<const FaceRec *>(records), static_cast<const FaceBox *>(bboxes), F, is, anti_aliasing, near_, far_,
-        face_index, alpha, cov_row, cov_col, face_vis, cov_blocks);
+        face_index, alpha, cov_row, cov_col, face_vis, cov_blocks, image_boxes(const_cast<void *>(bboxes), B, F));
     HM_CHECK_LAUNCH("hm_raster_sil_fwd");
     return HM_OK;
 }

@@ -67,7 +67,7 @@ class RasterBuffers:
         S = image_size * 2 if anti_aliasing else image_size
         self.S = S
         self.records = torch.empty(B * F * 224, dtype=torch.uint8, device=device)   # HM_FACE_RECORD_BYTES
-        self.bboxes = torch.empty(B * F * 8, dtype=torch.uint8, device=device)
+        self.bboxes = torch.empty(((B * F * 8 + 15) // 16) * 16 + B * 16, dtype=torch.uint8, device=device)   # HM_FACE_BBOX_BUFFER_BYTES
         self.face_index = torch.empty(B, S, S, dtype=torch.int32, device=device)
         self.alpha = torch.empty(B, image_size, image_size, dtype=torch.float32, device=device)
         self.cov_row = torch.empty(B, S, S // 32, dtype=torch.int32, device=device)

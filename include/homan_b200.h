@@ -56,8 +56,11 @@ int hm_project_bwd(const float *verts, const float *K, int K_batch, const float 
 #define HM_FACE_RECORD_BYTES 224
 #define HM_FACE_BBOX_BYTES 8
 /* ndc [B,V,3], faces [faces_batch,F,3] -> records (B*F*HM_FACE_RECORD_BYTES bytes: a plane of 128-byte forward
- * records followed by a plane of 96-byte backward records) + bboxes [B,F,8 B] (front-facing winding of every face;
- * never materialises the doubled face array). */
+ * records followed by a plane of 96-byte backward records) + bboxes (HM_FACE_BBOX_BUFFER_BYTES(B, F) bytes: the pixel
+ * box of every face [B,F,8 B], then, 16-byte aligned, the pixel box of every image [B,16 B]: tiles outside it are
+ * skipped). Front-facing winding of every face; never materialises the doubled face array. */
+#define HM_FACE_BBOX_BUFFER_BYTES(B, F) \
+    ((((size_t)(B) * (size_t)(F) * HM_FACE_BBOX_BYTES + 15) & ~(size_t)15) + (size_t)(B) * 16)
 int hm_raster_setup(const float *ndc, const int32_t *faces, int faces_batch, int B, int V, int F,
                     int image_size, int anti_aliasing, int fill_back, void *records, void *bboxes,
                     void *stream);
