@@ -132,13 +132,14 @@ def run_reference(args):
         f = torch.from_numpy(faces.astype(np.int32))[None].repeat(len(verts), 1, 1)
         return r(torch.from_numpy(verts), f, mode="silhouettes").numpy()
 
-    clip = synth.make_clip(cfg["T"], cfg["obj"], seed=cfg["seed"], mano_asset=asset, render_fn=render_fn)
+    obj = cfg["obj"] + (str(cfg["seed"]) if cfg["obj"].endswith("@") else "")
+    clip = synth.make_clip(cfg["T"], obj, seed=cfg["seed"], mano_asset=asset, render_fn=render_fn)
     inits = synth.make_inits(clip, 1, seed=cfg["seed"])
     batch = synth.make_batch(clip, inits)
     lw = loss_weights(cfg["lw"])
     steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
     sec = cpu_reference_iteration_rate(args.workload, steps, warmup, batch, lw, asset)
-    P = cfg["P"]
+    P = cfg["P"] * cfg.get("clips", 1)   # problems of one GPU's batch
     value = 1.0 / (sec * P)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "iters/s", "n_gpus": args.gpus,
@@ -199,10 +200,30 @@ def run_ours(args):
     from homan_b200.workload import CONFIGS, make_workload
     cfg = CONFIGS[args.workload]
     asset = synth.make_mano_asset(0, "right", mesh=args.hand_mesh)
-    # weak scaling: every rank fits the same clip from its own block of P random initialisations (equal work per
-    # GPU); the job's answer is the argmin over all N*P inits, gathered once at the end
-    batch, lw = make_workload(args.workload, clip_index=0, init_shard=rank, mano_asset=asset)
+    multi = "clips" in cfg
+    if multi:
+        # cfg4: whole clips per GPU (a clip is never split), every clip with its own object and its 16 inits on the
+        # same GPU, so the per-clip argmin is local; weak scaling: cfg["clips"] clips per rank (8 ranks = the 64 clips
+        # of BASELINE.json config 4); the final all_gather carries (clip id, best init, best loss, winner parameters)
+        n_local = cfg["clips"]
+        clip_ids = list(range(rank * n_local, (rank + 1) * n_local))
+        batch, lw = make_workload(args.workload, clips=clip_ids, mano_asset=asset)
+    else:
+        # weak scaling: every rank fits the same clip from its own block of P random initialisations (equal work per
+        # GPU); the job's answer is the argmin over all N*P inits, gathered once at the end
+        n_local, clip_ids = 1, [rank]
+        batch, lw = make_workload(args.workload, clip_index=0, init_shard=rank, mano_asset=asset)
     eng = FitEngine(batch, lw, lr=1e-2, mano_asset=asset, use_graph=True)
+
+    def final_reduce():
+        """The only collective of the job: per-clip argmin over the inits (local), one all_gather of the winners."""
+        bi, bl = eng.best_init(clips=n_local)
+        payload = None
+        if multi:   # the winner's fitted parameters travel with it
+            inits = eng.P // n_local
+            sel = (torch.arange(n_local, device=bi.device) * inits + bi.long())
+            payload = torch.cat([eng.params[k].view(eng.P, -1)[sel] for k in eng.params], 1)
+        return hd.gather_best(clip_ids, bi.long(), bl, n_local * world, payload)
     host = eng.stage_host(batch, pin=True)
     eng.capture()
 
@@ -215,7 +236,7 @@ def run_ours(args):
     from homan_b200 import distributed as hd
     for _ in range(args.warmup):
         eng.step()
-    hd.gather_best([rank], *[x if i else x.long() for i, x in enumerate(eng.best_init(clips=1))], world)  # NCCL warm-up
+    final_reduce()  # NCCL warm-up
     sampler = ClockSampler(local)
     barrier()
     sampler.start()
@@ -223,9 +244,7 @@ def run_ours(args):
     e0.record()
     for _ in range(args.steps):
         eng.step()
-    # final best-init reduction (the only collective of the job): per-clip argmin, then one all_gather
-    bi, bl = eng.best_init(clips=1)
-    hd.gather_best([rank], bi.long(), bl, world)
+    final_reduce()
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -266,11 +285,7 @@ def run_ours(args):
            raster_bwd_algorithmic_bytes(eng.B, eng.faces_obj.shape[1])) / 2 if eng.on_sil_hand else \
         raster_bwd_algorithmic_bytes(eng.B, eng.faces_obj.shape[1])
     roofline = None
-    traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
-    tpath = os.path.join(ROOT, "profiles", "raster_bwd_traffic.json")
-    if os.path.exists(tpath) and args.workload == "cfg3":
-        with open(tpath) as fh:
-            traffic = json.load(fh)["traffic_bytes_per_launch"]
+    traffic = None   # not measurable inside this run (needs ncu): see profiles/ for the ncu capture of this kernel
     if bwd:
         achieved = alg / (bwd["us_per_launch"] * 1e-6) / 1e9
         roofline = {"kernel": "raster_bwd_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
@@ -297,7 +312,10 @@ def run_ours(args):
                    "object": cfg["obj"], "hand_mesh": args.hand_mesh,
                    "faces": [int(eng.faces_hand.shape[1]), int(eng.faces_obj.shape[1])],
                    "losses": cfg["lw"], "render": "256^2 (512^2 raster, AA)", "cuda_graph": True,
-                   "sharding": "inits: every rank fits the clip from its own block of P random inits, one all_gather of the best init at the end",
+                   "sharding": ("clips: %d whole clips (own object each) x %d inits per rank, per-clip argmin local, one "
+                                "all_gather of the winners and their parameters at the end" % (n_local, eng.P // n_local)) if multi else
+                               "inits: every rank fits the clip from its own block of P random inits, one all_gather of the best init at the end",
+                   "clips_per_gpu": n_local,
                    "l2": "inputs larger than L2 (face_index maps alone are %d MB per step)" %
                          (eng.B * 2 * 512 * 512 * 4 // 2 ** 20),
                    "problem_frame_iters_per_s": value * eng.B},
@@ -316,7 +334,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--workload", default="cfg3")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

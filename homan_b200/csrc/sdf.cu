@@ -112,9 +112,9 @@ __device__ __forceinline__ Corner unnormalise(float x, float y, float z) {
 }
 
 __global__ void __launch_bounds__(PNT)
-sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ faces, const float *__restrict__ verts_s,
-                int Vg, int Fg, int Vs, float half_factor, float weight, float *__restrict__ phi_all,
-                float *__restrict__ partials, float *__restrict__ g_vs) {
+sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ faces, int faces_batch,
+                const float *__restrict__ verts_s, int Vg, int Fg, int Vs, float half_factor, float weight,
+                float *__restrict__ phi_all, float *__restrict__ partials, float *__restrict__ g_vs) {
     extern __shared__ __align__(16) float lv[];  // Vg * 3 normalised mesh vertices, then Fg bounding spheres
     float4 *sph = reinterpret_cast<float4 *>(lv + ((Vg * 3 + 3) / 4) * 4);
     __shared__ unsigned needed[G * G], inside[G * G];
@@ -126,6 +126,7 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
     const float *vg = verts_g + (long)b * Vg * 3;
     const float *vs = verts_s + (long)b * Vs * 3;
     float *phi = phi_all + (long)b * G * G * G;
+    if (faces_batch > 1) faces += (long)b * Fg * 3;   // one face list per image (clips with different objects)
     // ---- 1. bbox cube of the grid mesh
     float mx[6] = {-3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
     for (int i = tid; i < Vg; i += PNT) {
@@ -320,11 +321,11 @@ sdf_grid_kernel(const int32_t *__restrict__ faces, const float *__restrict__ ver
 
 extern "C" {
 
-int hm_sdf_pair(const float *verts_g, const int32_t *faces_g, const float *verts_s, int B, int Vg, int Fg,
-                int Vs, int grid, float scale_factor, float weight, float *phi_scratch, float *partials,
+int hm_sdf_pair(const float *verts_g, const int32_t *faces_g, int faces_batch, const float *verts_s, int B, int Vg,
+                int Fg, int Vs, int grid, float scale_factor, float weight, float *phi_scratch, float *partials,
                 float *grad_verts_s, void *stream) {
     HM_REQUIRE(verts_g && faces_g && verts_s && phi_scratch && partials, "hm_sdf_pair: null pointer");
-    HM_REQUIRE(B >= 0 && Vg > 0 && Fg > 0 && Vs > 0, "hm_sdf_pair: bad sizes");
+    HM_REQUIRE(B >= 0 && Vg > 0 && Fg > 0 && Vs > 0 && (faces_batch == 1 || faces_batch == B), "hm_sdf_pair: bad sizes");
     HM_UNSUPPORTED(grid != G, "hm_sdf_pair: grid size %d (only %d, the reference's grid_size)", grid, G);
     const size_t smem = (size_t)((Vg * 3 + 3) / 4) * 4 * sizeof(float) + (size_t)Fg * 4 * sizeof(float);
     HM_UNSUPPORTED(smem > 160 * 1024, "hm_sdf_pair: grid mesh with %d vertices does not fit shared memory", Vg);
@@ -332,8 +333,8 @@ int hm_sdf_pair(const float *verts_g, const int32_t *faces_g, const float *verts
     static HmSmemOptIn opt_in;
     if (int rc = hm_smem_opt_in(sdf_pair_kernel, smem, opt_in, "hm_sdf_pair")) return rc;
     const float half_factor = (float)((1.0 + (double)scale_factor) * 0.5);
-    sdf_pair_kernel<<<B, PNT, smem, hm_stream(stream)>>>(verts_g, faces_g, verts_s, Vg, Fg, Vs, half_factor, weight,
-                                                        phi_scratch, partials, grad_verts_s);
+    sdf_pair_kernel<<<B, PNT, smem, hm_stream(stream)>>>(verts_g, faces_g, faces_batch, verts_s, Vg, Fg, Vs, half_factor,
+                                                        weight, phi_scratch, partials, grad_verts_s);
     HM_CHECK_LAUNCH("hm_sdf_pair");
     return HM_OK;
 }

@@ -76,11 +76,17 @@ class FitEngine:
         self.mano = mano_blob(asset, ncomps, dev)
 
         # ---- constants (shapes from the batch; values come in through upload())
-        self.Vo = Vo = int(np.asarray(batch["obj_verts_can"]).shape[0])
-        Fo = int(np.asarray(batch["obj_faces"]).shape[0])
+        # One object mesh for every problem ([Vo,3] / [Fo,3]), or one per clip ([C,Vo,3] / [C,Fo,3] + "clip_of_problem"
+        # [P]: the reference fits a different object per sample, fit_vid_dataset.py:190-296). The clips of one batch
+        # must agree on Vo and Fo; the per-clip tables are expanded to one mesh / face list per image on the device.
+        ov = np.asarray(batch["obj_verts_can"])
+        self.n_meshes = 1 if ov.ndim == 2 else int(ov.shape[0])
+        self.Vo = Vo = int(ov.shape[-2])
+        Fo = int(np.asarray(batch["obj_faces"]).shape[-2])
         R = REND_SIZE
-        self.mesh_obj = torch.empty(1, Vo, 3, device=dev)
-        self.faces_obj = torch.empty(1, Fo, 3, dtype=torch.int32, device=dev)
+        nm = 1 if self.n_meshes == 1 else B
+        self.mesh_obj = torch.empty(nm, Vo, 3, device=dev)
+        self.faces_obj = torch.empty(nm, Fo, 3, dtype=torch.int32, device=dev)
         self.faces_hand = torch.as_tensor(np.ascontiguousarray(batch["hand_faces"]).astype(np.int32)).to(dev).view(1, -1, 3)
         self.faces_hand_closed = torch.as_tensor(np.ascontiguousarray(asset["closed_faces"]).astype(np.int32)).to(dev).view(-1, 3)
         self.camintr = torch.empty(B, 3, 3, device=dev)
@@ -193,8 +199,14 @@ class FitEngine:
             return x.pin_memory() if pin and torch.cuda.is_available() else x
         P, T = np.asarray(batch["obj_t"]).shape[:2]
         f = torch.float32
+        mesh, faces = np.asarray(batch["obj_verts_can"]), np.asarray(batch["obj_faces"])
+        if mesh.ndim == 3:   # one object per clip -> one per image (problem-major)
+            cop = np.asarray(batch["clip_of_problem"]).astype(np.int64)
+            if cop.shape != (P,) or faces.ndim != 3 or faces.shape[0] != mesh.shape[0]:
+                raise _lib.HomanB200Error("per-clip objects need obj_verts_can [C,Vo,3], obj_faces [C,Fo,3], clip_of_problem [P]")
+            mesh, faces = np.repeat(mesh[cop], T, 0), np.repeat(faces[cop], T, 0)
         return {
-            "mesh_obj": t(batch["obj_verts_can"], f), "faces_obj": t(batch["obj_faces"], torch.int32),
+            "mesh_obj": t(mesh, f), "faces_obj": t(faces, torch.int32),
             "camintr": t(batch["camintr"], f), "K_roi_obj": t(batch["K_roi_obj"], f),
             "K_roi_hand": t(batch["K_roi_hand"], f), "ref_verts2d": t(batch["verts2d"], f),
             "target_obj": t(batch["target_masks_object"], torch.int8),
@@ -246,7 +258,7 @@ class FitEngine:
 
     def _forward_vertices(self, s):
         p = self.params
-        call("hm_rigid_fwd", ptr(self.mesh_obj), 1, ptr(p["rotations_object"]), ptr(p["translations_object"]),
+        call("hm_rigid_fwd", ptr(self.mesh_obj), self.mesh_obj.shape[0], ptr(p["rotations_object"]), ptr(p["translations_object"]),
              ptr(self.scale_obj), self.B, self.Vo, ptr(self.verts_obj), s)
         call("hm_mano_fwd", ptr(self.mano), self.ncomps, self.side_left, ptr(p["mano_pca_pose"]), self.pca_dim,
              ptr(p["mano_rot"]), ptr(p["mano_betas"]), ptr(p["mano_trans"]), ptr(p["rotations_hand"]),
@@ -284,11 +296,11 @@ class FitEngine:
             n += 1
         if self.on_collision:
             # pair (hand grid <- object vertices): value only (the object is detached, homan.py:445-449)
-            call("hm_sdf_pair", ptr(self.verts_hand), ptr(self.faces_hand_closed), ptr(self.verts_obj), B, 778,
+            call("hm_sdf_pair", ptr(self.verts_hand), ptr(self.faces_hand_closed), 1, ptr(self.verts_obj), B, 778,
                  self.faces_hand_closed.shape[0], self.Vo, SDF_GRID, SDF_SCALE_FACTOR, 0.0, ptr(self.phi_scratch),
                  ptr(self.partials), None, s)
             # pair (object grid <- hand vertices): gradient to the hand
-            call("hm_sdf_pair", ptr(self.verts_obj), ptr(self.faces_obj), ptr(self.verts_hand), B, self.Vo,
+            call("hm_sdf_pair", ptr(self.verts_obj), ptr(self.faces_obj), self.faces_obj.shape[0], ptr(self.verts_hand), B, self.Vo,
                  self.faces_obj.shape[1], 778, SDF_GRID, SDF_SCALE_FACTOR, lw["lw_collision"], ptr(self.phi_scratch),
                  ptr(self.partials), ptr(self.g_verts_hand), s)
             n += 2
@@ -299,7 +311,7 @@ class FitEngine:
              ptr(self.scale_hand), B, ptr(self.g_verts_hand), ptr(self.g_cdet) if self.on_inter else None,
              ptr(g["mano_pca_pose"]), ptr(g["mano_rot"]), ptr(g["mano_betas"]), ptr(g["mano_trans"]),
              ptr(g["rotations_hand"]), ptr(g["translations_hand"]), s)
-        call("hm_rigid_bwd", ptr(self.mesh_obj), 1, ptr(self.params["rotations_object"]), ptr(self.scale_obj), B,
+        call("hm_rigid_bwd", ptr(self.mesh_obj), self.mesh_obj.shape[0], ptr(self.params["rotations_object"]), ptr(self.scale_obj), B,
              self.Vo, ptr(self.g_verts_obj), ptr(g["rotations_object"]), ptr(g["translations_object"]), s)
         call("hm_finalize_losses", ptr(self.partials), ptr(self.weights_part), self.P, T, ptr(self.losses),
              ptr(self.total), ptr(self.step_counter) if adam else None, s)   # forward-only: Adam's step count untouched

@@ -308,6 +308,13 @@ def make_object(kind):
         return make_ellipsoid(100, 100, (0.04, 0.06, 0.04))
     if kind == "ellipsoid80":
         return make_ellipsoid(8, 5, (0.04, 0.06, 0.04))
+    if kind.startswith("ellipsoid500@") or kind.startswith("ellipsoid80@"):
+        # a clip-specific object: same topology, semi-axes drawn from the number after the @ (cfg4: every clip
+        # fits its own object, as the reference does per sample)
+        base, seed = kind.split("@")
+        rng = np.random.default_rng(int(seed))
+        axes = tuple(float(x) for x in rng.uniform(0.03, 0.07, size=3))
+        return make_ellipsoid(25, 10, axes) if base == "ellipsoid500" else make_ellipsoid(8, 5, axes)
     raise ValueError(kind)
 
 
@@ -494,10 +501,16 @@ def make_batch(clip, inits):
 
 
 def concat_batches(batches):
-    """Stack the problems of several clips that share T, meshes and the MANO asset (cfg4)."""
+    """Stacks the problems of several clips (same T, Vo, Fo and MANO asset; cfg4) into one clip-major batch: every
+    clip keeps its own object mesh (obj_verts_can [C,Vo,3], obj_faces [C,Fo,3], clip_of_problem [P])."""
     out = dict(batches[0])
     for k, v in batches[0].items():
         if isinstance(v, np.ndarray) and k not in ("obj_verts_can", "obj_faces", "hand_faces"):
             out[k] = np.concatenate([b[k] for b in batches], 0)
+    out["obj_verts_can"] = np.stack([np.asarray(b["obj_verts_can"]) for b in batches])
+    out["obj_faces"] = np.stack([np.asarray(b["obj_faces"]) for b in batches])
+    out["clip_of_problem"] = np.concatenate([np.full(b["P"], c, np.int64) for c, b in enumerate(batches)])
     out["P"] = sum(b["P"] for b in batches)
     return out
+
+

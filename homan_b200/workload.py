@@ -13,8 +13,12 @@ CONFIGS = {
     "cfg1": dict(P=1, T=1, obj="cube", lw="sil_obj", seed=1000),
     "cfg2": dict(P=16, T=10, obj="ellipsoid500", lw="step1+sil_hand", seed=2000),
     "cfg3": dict(P=16, T=30, obj="ellipsoid500", lw="step2+sil_hand", seed=3000),
+    # cfg4: 64 clips x 16 inits x 10 frames over 8 GPUs = 8 whole clips (128 problems, 1280 images) per GPU, every clip
+    # with its own object; `clips` = clips per GPU
+    "cfg4": dict(P=16, T=10, obj="ellipsoid500@", lw="step1+sil_hand", seed=4000, clips=8, total_clips=64),
     "cfg5": dict(P=32, T=30, obj="ellipsoid20k", lw="sil_obj", seed=5000),
     "tiny": dict(P=2, T=4, obj="ellipsoid80", lw="step2+sil_hand", seed=7000),
+    "tiny4": dict(P=2, T=3, obj="ellipsoid80@", lw="step2+sil_hand", seed=7400, clips=3, total_clips=3),
 }
 
 
@@ -38,13 +42,24 @@ def gpu_render_fn(device="cuda"):
     return render
 
 
-def make_workload(name, clip_index=0, device="cuda", mano_asset=None, init_shard=0, hand_mesh="delaunay"):
+def make_workload(name, clip_index=0, device="cuda", mano_asset=None, init_shard=0, hand_mesh="delaunay", clips=None):
     """-> (batch dict of numpy arrays [P,T,...], loss weights). `clip_index` selects the synthetic clip (ground-truth
     trajectory and target masks), `init_shard` the block of P random initialisations of that clip, `hand_mesh` the
-    triangulation of the synthetic hand when no asset is passed (synth._hand_template)."""
+    triangulation of the synthetic hand when no asset is passed (synth._hand_template). Multi-clip configurations
+    (cfg4): `clips` = the clip ids to stack (default: the first CONFIGS[name]["clips"]); the batch is clip-major and
+    every clip carries its own object mesh."""
     cfg = CONFIGS[name]
     asset = mano_asset if mano_asset is not None else synth.make_mano_asset(0, "right", mesh=hand_mesh)
-    seed = cfg["seed"] + clip_index
-    clip = synth.make_clip(cfg["T"], cfg["obj"], seed=seed, mano_asset=asset, render_fn=gpu_render_fn(device))
-    inits = synth.make_inits(clip, cfg["P"], seed=seed + 7919 * init_shard)
-    return synth.make_batch(clip, inits), loss_weights(cfg["lw"])
+
+    def one(clip_id, obj):
+        seed = cfg["seed"] + clip_id
+        clip = synth.make_clip(cfg["T"], obj, seed=seed, mano_asset=asset, render_fn=gpu_render_fn(device))
+        inits = synth.make_inits(clip, cfg["P"], seed=seed + 7919 * init_shard)
+        return synth.make_batch(clip, inits)
+
+    if "clips" in cfg:
+        ids = list(range(cfg["clips"])) if clips is None else list(clips)
+        batch = synth.concat_batches([one(c, cfg["obj"] + str(cfg["seed"] + c)) for c in ids])
+        batch["clip_ids"] = np.asarray(ids, np.int64)
+        return batch, loss_weights(cfg["lw"])
+    return one(clip_index, cfg["obj"]), loss_weights(cfg["lw"])

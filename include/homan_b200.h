@@ -192,11 +192,11 @@ int hm_contact_fwd_bwd(const float *verts_hand, const float *verts_obj, int B, i
  * compute_collision_loss, homan/lossutils.py:43-64): phi = clamp(SDF, 0) of the grid mesh in its own
  * normalised bbox cube, sampled trilinearly (grid_sample, zeros padding, align_corners=False) at the other
  * mesh's vertices.  Evaluated sparsely: only the voxels that samples touch.  One call = one ordered pair:
- * grid mesh (verts_g [B,Vg,3], faces_g [Fg,3]) sampled at verts_s [B,Vs,3].
+ * grid mesh (verts_g [B,Vg,3], faces_g [faces_batch,Fg,3] with faces_batch 1 or B) sampled at verts_s [B,Vs,3].
  * partials[b*HM_NPART + HM_PART_COLLISION] += sum of samples; grad_verts_s += weight * d/d verts_s (may be NULL).
  * workspace: phi [B, G^3] fp32 scratch (written sparsely). */
-int hm_sdf_pair(const float *verts_g, const int32_t *faces_g, const float *verts_s, int B, int Vg, int Fg,
-                int Vs, int grid, float scale_factor, float weight, float *phi_scratch, float *partials,
+int hm_sdf_pair(const float *verts_g, const int32_t *faces_g, int faces_batch, const float *verts_s, int B, int Vg,
+                int Fg, int Vs, int grid, float scale_factor, float weight, float *phi_scratch, float *partials,
                 float *grad_verts_s, void *stream);
 /* sdf.SDF()(faces, vertices) (un-vendored `sdf` package; homan/interactions/scenesdf.py:32,119): dense
  * signed distance grid phi [B,G,G,G] (inside positive) of vertices already normalised to [-1,1]^3. */

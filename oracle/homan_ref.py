@@ -276,6 +276,9 @@ def make_optimizer(model, lr):
 def problem_slice(batch, p):
     """Problem p of a batched problem dict (see homan_b200.problem.make_batch)."""
     out = {k: batch[k] for k in ("obj_verts_can", "obj_faces", "hand_faces", "side", "image_size") if k in batch}
+    if np.asarray(batch["obj_verts_can"]).ndim == 3:   # one object per clip (clip-major multi-clip batch)
+        c = int(np.asarray(batch["clip_of_problem"])[p])
+        out["obj_verts_can"], out["obj_faces"] = batch["obj_verts_can"][c], batch["obj_faces"][c]
     for k in ("obj_t", "obj_R", "hand_t", "hand_R", "pca", "mano_rot", "mano_trans", "betas",
               "target_masks_object", "target_masks_hand", "K_roi_obj", "K_roi_hand", "camintr", "verts2d"):
         out[k] = batch[k][p]

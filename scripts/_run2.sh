@@ -1,8 +1,10 @@
-for mesh in delaunay polar; do
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --hand-mesh $mesh > gpurun_out/bench_$mesh.json 2> gpurun_out/bench_a.err; python - <<PY
+python bench.py --workload cfg4 --steps 30 --no-cpu-baseline > gpurun_out/bench_cfg4_n1.json 2> gpurun_out/bench_cfg4_n1.err; tail -3 gpurun_out/bench_cfg4_n1.err; python - <<PY
 import json
-d=json.load(open("gpurun_out/bench_$mesh.json")); b=d["breakdown_us"]
-print("$mesh", d["value"], d["ms_per_step"], {k:v["us_each"] for k,v in b.items() if "raster" in k or "sdf" in k or "mano" in k})
+d=json.load(open("gpurun_out/bench_cfg4_n1.json")); b=d["breakdown_us"]
+print("cfg4", d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], {k:v["us_each"] for k,v in b.items() if "raster" in k or "sdf" in k})
 PY
-done
-bash scripts/gpu_tests.sh 2>&1 | tail -30
+python bench.py --steps 100 > gpurun_out/bench_cfg3_n1.json 2> gpurun_out/bench_cfg3_n1.err; tail -3 gpurun_out/bench_cfg3_n1.err; python - <<PY
+import json
+d=json.load(open("gpurun_out/bench_cfg3_n1.json")); b=d["breakdown_us"]
+print("cfg3", d["value"], d["ms_per_step"], d["e2e"]["value"], d["roofline"]["frac"], d["cpu_baseline"], {k:v["us_each"] for k,v in b.items() if "raster" in k or "sdf" in k or "mano" in k})
+PY

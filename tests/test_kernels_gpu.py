@@ -123,10 +123,10 @@ def test_sdf_pair_matches_oracle(mano_assets):
     phi = torch.empty(B, 32 ** 3, device="cuda")
     s = current_stream()
     d_closed, d_fo = torch.from_numpy(closed).cuda(), torch.from_numpy(fo.astype(np.int32)).cuda()
-    call("hm_sdf_pair", ptr(dh), ptr(d_closed), ptr(do), B, 778, closed.shape[0], vo.shape[1],
+    call("hm_sdf_pair", ptr(dh), ptr(d_closed), 1, ptr(do), B, 778, closed.shape[0], vo.shape[1],
          32, 0.2, 0.0, ptr(phi), ptr(part), None, s)
     a = part[:, 10].sum().item()
-    call("hm_sdf_pair", ptr(do), ptr(d_fo), ptr(dh), B, vo.shape[1],
+    call("hm_sdf_pair", ptr(do), ptr(d_fo), 1, ptr(dh), B, vo.shape[1],
          fo.shape[0], 778, 32, 0.2, 0.5, ptr(phi), ptr(part), ptr(gh), s)
     torch.cuda.synchronize()
     total = part[:, 10].sum().item()
