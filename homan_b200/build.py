@@ -49,7 +49,7 @@ def build(force=False, verbose=False):
             relink = True
         objs.append(obj)
     if relink:
-        subprocess.check_call([_nvcc(), "-shared", "-o", OUT] + objs + ["-lcudart"])
+        subprocess.check_call([_nvcc(), "-shared", "-o", OUT] + objs + ["-lcudart", "-ldl"])
     return OUT
 
 

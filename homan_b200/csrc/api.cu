@@ -14,6 +14,7 @@ void hm_set_error(const char *fmt, ...) {
 }
 
 extern "C" {
-int hm_version(void) { return HM_VERSION; }
+int hm_version(void) {
+ return HM_VERSION; }
 const char *hm_last_error(void) { return g_last_error; }
 }

@@ -6,6 +6,8 @@
 
 #include <atomic>
 
+#include <nvtx3/nvToolsExt.h>   // header-only; a no-op unless a profiler (nsys, ncu --nvtx) is attached
+
 #include "../../include/homan_b200.h"
 
 void hm_set_error(const char *fmt, ...);
@@ -38,6 +40,15 @@ void hm_set_error(const char *fmt, ...);
     } while (0)
 
 static inline cudaStream_t hm_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+// One NVTX range per C-ABI call (named after the entry point): the host-side enqueue of the call's launches.
+struct HmNvtxRange {
+    explicit HmNvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~HmNvtxRange() { nvtxRangePop(); }
+    HmNvtxRange(const HmNvtxRange &) = delete;
+    HmNvtxRange &operator=(const HmNvtxRange &) = delete;
+};
+#define HM_NVTX(name) HmNvtxRange hm_nvtx_range__(name)
 
 // Opt-in to more than 48 KB of dynamic shared memory. The attribute belongs to the (device, kernel) pair, so the
 // bookkeeping is per device: one slot per ordinal, written with relaxed atomics (two host threads racing on the same

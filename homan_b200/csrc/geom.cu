@@ -372,6 +372,7 @@ extern "C" {
 
 int hm_rigid_fwd(const float *mesh, int mesh_batch, const float *rot6d, const float *trans, const float *scale,
                  int B, int V, float *verts, void *stream) {
+    HM_NVTX("hm_rigid_fwd");
     HM_REQUIRE(mesh && rot6d && trans && verts, "hm_rigid_fwd: null pointer");
     HM_REQUIRE(B >= 0 && V > 0 && (mesh_batch == 1 || mesh_batch == B), "hm_rigid_fwd: bad sizes");
     if (B == 0) return HM_OK;
@@ -382,6 +383,7 @@ int hm_rigid_fwd(const float *mesh, int mesh_batch, const float *rot6d, const fl
 
 int hm_rigid_bwd(const float *mesh, int mesh_batch, const float *rot6d, const float *scale, int B, int V,
                  const float *grad_verts, float *grad_rot6d, float *grad_trans, void *stream) {
+    HM_NVTX("hm_rigid_bwd");
     HM_REQUIRE(mesh && rot6d && grad_verts, "hm_rigid_bwd: null pointer");
     HM_REQUIRE(B >= 0 && V > 0 && (mesh_batch == 1 || mesh_batch == B), "hm_rigid_bwd: bad sizes");
     if (B == 0) return HM_OK;
@@ -396,6 +398,7 @@ int hm_vertex_losses(const float *verts_hand, const float *verts_obj, const floa
                      float image_size, float w_smooth_hand, float w_smooth_obj, float w_v2d, float w_inter,
                      float w_pca, int flags, float *partials, float *grad_verts_hand, float *grad_verts_obj,
                      float *grad_centroid_det, float *grad_pca, void *stream) {
+    HM_NVTX("hm_vertex_losses");
     HM_REQUIRE(verts_hand && verts_obj && camintr && partials, "hm_vertex_losses: null pointer");
     HM_REQUIRE(B >= 0 && T > 0 && B % T == 0 && Vo > 0, "hm_vertex_losses: bad sizes (B must be P*T)");
     HM_REQUIRE(!(flags & HM_VL_V2D) || ref_verts2d, "hm_vertex_losses: v2d needs ref_verts2d");
@@ -411,6 +414,7 @@ int hm_vertex_losses(const float *verts_hand, const float *verts_obj, const floa
 
 int hm_finalize_losses(const float *partials, const float *weights_part, int P, int T, float *losses,
                        float *total, int *step_counter, void *stream) {
+    HM_NVTX("hm_finalize_losses");
     HM_REQUIRE(partials && weights_part && losses, "hm_finalize_losses: null pointer");
     HM_REQUIRE(P >= 0 && T > 0, "hm_finalize_losses: bad sizes");
     if (P == 0) return HM_OK;
@@ -424,6 +428,7 @@ int hm_finalize_losses(const float *partials, const float *weights_part, int P, 
 int hm_adam_step(float *params, const float *grads, float *exp_avg, float *exp_avg_sq,
                  const float *lr_per_elem, int n, float beta1, float beta2, float eps,
                  const int *step_counter, void *stream) {
+    HM_NVTX("hm_adam_step");
     HM_REQUIRE(params && grads && exp_avg && exp_avg_sq && lr_per_elem && step_counter, "hm_adam_step: null pointer");
     HM_REQUIRE(n >= 0, "hm_adam_step: bad size");
     if (n == 0) return HM_OK;
@@ -435,6 +440,7 @@ int hm_adam_step(float *params, const float *grads, float *exp_avg, float *exp_a
 
 int hm_argmin_over_inits(const float *total, int C, int I, int32_t *best_index, float *best_loss,
                          void *stream) {
+    HM_NVTX("hm_argmin_over_inits");
     HM_REQUIRE(total && best_index, "hm_argmin_over_inits: null pointer");
     HM_REQUIRE(C >= 0 && I > 0, "hm_argmin_over_inits: bad sizes");
     if (C == 0) return HM_OK;
@@ -445,6 +451,7 @@ int hm_argmin_over_inits(const float *total, int C, int I, int32_t *best_index, 
 
 int hm_offscreen_loss_fwd_bwd(const float *ndc, int B, int V, float far_, float weight, float *partials,
                               float *grad_ndc, void *stream) {
+    HM_NVTX("hm_offscreen_loss_fwd_bwd");
     HM_REQUIRE(ndc && partials, "hm_offscreen_loss_fwd_bwd: null pointer");
     HM_REQUIRE(B >= 0 && V >= 0, "hm_offscreen_loss_fwd_bwd: bad sizes");
     if (B == 0) return HM_OK;
@@ -454,6 +461,7 @@ int hm_offscreen_loss_fwd_bwd(const float *ndc, int B, int V, float far_, float 
 }
 int hm_track_best(const float *total, int N, const float *rot6d, const float *trans, float *best,
                   int32_t *best_index, void *stream) {
+    HM_NVTX("hm_track_best");
     HM_REQUIRE(total && rot6d && trans && best, "hm_track_best: null pointer");
     HM_REQUIRE(N >= 0, "hm_track_best: bad size");
     if (N == 0) return HM_OK;

@@ -455,6 +455,7 @@ extern "C" {
 int hm_mano_fwd(const float *model, int ncomps, int left, const float *pca, int pca_stride, const float *rot,
                 const float *betas, const float *mano_trans, const float *rot6d, const float *trans,
                 const float *scale, int B, float *verts, float *joints, void *stream) {
+    HM_NVTX("hm_mano_fwd");
     HM_REQUIRE(model && pca && rot && verts, "hm_mano_fwd: null pointer");
     HM_REQUIRE(B >= 0 && ncomps >= 0 && ncomps <= 45 && pca_stride >= ncomps, "hm_mano_fwd: bad sizes");
     if (B == 0) return HM_OK;
@@ -469,6 +470,7 @@ int hm_mano_bwd(const float *model, int ncomps, int left, const float *pca, int 
                 const float *scale, int B, const float *grad_verts, const float *grad_centroid_det,
                 float *grad_pca, float *grad_rot, float *grad_betas, float *grad_mano_trans, float *grad_rot6d,
                 float *grad_trans, void *stream) {
+    HM_NVTX("hm_mano_bwd");
     HM_REQUIRE(model && pca && rot && grad_verts, "hm_mano_bwd: null pointer");
     HM_REQUIRE(B >= 0 && ncomps >= 0 && ncomps <= 45 && pca_stride >= ncomps, "hm_mano_bwd: bad sizes");
     if (B == 0) return HM_OK;

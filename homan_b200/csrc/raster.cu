@@ -14,6 +14,12 @@
 
 namespace {
 
+// Named knob, parity unpinned (the un-vendored package is not available): upstream's face set-up reportedly keeps
+// the barycentric determinant away from zero (|det| >= 1e-10) before dividing by it. 0 = divide by the raw determinant.
+// The oracle carries the same constant (NMR_DET_CLAMP in oracle/csrc/nmr_raster.c); they must be changed together.
+#ifndef HM_RASTER_DET_CLAMP
+#define HM_RASTER_DET_CLAMP 0.f
+#endif
 constexpr int TILE = 64;
 constexpr int NTHREADS = 256;
 constexpr int NWARPS = NTHREADS / 32;
@@ -187,7 +193,11 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
         const float m[9] = {p11 - p21, p20 - p10, p10 * p21 - p20 * p11,
                             p21 - p01, p00 - p20, p20 * p01 - p00 * p21,
                             p01 - p11, p10 - p00, p00 * p11 - p10 * p01};
-        const float den = p20 * (p01 - p11) + p00 * (p11 - p21) + p10 * (p21 - p01);
+        float den = p20 * (p01 - p11) + p00 * (p11 - p21) + p10 * (p21 - p01);
+        if (HM_RASTER_DET_CLAMP > 0.f) {   // (see the constant: 0 = the raw determinant, as the oracle)
+            if (den > 0.f) den = fmaxf(den, HM_RASTER_DET_CLAMP);
+            else den = fminf(den, -HM_RASTER_DET_CLAMP);
+        }
 #pragma unroll
         for (int k = 0; k < 9; ++k) r.inv[k] = m[k] / den;
         r.exact = 0;
@@ -1542,6 +1552,40 @@ raster_shade_kernel(const FaceRec *__restrict__ recs, const int32_t *__restrict_
     if (depth) depth[(long)b * plane + o] = acc[3] * s;
 }
 
+// nr.lighting for flat per-face colours (texture_size 1), both windings of every face: normal of the 3-D triangle
+// n = (v0 - v1) x (v2 - v1) / max(|.|, 1e-5), light = ambient + directional * relu(n . direction), lit = colour * light.
+// lit [B, 2F, 3]: face f, then its reversed (fill_back) copy F + f (normal negated; zeros when fill_back is off).
+__global__ void __launch_bounds__(NTHREADS)
+face_lighting_kernel(const float *__restrict__ verts, const int32_t *__restrict__ faces, int faces_batch,
+                     const float *__restrict__ colours, int colours_batch, int B, int V, int F, int fill_back, float ia,
+                     float id, float ca0, float ca1, float ca2, float cd0, float cd1, float cd2, float d0, float d1,
+                     float d2, float *__restrict__ lit) {
+    const long i = (long)blockIdx.x * NTHREADS + threadIdx.x;
+    if (i >= (long)B * F) return;
+    const int b = (int)(i / F), f = (int)(i % F);
+    const int32_t *fc = faces + ((faces_batch > 1 ? (long)b * F : 0) + f) * 3;
+    const float *col = colours + ((colours_batch > 1 ? (long)b * F : 0) + f) * 3;
+    float p[3][3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int vi = min(max(fc[k], 0), V - 1);
+        const float *q = verts + ((long)b * V + vi) * 3;
+        p[k][0] = q[0]; p[k][1] = q[1]; p[k][2] = q[2];
+    }
+    const float a[3] = {p[0][0] - p[1][0], p[0][1] - p[1][1], p[0][2] - p[1][2]};
+    const float c[3] = {p[2][0] - p[1][0], p[2][1] - p[1][1], p[2][2] - p[1][2]};
+    float n[3] = {a[1] * c[2] - a[2] * c[1], a[2] * c[0] - a[0] * c[2], a[0] * c[1] - a[1] * c[0]};
+    const float inv = 1.f / fmaxf(sqrtf(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]), 1e-5f);
+    const float cs = (n[0] * d0 + n[1] * d1 + n[2] * d2) * inv;
+    const float amb[3] = {ia * ca0, ia * ca1, ia * ca2}, dirc[3] = {id * cd0, id * cd1, id * cd2};
+    float *o0 = lit + ((long)b * 2 * F + f) * 3, *o1 = lit + ((long)b * 2 * F + F + f) * 3;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        o0[k] = col[k] * (amb[k] + dirc[k] * fmaxf(cs, 0.f));
+        o1[k] = fill_back ? col[k] * (amb[k] + dirc[k] * fmaxf(-cs, 0.f)) : 0.f;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ silhouette loss
 __global__ void __launch_bounds__(NTHREADS)
 sil_loss_kernel(const float *__restrict__ alpha, const int8_t *__restrict__ target, const float *__restrict__ norm,
@@ -1601,6 +1645,7 @@ extern "C" {
 int hm_project_fwd(const float *verts, const float *K, int K_batch, const float *R, const float *t,
                    const float *dist, int dist_batch, float orig_size, float eps, int B, int V, float *ndc,
                    void *stream) {
+    HM_NVTX("hm_project_fwd");
     HM_REQUIRE(verts && K && ndc, "hm_project_fwd: null pointer");
     HM_REQUIRE(B >= 0 && V >= 0 && (K_batch == 1 || K_batch == B), "hm_project_fwd: bad sizes B=%d V=%d K_batch=%d", B, V, K_batch);
     if ((long)B * V == 0) return HM_OK;
@@ -1614,6 +1659,7 @@ int hm_project_fwd(const float *verts, const float *K, int K_batch, const float 
 int hm_project_bwd(const float *verts, const float *K, int K_batch, const float *R, const float *t,
                    float orig_size, float eps, int B, int V, const float *grad_ndc, float *grad_verts,
                    int accumulate, void *stream) {
+    HM_NVTX("hm_project_bwd");
     HM_REQUIRE(verts && K && grad_ndc && grad_verts, "hm_project_bwd: null pointer");
     HM_REQUIRE(B >= 0 && V >= 0 && (K_batch == 1 || K_batch == B), "hm_project_bwd: bad sizes");
     if ((long)B * V == 0) return HM_OK;
@@ -1628,6 +1674,7 @@ int hm_project_bwd(const float *verts, const float *K, int K_batch, const float 
 int hm_raster_setup(const float *ndc, const int32_t *faces, int faces_batch, int B, int V, int F,
                     int image_size, int anti_aliasing, int fill_back, void *records, void *bboxes,
                     void *stream) {
+    HM_NVTX("hm_raster_setup");
     HM_REQUIRE(B >= 0 && V >= 0 && F >= 0 && (faces_batch == 1 || faces_batch == B), "hm_raster_setup: bad sizes");
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
@@ -1654,6 +1701,7 @@ int hm_raster_setup(const float *ndc, const int32_t *faces, int faces_batch, int
 int hm_raster_sil_fwd(const void *records, const void *bboxes, int B, int F, int image_size,
                       int anti_aliasing, float near_, float far_, int32_t *face_index, float *alpha,
                       uint32_t *cov_row, uint32_t *cov_col, uint32_t *face_vis, uint8_t *cov_blocks, void *stream) {
+    HM_NVTX("hm_raster_sil_fwd");
     HM_REQUIRE(B >= 0 && F >= 0 && B <= 65535, "hm_raster_sil_fwd: bad sizes (B <= 65535)");
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
@@ -1680,6 +1728,7 @@ int hm_raster_sil_fwd(const void *records, const void *bboxes, int B, int F, int
 int hm_raster_grad_prep(const float *grad_alpha, const uint32_t *cov_row, const uint32_t *cov_col, int B,
                         int image_size, int anti_aliasing, uint32_t *m_row, uint32_t *m_col, void *runs,
                         uint32_t *run_counts, void *stream) {
+    HM_NVTX("hm_raster_grad_prep");
     HM_REQUIRE(B >= 0 && B <= 65535, "hm_raster_grad_prep: bad sizes");
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
@@ -1707,6 +1756,7 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
                       const uint32_t *m_row, const uint32_t *m_col, const void *runs, const uint32_t *run_counts,
                       int B, int V, int F, int image_size, int anti_aliasing, float eps, float *grad_ndc,
                       void *stream) {
+    HM_NVTX("hm_raster_sil_bwd");
     HM_REQUIRE(B >= 0 && F >= 0 && V >= 0 && B <= 65535, "hm_raster_sil_bwd: bad sizes");
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
@@ -1728,6 +1778,7 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
 int hm_sil_loss_fwd_bwd(const float *alpha, const int8_t *target, const float *norm, float weight, int B,
                         int image_size, float *loss_img, int loss_stride, float *iou_img, int iou_stride,
                         float *grad_alpha, void *stream) {
+    HM_NVTX("hm_sil_loss_fwd_bwd");
     HM_REQUIRE(alpha && target && norm, "hm_sil_loss_fwd_bwd: null pointer");
     HM_REQUIRE(B >= 0 && image_size > 0 && (image_size * image_size) % 4 == 0, "hm_sil_loss_fwd_bwd: bad sizes");
     if (B == 0) return HM_OK;
@@ -1737,9 +1788,29 @@ int hm_sil_loss_fwd_bwd(const float *alpha, const int8_t *target, const float *n
     return HM_OK;
 }
 
+int hm_face_lighting(const float *verts, const int32_t *faces, int faces_batch, const float *colours, int colours_batch,
+                     int B, int V, int F, int fill_back, float intensity_ambient, float intensity_directional,
+                     const float *color_ambient, const float *color_directional, const float *direction, float *lit,
+                     void *stream) {
+    HM_NVTX("hm_face_lighting");
+    HM_REQUIRE(B >= 0 && V >= 0 && F >= 0 && (faces_batch == 1 || faces_batch == B) && (colours_batch == 1 || colours_batch == B),
+               "hm_face_lighting: bad sizes");
+    if ((long)B * F == 0) return HM_OK;
+    HM_REQUIRE(verts && faces && colours && color_ambient && color_directional && direction && lit && V > 0,
+               "hm_face_lighting: null pointer");
+    const long n = (long)B * F;   // (the three host vectors are read here, at enqueue time)
+    face_lighting_kernel<<<(unsigned)((n + NTHREADS - 1) / NTHREADS), NTHREADS, 0, hm_stream(stream)>>>(
+        verts, faces, faces_batch, colours, colours_batch, B, V, F, fill_back, intensity_ambient, intensity_directional,
+        color_ambient[0], color_ambient[1], color_ambient[2], color_directional[0], color_directional[1],
+        color_directional[2], direction[0], direction[1], direction[2], lit);
+    HM_CHECK_LAUNCH("hm_face_lighting");
+    return HM_OK;
+}
+
 int hm_raster_shade(const void *records, const int32_t *face_index, const float *colours, int colours_batch, int B,
                     int F, int image_size, int anti_aliasing, float far_, float bg_r, float bg_g, float bg_b,
                     float *rgb, float *depth, void *stream) {
+    HM_NVTX("hm_raster_shade");
     HM_REQUIRE(B >= 0 && F >= 0 && (colours_batch == 1 || colours_batch == B), "hm_raster_shade: bad sizes");
     int is;
     if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;

@@ -114,7 +114,8 @@ __device__ __forceinline__ Corner unnormalise(float x, float y, float z) {
 __global__ void __launch_bounds__(PNT)
 sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ faces, int faces_batch,
                 const float *__restrict__ verts_s, int Vg, int Fg, int Vs, float half_factor, float weight,
-                float *__restrict__ phi_all, float *__restrict__ partials, float *__restrict__ g_vs) {
+                float *__restrict__ phi_all, float *__restrict__ partials, float *__restrict__ g_vs,
+                float *__restrict__ dist_values) {
     extern __shared__ __align__(16) float lv[];  // Vg * 3 normalised mesh vertices, then Fg bounding spheres
     float4 *sph = reinterpret_cast<float4 *>(lv + ((Vg * 3 + 3) / 4) * 4);
     __shared__ unsigned needed[G * G], inside[G * G];
@@ -281,6 +282,7 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
                     gz += val * wx * wy * (dz ? 1.f : -1.f);
                 }
         acc[0] += out;
+        if (dist_values) dist_values[(long)b * Vs + i] = out * sc;   // back in the scene's units (scenesdf.py:143-146)
         if (g_vs && weight != 0.f) {
             const float k = weight * (0.5f * G) / sc;
             float *g = g_vs + ((long)b * Vs + i) * 3;
@@ -323,7 +325,8 @@ extern "C" {
 
 int hm_sdf_pair(const float *verts_g, const int32_t *faces_g, int faces_batch, const float *verts_s, int B, int Vg,
                 int Fg, int Vs, int grid, float scale_factor, float weight, float *phi_scratch, float *partials,
-                float *grad_verts_s, void *stream) {
+                float *grad_verts_s, float *dist_values, void *stream) {
+    HM_NVTX("hm_sdf_pair");
     HM_REQUIRE(verts_g && faces_g && verts_s && phi_scratch && partials, "hm_sdf_pair: null pointer");
     HM_REQUIRE(B >= 0 && Vg > 0 && Fg > 0 && Vs > 0 && (faces_batch == 1 || faces_batch == B), "hm_sdf_pair: bad sizes");
     HM_UNSUPPORTED(grid != G, "hm_sdf_pair: grid size %d (only %d, the reference's grid_size)", grid, G);
@@ -334,13 +337,14 @@ int hm_sdf_pair(const float *verts_g, const int32_t *faces_g, int faces_batch, c
     if (int rc = hm_smem_opt_in(sdf_pair_kernel, smem, opt_in, "hm_sdf_pair")) return rc;
     const float half_factor = (float)((1.0 + (double)scale_factor) * 0.5);
     sdf_pair_kernel<<<B, PNT, smem, hm_stream(stream)>>>(verts_g, faces_g, faces_batch, verts_s, Vg, Fg, Vs, half_factor,
-                                                        weight, phi_scratch, partials, grad_verts_s);
+                                                        weight, phi_scratch, partials, grad_verts_s, dist_values);
     HM_CHECK_LAUNCH("hm_sdf_pair");
     return HM_OK;
 }
 
 int hm_sdf_grid(const int32_t *faces, const float *verts, int B, int V, int F, int grid, float *phi,
                 void *stream) {
+    HM_NVTX("hm_sdf_grid");
     HM_REQUIRE(faces && verts && phi, "hm_sdf_grid: null pointer");
     HM_REQUIRE(B >= 0 && B <= 65535 && V > 0 && F > 0 && grid > 0 && grid <= 256, "hm_sdf_grid: bad sizes");
     if (B == 0) return HM_OK;

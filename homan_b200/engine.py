@@ -298,11 +298,11 @@ class FitEngine:
             # pair (hand grid <- object vertices): value only (the object is detached, homan.py:445-449)
             call("hm_sdf_pair", ptr(self.verts_hand), ptr(self.faces_hand_closed), 1, ptr(self.verts_obj), B, 778,
                  self.faces_hand_closed.shape[0], self.Vo, SDF_GRID, SDF_SCALE_FACTOR, 0.0, ptr(self.phi_scratch),
-                 ptr(self.partials), None, s)
+                 ptr(self.partials), None, None, s)
             # pair (object grid <- hand vertices): gradient to the hand
             call("hm_sdf_pair", ptr(self.verts_obj), ptr(self.faces_obj), self.faces_obj.shape[0], ptr(self.verts_hand), B, self.Vo,
                  self.faces_obj.shape[1], 778, SDF_GRID, SDF_SCALE_FACTOR, lw["lw_collision"], ptr(self.phi_scratch),
-                 ptr(self.partials), ptr(self.g_verts_hand), s)
+                 ptr(self.partials), ptr(self.g_verts_hand), None, s)
             n += 2
         g = self.grads
         call("hm_mano_bwd", ptr(self.mano), self.ncomps, self.side_left, ptr(self.params["mano_pca_pose"]),

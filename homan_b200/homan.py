@@ -134,6 +134,20 @@ class HOMan(nn.Module):
         with torch.no_grad():
             self.verts_object_init, _ = self.get_verts_object()
             self.verts_hand_init, _ = self.get_verts_hand()
+        # ---- visualisation (homan/homan.py:168-217): full-frame renderer, object gold + hand grey, one combined mesh
+        from .shims import neural_renderer as nr
+        from .visualize import COLORS
+        self.renderer = nr.Renderer(image_size=image_size, K=self.camintr.clone(), R=torch.eye(3, device=dev)[None],
+                                    t=torch.zeros(1, 3, device=dev), orig_size=1)
+        self.renderer.light_direction = [1, 0.5, 1]
+        self.renderer.light_intensity_direction = 0.3   # (sic: the reference sets this misspelt, unused attribute)
+        self.renderer.light_intensity_ambient = 0.5
+        self.renderer.background_color = [1.0, 1.0, 1.0]
+        fo_, fh_ = torch.as_tensor(batch["obj_faces"]).long().to(dev), torch.as_tensor(batch["hand_faces"]).long().to(dev)
+        self.faces = torch.cat((fo_, fh_ + batch["obj_verts_can"].shape[0]))[None].repeat(B, 1, 1)
+        tex = torch.cat((torch.tensor(COLORS["gold"], device=dev).expand(fo_.shape[0], 3),
+                         torch.tensor(COLORS["grey"], device=dev).expand(fh_.shape[0], 3)))
+        self.textures = tex.view(1, -1, 1, 1, 1, 3).repeat(B, 1, 1, 1, 1, 1)
 
     # ------------------------------------------------------------------ engine plumbing
     def _build_engine(self, loss_weights):
@@ -168,6 +182,26 @@ class HOMan(nn.Module):
         self.engine._forward_vertices(s)
         v = self.engine.verts_hand.clone()
         return v, v
+
+    def render_limem(self, renderer, verts, faces, textures, K, max_in_batch=5):
+        """homan/homan.py:510-545: (images [N,S,S,3] in [0,1], masks [N,S,S] bool). One batch (memory is not the limit
+        here: `max_in_batch` is accepted and ignored)."""
+        rgb, _, alpha = renderer.render(vertices=verts, faces=faces, textures=textures, K=K)
+        return np.clip(rgb.permute(0, 2, 3, 1).cpu().numpy(), 0, 1), alpha.cpu().numpy().astype(bool)
+
+    def render(self, renderer=None, rotate=False, viz_len=10, max_in_batch=None):
+        """homan/homan.py:547-562: RGB render of the fitted object + hand of the first `viz_len` frames (optionally
+        rotated about the scene centroid for the "top-down" view)."""
+        from .visualize import rot_points
+        renderer = self.renderer if renderer is None else renderer
+        with torch.no_grad():
+            verts = torch.cat((self.get_verts_object()[0], self.get_verts_hand()[0]), 1)
+            if rotate:
+                verts = rot_points(verts)
+            K = renderer.K.view(-1, 3, 3)
+            K = K.repeat(verts.shape[0] // K.shape[0], 1, 1) if verts.shape[0] % K.shape[0] == 0 else K[:1].expand(verts.shape[0], -1, -1)
+            return self.render_limem(renderer, verts[:viz_len].contiguous(), self.faces[:viz_len], self.textures[:viz_len],
+                                     K=K[:viz_len].contiguous(), max_in_batch=max_in_batch)
 
     def forward(self, loss_weights=None):
         if loss_weights is None:

@@ -3,7 +3,8 @@
 The loop body of the reference (jointopt.py:158-192: zero_grad, forward, weighting, backward, Adam with its
 three learning-rate groups) is one CUDA-graph replay of the fused engine per iteration; the per-iteration
 `.item()` logging of the reference becomes one device-side copy per iteration and a single read-back at the
-end. Visualisation (`viz_step`, gif / video writing) is out of scope: `imgs` is returned empty.
+end. When `images` are given, every `viz_step` iterations the fitted scene is rendered (RGB, sm_100a rasteriser)
+over the frames and saved as JPEG, as the reference does; the gif / video writers are out of scope.
 """
 import os
 from collections import OrderedDict, defaultdict
@@ -13,6 +14,22 @@ import torch
 
 from .engine import NPART
 from .homan import HOMan
+
+
+def _save_viz(model, images, viz_folder, step, viz_len):
+    """The periodic picture of /root/reference/homan/jointopt.py:159-177: frontal views side by side over the top-down
+    views, at half size, as <viz_folder>/<step:08d>.jpg. (The gif / webm / mp4 writers around it are out of scope.)"""
+    from PIL import Image
+    from .visualize import visualize_hand_object
+    with torch.no_grad():
+        frontal, top_down = visualize_hand_object(model, images, dist=1, viz_len=viz_len)
+    frontal = np.concatenate(list(frontal), 1)
+    top_down = np.concatenate(list(top_down), 1)
+    front_top = np.concatenate([frontal, top_down[:frontal.shape[0], :frontal.shape[1]]], 0)
+    front_top = Image.fromarray(front_top).resize((front_top.shape[1] // 2, front_top.shape[0] // 2), Image.BILINEAR)
+    path = os.path.join(viz_folder, f"{step:08d}.jpg")
+    front_top.save(path)
+    return path
 
 
 def optimize_hand_object(person_parameters, object_parameters, class_name="default", objvertices=None, objfaces=None,
@@ -44,7 +61,10 @@ def optimize_hand_object(person_parameters, object_parameters, class_name="defau
     eng = model.engine
     hist = torch.zeros(num_iterations, eng.P, NPART, device=eng.device)
     tot = torch.zeros(num_iterations, eng.P, device=eng.device)
+    imgs = OrderedDict()
     for it in range(num_iterations):
+        if images is not None and viz_step and it % viz_step == 0:   # jointopt.py:159-177
+            imgs[it] = _save_viz(model, images, viz_folder, it, viz_len)
         eng.step()
         hist[it].copy_(eng.losses)
         tot[it].copy_(eng.total)
@@ -58,4 +78,4 @@ def optimize_hand_object(person_parameters, object_parameters, class_name="defau
             loss_evolution[k].append(float(v.max() if k == "handobj_maxdist" else v.mean()))
         loss_evolution["loss"].append(float(tot_c[it].sum()))
     model.loss_per_problem = tot_c  # [iterations, P] (problem-axis extension)
-    return model, dict(loss_evolution), OrderedDict()
+    return model, dict(loss_evolution), imgs

@@ -157,6 +157,26 @@ def lighting(faces_xyz, colours, intensity_ambient=0.5, intensity_directional=0.
     return colours * light
 
 
+def face_lighting(verts, faces, colours, fill_back=True, intensity_ambient=0.5, intensity_directional=0.5,
+                  color_ambient=(1, 1, 1), color_directional=(1, 1, 1), direction=(0, 1, 0)):
+    """nr.lighting for flat per-face colours, in the kernel (hm_face_lighting): verts [B,V,3], faces [1|B,F,3],
+    colours [1|B,F,3] -> lit colours [B,2F,3] in the doubled numbering (f, F + f = reversed copy)."""
+    import ctypes
+    _check_cuda(verts, faces, colours)
+    v = _f32(verts)
+    f = faces.detach().contiguous().int()
+    f = f[None] if f.dim() == 2 else f
+    c = _f32(colours).view(-1, f.shape[1], 3)
+    B, V, F = v.shape[0], v.shape[1], f.shape[1]
+    lit = torch.empty(B, 2 * F, 3, device=v.device)
+    vec = lambda x: (ctypes.c_float * 3)(*[float(y) for y in x])  # noqa: E731  (host vectors, read at enqueue time)
+    ca, cd, d = vec(color_ambient), vec(color_directional), vec(direction)
+    call("hm_face_lighting", ptr(v), ptr(f), f.shape[0], ptr(c), c.shape[0], B, V, F, int(bool(fill_back)),
+         float(intensity_ambient), float(intensity_directional), ctypes.addressof(ca), ctypes.addressof(cd),
+         ctypes.addressof(d), ptr(lit), current_stream())
+    return lit
+
+
 def render_rgbd(ndc, faces, lit_colours, image_size=256, anti_aliasing=True, fill_back=True, near=NEAR, far=FAR,
                 background_color=(0, 0, 0)):
     """Forward of nr.rasterize_rgbad for texture_size 1 (visualisation, no gradient): ndc [B,V,3] projected

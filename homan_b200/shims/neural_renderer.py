@@ -62,21 +62,12 @@ class Renderer(nn.Module):
         dist_coeffs = self.dist_coeffs if dist_coeffs is None else dist_coeffs
         orig_size = self.orig_size if orig_size is None else orig_size
         with torch.no_grad():
-            B, F = vertices.shape[0], faces.shape[-2]
-            f = faces if faces.dim() == 3 else faces[None]
-            f = f.expand(B, -1, -1)
-            colours = textures.reshape(textures.shape[0], F, 3).float().expand(B, -1, -1)
-            if self.fill_back:
-                f2 = torch.cat((f, f.flip(-1)), dim=1)
-                colours = torch.cat((colours, colours), dim=1)
-            else:
-                f2 = f
-                colours = torch.cat((colours, torch.zeros_like(colours)), dim=1)
-            lit = ops.lighting(vertices_to_faces(vertices.float(), f2), colours[:, :f2.shape[1]],
-                               self.light_intensity_ambient, self.light_intensity_directional,
-                               self.light_color_ambient, self.light_color_directional, self.light_direction)
-            if not self.fill_back:
-                lit = torch.cat((lit, torch.zeros_like(lit)), dim=1)
+            F = faces.shape[-2]
+            f = faces if faces.dim() == 3 else faces[None]   # [1|B,F,3]
+            colours = textures.reshape(textures.shape[0], F, 3).float()
+            lit = ops.face_lighting(vertices, f, colours, self.fill_back, self.light_intensity_ambient,
+                                    self.light_intensity_directional, self.light_color_ambient,
+                                    self.light_color_directional, self.light_direction)
             ndc = ops.project(vertices, K, R, t, dist_coeffs, orig_size)
             return ops.render_rgbd(ndc, f, lit, self.image_size, self.anti_aliasing, self.fill_back, self.near,
                                    self.far, self.background_color)

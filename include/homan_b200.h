@@ -94,6 +94,14 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
  * colours [colours_batch, 2F, 3] = lit colour of every face in the doubled numbering (f, F + f);
  * rgb [B,3,R,R] (may be NULL) = colour of the winning face or the background, depth [B,R,R] (may be NULL) = the
  * reference's interpolated depth or `far`; both after the vertical flip and the 2x2 average when anti-aliasing. */
+/* nr.lighting for flat per-face colours (the lighting step of Renderer.render, texture_size 1): verts [B,V,3] (3-D, the
+ * space the light direction lives in), faces [faces_batch,F,3], colours [colours_batch,F,3]; the three light vectors
+ * are HOST pointers to 3 floats. -> lit [B,2F,3] in the doubled numbering hm_raster_shade reads (F + f = the reversed
+ * copy, lit from its flipped normal; zeros when fill_back is 0). */
+int hm_face_lighting(const float *verts, const int32_t *faces, int faces_batch, const float *colours, int colours_batch,
+                     int B, int V, int F, int fill_back, float intensity_ambient, float intensity_directional,
+                     const float *color_ambient, const float *color_directional, const float *direction, float *lit,
+                     void *stream);
 int hm_raster_shade(const void *records, const int32_t *face_index, const float *colours, int colours_batch, int B,
                     int F, int image_size, int anti_aliasing, float far_, float bg_r, float bg_g, float bg_b,
                     float *rgb, float *depth, void *stream);
@@ -193,11 +201,13 @@ int hm_contact_fwd_bwd(const float *verts_hand, const float *verts_obj, int B, i
  * normalised bbox cube, sampled trilinearly (grid_sample, zeros padding, align_corners=False) at the other
  * mesh's vertices.  Evaluated sparsely: only the voxels that samples touch.  One call = one ordered pair:
  * grid mesh (verts_g [B,Vg,3], faces_g [faces_batch,Fg,3] with faces_batch 1 or B) sampled at verts_s [B,Vs,3].
- * partials[b*HM_NPART + HM_PART_COLLISION] += sum of samples; grad_verts_s += weight * d/d verts_s (may be NULL).
+ * partials[b*HM_NPART + HM_PART_COLLISION] += sum of samples; grad_verts_s += weight * d/d verts_s (may be NULL);
+ * dist_values [B,Vs] (may be NULL) = the samples in scene units, the `dist_values[(g, s)]` of the reference, which its
+ * penetration metric reads (homan/eval/pointmetrics.py:102-124).
  * workspace: phi [B, G^3] fp32 scratch (written sparsely). */
 int hm_sdf_pair(const float *verts_g, const int32_t *faces_g, int faces_batch, const float *verts_s, int B, int Vg,
                 int Fg, int Vs, int grid, float scale_factor, float weight, float *phi_scratch, float *partials,
-                float *grad_verts_s, void *stream);
+                float *grad_verts_s, float *dist_values, void *stream);
 /* sdf.SDF()(faces, vertices) (un-vendored `sdf` package; homan/interactions/scenesdf.py:32,119): dense
  * signed distance grid phi [B,G,G,G] (inside positive) of vertices already normalised to [-1,1]^3. */
 int hm_sdf_grid(const int32_t *faces, const float *verts, int B, int V, int F, int grid, float *phi,

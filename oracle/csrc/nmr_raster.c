@@ -30,6 +30,21 @@ static inline int f2i(float v) {
     return (int)v;
 }
 
+/* Named knob (parity unpinned, like the raster eps): upstream's face set-up reportedly keeps the barycentric
+ * determinant away from zero (|det| >= 1e-10) before dividing by it. Only faces that are degenerate to that degree
+ * are affected (their samples fail the near / far test either way: inf or NaN depth). 0 = divide by the raw
+ * determinant. The CUDA kernel carries the same constant (HM_RASTER_DET_CLAMP in homan_b200/csrc/raster.cu). */
+#ifndef NMR_DET_CLAMP
+#define NMR_DET_CLAMP 0.f
+#endif
+static inline float clamp_det(float den) {
+    if (NMR_DET_CLAMP > 0.f) {
+        if (den > 0.f) return den < NMR_DET_CLAMP ? NMR_DET_CLAMP : den;
+        return den > -NMR_DET_CLAMP ? -NMR_DET_CLAMP : den;
+    }
+    return den;
+}
+
 static inline int is_backface(const float *f) {
     /* f = x0 y0 z0 x1 y1 z1 x2 y2 z2 */
     return (f[7] - f[1]) * (f[3] - f[0]) < (f[4] - f[1]) * (f[6] - f[0]);
@@ -68,6 +83,7 @@ void nmr_face_index_map(const float *faces, int B, int nf, int is, float near_, 
                 p[0][1] - p[1][1], p[1][0] - p[0][0], p[0][0] * p[1][1] - p[1][0] * p[0][1]};
             float den = p[2][0] * (p[0][1] - p[1][1]) + p[0][0] * (p[1][1] - p[2][1]) +
                         p[1][0] * (p[2][1] - p[0][1]);
+            den = clamp_det(den);
             for (int k = 0; k < 9; ++k) inv[k] /= den;
             /* conservative pixel bbox (1 px slack each side) */
             float xmin = fminf(fminf(p[0][0], p[1][0]), p[2][0]), xmax = fmaxf(fmaxf(p[0][0], p[1][0]), p[2][0]);

@@ -104,3 +104,31 @@ def test_shims_match_oracle(mano_assets):
     (vg * w.cuda()).sum().backward()
     assert (pg.grad.cpu() - po.grad).abs().max() <= 1e-4 * po.grad.abs().max()
     assert lg.hand_components.shape == (16, 45) and lg.hand_mean.shape == (45,)
+
+
+def test_visualisation_inside_the_loop(mano_assets, tmp_path):
+    """viz_step of optimize_hand_object (/root/reference/homan/jointopt.py:159-177): every k iterations the fitted scene
+    is rendered over the frames and saved; HOMan.render (homan/homan.py:547-562) returns images and masks."""
+    from PIL import Image
+    from homan_b200.jointopt import optimize_hand_object
+    z, batch, lw, iters = load("ref_small_step2", mano_assets["right"])
+    inp = reference_inputs(batch, 0, mano_assets["right"])
+    T = batch["T"]
+    frames = [np.full((480, 640, 3), 64, np.uint8) for _ in range(T)]
+    model, ev, imgs = optimize_hand_object(loss_weights=lw, num_iterations=5, lr=1e-2, viz_folder=str(tmp_path),
+                                           optimize_mano=True, optimize_mano_beta=True, image_size=640, images=frames,
+                                           viz_step=2, viz_len=3, mano_asset=mano_assets["right"], **inp)
+    assert list(imgs.keys()) == [0, 2, 4]
+    n = min(3, T)
+    for path in imgs.values():
+        im = np.asarray(Image.open(path))
+        assert im.shape == ((480 + 480) // 2, 640 * n // 2, 3) and im.std() > 5   # top-down view cropped to the frame
+    rends, masks = model.render(viz_len=3)
+    assert rends.shape == (n, 640, 640, 3) and masks.shape == (n, 640, 640) and masks.any() and not masks.all()
+    # the object is gold and the hand grey (flat lighting keeps the hue): both colours are present where the mask is set
+    px = rends[masks]
+    assert (px[:, 2] < 0.3 * px[:, 0]).any() and (np.abs(px[:, 0] - px[:, 2]) < 0.02).any()
+    assert np.allclose(rends[~masks], 1.0)   # white background
+    # the loss values are those of the run without pictures
+    ref = z["ev_loss_p0"]
+    assert np.all(np.abs(np.asarray(ev["loss"])[:2] - ref[:2]) <= 1e-4 * np.abs(ref[:2]))

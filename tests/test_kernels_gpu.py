@@ -124,10 +124,10 @@ def test_sdf_pair_matches_oracle(mano_assets):
     s = current_stream()
     d_closed, d_fo = torch.from_numpy(closed).cuda(), torch.from_numpy(fo.astype(np.int32)).cuda()
     call("hm_sdf_pair", ptr(dh), ptr(d_closed), 1, ptr(do), B, 778, closed.shape[0], vo.shape[1],
-         32, 0.2, 0.0, ptr(phi), ptr(part), None, s)
+         32, 0.2, 0.0, ptr(phi), ptr(part), None, None, s)
     a = part[:, 10].sum().item()
     call("hm_sdf_pair", ptr(do), ptr(d_fo), 1, ptr(dh), B, vo.shape[1],
-         fo.shape[0], 778, 32, 0.2, 0.5, ptr(phi), ptr(part), ptr(gh), s)
+         fo.shape[0], 778, 32, 0.2, 0.5, ptr(phi), ptr(part), ptr(gh), None, s)
     torch.cuda.synchronize()
     total = part[:, 10].sum().item()
     ref_a = float(dv[(0, 1)].sum() / 1.0)  # rescaled values; compare the normalised sums through the loss instead
@@ -197,3 +197,21 @@ def test_adam_matches_torch():
     assert np.allclose(out[:400], ref_a.detach().numpy(), rtol=1e-5, atol=1e-7)
     assert np.allclose(out[400:800], ref_b.detach().numpy(), rtol=1e-5, atol=1e-7)
     assert np.array_equal(out[800:], p0[800:])
+
+
+def test_inter_metrics_match_oracle(mano_assets):
+    """Penetration depth / contact flag of the reference's evaluation (homan/eval/pointmetrics.py:102-124) against
+    the oracle's SDFSceneLoss restatement: dist_values[(1, 0)].max(1)."""
+    from homan_b200.eval.pointmetrics import get_inter_metrics
+    from oracle import homan_ref
+    vh, vo, clip = _grasp(4, 33, mano_assets)
+    vo = (vo + (vh.mean(1, keepdims=True) - vo.mean(1, keepdims=True)) * np.array([0.9, 0.6, 0.3, -2.0])[:, None, None]).astype(np.float32)
+    closed, fo = mano_assets["right"]["closed_faces"], clip["obj_faces"]
+    _, dv = homan_ref.sdf_scene([torch.from_numpy(vh), torch.from_numpy(vo)],
+                                [torch.from_numpy(closed), torch.from_numpy(fo)])
+    ref = dv[(1, 0)].max(1)[0].numpy()
+    got = get_inter_metrics(torch.from_numpy(vh).cuda(), torch.from_numpy(vo).cuda(),
+                            torch.from_numpy(closed)[None].cuda(), torch.from_numpy(fo.astype(np.int64))[None].cuda())
+    assert ref[:3].min() > 0 and ref[3] == 0   # three interpenetrating scenes, one apart
+    assert np.allclose(got["pen_depths"], ref, rtol=1e-4, atol=1e-7), (got["pen_depths"], ref)
+    assert got["has_contact"] == (ref > 0).tolist()

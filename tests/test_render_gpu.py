@@ -1,7 +1,7 @@
 """GPU: forward of the RGB / depth render used by the reference for visualisation (`nr.Renderer.render`,
 /root/reference/homan/homan.py:510-613) through the neural_renderer drop-in, against the CPU
 oracle (oracle/nmr.py::Renderer.render, restated from the un-vendored package: parity unpinned). Bar: alpha and depth
-bit-exact (same z-buffer arithmetic), colours 1e-5 (lighting is evaluated in PyTorch on either side)."""
+bit-exact (same z-buffer arithmetic), colours 1e-5 (flat lighting: hm_face_lighting on the GPU, PyTorch in the oracle)."""
 import numpy as np
 import pytest
 import torch
