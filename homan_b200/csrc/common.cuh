@@ -75,6 +75,15 @@ static inline int hm_smem_opt_in(Kernel kernel, size_t bytes, HmSmemOptIn &state
     return HM_OK;
 }
 
+// Order-independent accumulation (test mode): contributions are rounded to 2^-44 fixed point and summed with 64-bit
+// integer atomics, so the result does not depend on the order in which CTAs and warps arrive (float atomics do).
+// |value| must stay below 2^19; hm_fold_fixed converts the sums back.
+constexpr float HM_FIXED_SCALE = 17592186044416.f;   // 2^44
+__device__ __forceinline__ void hm_accumulate(float *dst, unsigned long long *fixed, long idx, float v) {
+    if (fixed) atomicAdd(fixed + idx, (unsigned long long)__float2ll_rn(fminf(fmaxf(v, -5e5f), 5e5f) * HM_FIXED_SCALE));
+    else atomicAdd(dst + idx, v);
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -19,7 +19,8 @@ constexpr int CHUNK = 2048;                 // object vertices staged per pass
 
 __global__ void __launch_bounds__(NT)
 contact_kernel(const float *__restrict__ vh, const float *__restrict__ vo, int T, int Vo, float thresh, float weight,
-               float *__restrict__ partials, float *__restrict__ g_vh, float *__restrict__ g_vo) {
+               float *__restrict__ partials, float *__restrict__ g_vh, float *__restrict__ g_vo,
+               unsigned long long *__restrict__ g_vo_fixed) {
     __shared__ float4 so[CHUNK];  // x y z |o|^2
     __shared__ float red[2 * 32];
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -73,8 +74,9 @@ contact_kernel(const float *__restrict__ vh, const float *__restrict__ vo, int T
             const float c = a > 0.f ? weight * scale * (1.f - th * th) / a : 0.f;
             const float gx = c * dx, gy = c * dy, gz = c * dz;
             if (g_vo) {
-                float *g = g_vo + ((long)b * Vo + bi[s]) * 3;
-                atomicAdd(g, gx); atomicAdd(g + 1, gy); atomicAdd(g + 2, gz);
+                const long at = ((long)b * Vo + bi[s]) * 3;   // several hand vertices can share their nearest object vertex
+                hm_accumulate(g_vo, g_vo_fixed, at, gx); hm_accumulate(g_vo, g_vo_fixed, at + 1, gy);
+                hm_accumulate(g_vo, g_vo_fixed, at + 2, gz);
             }
             if (g_vh) {
                 float *g = g_vh + ((long)b * NVH + i) * 3;
@@ -94,12 +96,13 @@ contact_kernel(const float *__restrict__ vh, const float *__restrict__ vo, int T
 
 extern "C" int hm_contact_fwd_bwd(const float *verts_hand, const float *verts_obj, int B, int T, int Vo, float thresh,
                                   float weight, float *partials, float *grad_verts_hand, float *grad_verts_obj,
-                                  void *stream) {
+                                  unsigned long long *grad_fixed_obj, void *stream) {
+    HM_NVTX("hm_contact_fwd_bwd");
     HM_REQUIRE(verts_hand && verts_obj && partials, "hm_contact_fwd_bwd: null pointer");
     HM_REQUIRE(B >= 0 && T > 0 && Vo > 0 && thresh > 0.f, "hm_contact_fwd_bwd: bad sizes");
     if (B == 0) return HM_OK;
     contact_kernel<<<B, NT, 0, hm_stream(stream)>>>(verts_hand, verts_obj, T, Vo, thresh, weight, partials,
-                                                    grad_verts_hand, grad_verts_obj);
+                                                    grad_verts_hand, grad_verts_obj, grad_fixed_obj);
     HM_CHECK_LAUNCH("hm_contact_fwd_bwd");
     return HM_OK;
 }

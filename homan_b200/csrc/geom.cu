@@ -368,6 +368,12 @@ track_best_kernel(const float *__restrict__ total, int N, const float *__restric
     }
 }
 
+// Sums of hm_accumulate's fixed-point mode back to float: dst[i] += fixed[i] * 2^-44.
+__global__ void fold_fixed_kernel(const unsigned long long *__restrict__ fixed, int n, float *__restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] += __ll2float_rn((long long)fixed[i]) * (1.f / HM_FIXED_SCALE);
+}
+
 extern "C" {
 
 int hm_rigid_fwd(const float *mesh, int mesh_batch, const float *rot6d, const float *trans, const float *scale,
@@ -467,6 +473,16 @@ int hm_track_best(const float *total, int N, const float *rot6d, const float *tr
     if (N == 0) return HM_OK;
     track_best_kernel<<<1, NT, 0, hm_stream(stream)>>>(total, N, rot6d, trans, best, best_index);
     HM_CHECK_LAUNCH("hm_track_best");
+    return HM_OK;
+}
+
+int hm_fold_fixed(const unsigned long long *fixed, int n, float *dst, void *stream) {
+    HM_NVTX("hm_fold_fixed");
+    HM_REQUIRE(n >= 0, "hm_fold_fixed: bad size");
+    if (n == 0) return HM_OK;
+    HM_REQUIRE(fixed && dst, "hm_fold_fixed: null pointer");
+    fold_fixed_kernel<<<(unsigned)((n + 255) / 256), 256, 0, hm_stream(stream)>>>(fixed, n, dst);
+    HM_CHECK_LAUNCH("hm_fold_fixed");
     return HM_OK;
 }
 }  // extern "C"

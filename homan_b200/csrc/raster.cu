@@ -1220,7 +1220,8 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ 
                    const uint32_t *__restrict__ cov_row, const uint32_t *__restrict__ cov_col,
                    const uint32_t *__restrict__ face_vis, const unsigned char *__restrict__ cov_blocks,
                    const uint32_t *__restrict__ m_row, const uint32_t *__restrict__ m_col,
-                   const uint2 *__restrict__ runs, const uint32_t *__restrict__ run_info, float *__restrict__ grad_ndc) {
+                   const uint2 *__restrict__ runs, const uint32_t *__restrict__ run_info, float *__restrict__ grad_ndc,
+                   unsigned long long *__restrict__ grad_fixed) {
     __shared__ uint32_t list[B2_CAP];
     __shared__ int wsum[NWARPS];
     __shared__ SweepSrc S;
@@ -1235,6 +1236,7 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ 
     brecs += (long)b * F;
     boxes += (long)b * F;
     grad_ndc += (long)b * V * 3;
+    if (grad_fixed) grad_fixed += (long)b * V * 3;
     face_index += (long)b * is * is;
     cov_row += (long)b * is * W;
     cov_col += (long)b * is * W;
@@ -1415,7 +1417,7 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ 
                 for (int i0 = 0; i0 < npairs; i0 += 32) {
                     unsigned flags = 0;
                     int ra = 0, rc = 0, ls = 0, d0 = 0, owner = 0, r0 = 0, nr = 0;
-                    float x = 0.f, K0 = 0.f, K1 = 0.f;
+                    float x = 0.f, K0 = 0.f, K1 = 0.f, wa0 = 0.f, wa1 = 0.f;
                     if (i0 + lane < npairs) {
                         const unsigned pw = pr[i0 + lane];
                         owner = pw & 31;
@@ -1477,12 +1479,17 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ 
                             K1 = __fdividef(ka, fd0 - p0d0) * S.inv_is2;
                         }
                         if (nr < 0) {   // rare: run list overflowed or straddling sweep, walk the bit line in place
-                            float a0 = 0.f, a1 = 0.f;
-                            sweep_walk(S, ls, d0, ra, rc, x, K0, K1, flags, a0, a1);
-                            if (a0 != 0.f) atomicAdd(&sacc[warp][owner][0], a0);
-                            if (a1 != 0.f) atomicAdd(&sacc[warp][owner][1], a1);
+                            sweep_walk(S, ls, d0, ra, rc, x, K0, K1, flags, wa0, wa1);
                             nr = 0;
                         }
+                    }
+                    if (__any_sync(FULL, wa0 != 0.f || wa1 != 0.f)) {   // walked sums: lanes in order (fixed summation order)
+                        for (int l = 0; l < 32; ++l) {
+                            const float v0 = __shfl_sync(FULL, wa0, l), v1 = __shfl_sync(FULL, wa1, l);
+                            const int ow = __shfl_sync(FULL, owner, l);
+                            if (lane == 0 && (v0 != 0.f || v1 != 0.f)) { sacc[warp][ow][0] += v0; sacc[warp][ow][1] += v1; }
+                        }
+                        __syncwarp();
                     }
                     // (c) sweeps with runs go to the warp's queue in pair order (the sweeps of one segment stay
                     //     neighbours); 32 are evaluated at a time
@@ -1503,8 +1510,8 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ 
                 __syncwarp();
                 // slot pi0*3 + (1 - axis): axis 0 sweeps along y and yields the y gradient, axis 1 the x gradient
                 const float acc0 = sacc[warp][lane][0], acc1 = sacc[warp][lane][1];
-                if (acc0 != 0.f) atomicAdd(grad_ndc + g.vid0 * 3 + (1 - axis), acc0);
-                if (acc1 != 0.f) atomicAdd(grad_ndc + g.vid1 * 3 + (1 - axis), acc1);
+                if (acc0 != 0.f) hm_accumulate(grad_ndc, grad_fixed, g.vid0 * 3 + (1 - axis), acc0);
+                if (acc1 != 0.f) hm_accumulate(grad_ndc, grad_fixed, g.vid1 * 3 + (1 - axis), acc1);
                 __syncwarp();
             }
         }
@@ -1755,7 +1762,7 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
                       const uint32_t *face_vis, const uint8_t *cov_blocks,
                       const uint32_t *m_row, const uint32_t *m_col, const void *runs, const uint32_t *run_counts,
                       int B, int V, int F, int image_size, int anti_aliasing, float eps, float *grad_ndc,
-                      void *stream) {
+                      unsigned long long *grad_fixed, void *stream) {
     HM_NVTX("hm_raster_sil_bwd");
     HM_REQUIRE(B >= 0 && F >= 0 && V >= 0 && B <= 65535, "hm_raster_sil_bwd: bad sizes");
     int is;
@@ -1770,7 +1777,7 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
     const int n_rounds = (F + NTHREADS - 1) / NTHREADS;
     raster_bwd_kernel<<<dim3(min(n_rounds, 8), B), NTHREADS, 0, hm_stream(stream)>>>(
         brecs, static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, face_index, grad_alpha, cov_row,
-        cov_col, face_vis, cov_blocks, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc);
+        cov_col, face_vis, cov_blocks, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc, grad_fixed);
     HM_CHECK_LAUNCH("hm_raster_sil_bwd");
     return HM_OK;
 }

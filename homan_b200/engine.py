@@ -60,7 +60,7 @@ def mano_blob(asset, ncomps=16, device="cuda"):
 
 class FitEngine:
     def __init__(self, batch, loss_weights, lr=1e-2, mano_asset=None, device="cuda", use_graph=True, ncomps=16,
-                 betas=(0.9, 0.999), eps=1e-8):
+                 betas=(0.9, 0.999), eps=1e-8, deterministic=False):
         if not torch.cuda.is_available():
             raise _lib.HomanB200Error("FitEngine needs a CUDA device (there is no CPU path)")
         _lib.lib()
@@ -151,6 +151,15 @@ class FitEngine:
         self.total = torch.zeros(self.P, device=dev)
         self.step_counter = torch.zeros(1, dtype=torch.int32, device=dev)
 
+        # test mode: the scattered gradient sums (raster backward, contact) go through 64-bit fixed-point accumulators,
+        # which makes an iteration bit-reproducible whatever the arrival order of CTAs and warps
+        self.deterministic = bool(deterministic)
+        self.fixed_region = None
+        if self.deterministic:
+            self.fixed_region = torch.zeros(2 * B * Vo * 3 + B * 778 * 3, dtype=torch.int64, device=dev)
+            o = B * Vo * 3
+            self.fx_ndc_obj, self.fx_vobj = self.fixed_region[:o], self.fixed_region[o:2 * o]
+            self.fx_ndc_hand = self.fixed_region[2 * o:2 * o + B * 778 * 3]
         self.configure(loss_weights)
         self.gpu_launches_per_step = 0
         self.graph = None
@@ -244,7 +253,8 @@ class FitEngine:
         return nbytes
 
     # ------------------------------------------------------------------ one iteration, kernel by kernel
-    def _silhouette(self, verts, K_roi, faces, rb, target, norm, weight, ga, g_ndc, g_verts, slot_loss, slot_iou, s):
+    def _silhouette(self, verts, K_roi, faces, rb, target, norm, weight, ga, g_ndc, g_verts, slot_loss, slot_iou, s,
+                    fixed=None):
         B, V = verts.shape[:2]
         ndc = self.ndc_obj if verts is self.verts_obj else self.ndc_hand
         call("hm_project_fwd", ptr(verts), ptr(K_roi), B, None, None, None, 0, 1.0, 1e-9, B, V, ptr(ndc), s)
@@ -252,9 +262,9 @@ class FitEngine:
         pb = self.partials.data_ptr()
         call("hm_sil_loss_fwd_bwd", ptr(rb.alpha), ptr(target), ptr(norm), weight, B, REND_SIZE,
              pb + 4 * PART[slot_loss], NPART, pb + 4 * PART[slot_iou], NPART, ptr(ga), s)
-        ops.raster_backward(rb, ga, g_ndc)
+        ops.raster_backward(rb, ga, g_ndc, grad_fixed=fixed)
         call("hm_project_bwd", ptr(verts), ptr(K_roi), B, None, None, 1.0, 1e-9, B, V, ptr(g_ndc), ptr(g_verts), 1, s)
-        return 7
+        return 7 + (1 if fixed is not None else 0)
 
     def _forward_vertices(self, s):
         p = self.params
@@ -270,15 +280,19 @@ class FitEngine:
         lw, B, T = self.lw, self.B, self.T
         n = 1
         self.zero_region.zero_()
+        if self.deterministic:
+            self.fixed_region.zero_()
+            n += 1
         n += self._forward_vertices(s)
         if self.on_sil_obj:
             n += self._silhouette(self.verts_obj, self.K_roi_obj, self.faces_obj, self.rb_obj, self.target_obj,
                                   self.norm_obj, lw["lw_sil_obj"], self.ga_obj, self.g_ndc_obj, self.g_verts_obj,
-                                  "sil_obj", "iou_obj", s)
+                                  "sil_obj", "iou_obj", s, self.fx_ndc_obj if self.deterministic else None)
         if self.on_sil_hand:
             n += self._silhouette(self.verts_hand, self.K_roi_hand, self.faces_hand, self.rb_hand, self.target_hand,
                                   self.norm_hand, lw["lw_sil_hand"], self.ga_hand, self.g_ndc_hand,
-                                  self.g_verts_hand, "sil_hand", "iou_hand", s)
+                                  self.g_verts_hand, "sil_hand", "iou_hand", s,
+                                  self.fx_ndc_hand if self.deterministic else None)
         flags = (VL_SMOOTH if self.on_smooth else 0) | (VL_V2D if self.on_v2d else 0) | \
                 (VL_INTER if self.on_inter else 0) | (VL_PCA if self.on_pca else 0)
         if flags:
@@ -292,8 +306,11 @@ class FitEngine:
         if self.on_contact or self.on_inter:
             call("hm_contact_fwd_bwd", ptr(self.verts_hand), ptr(self.verts_obj), B, T, self.Vo, COLLISION_THRESH,
                  lw.get("lw_contact", 0.0) if self.on_contact else 0.0, ptr(self.partials), ptr(self.g_verts_hand),
-                 ptr(self.g_verts_obj), s)
+                 ptr(self.g_verts_obj), ptr(self.fx_vobj) if self.deterministic else None, s)
             n += 1
+            if self.deterministic:
+                call("hm_fold_fixed", ptr(self.fx_vobj), self.fx_vobj.numel(), ptr(self.g_verts_obj), s)
+                n += 1
         if self.on_collision:
             # pair (hand grid <- object vertices): value only (the object is detached, homan.py:445-449)
             call("hm_sdf_pair", ptr(self.verts_hand), ptr(self.faces_hand_closed), 1, ptr(self.verts_obj), B, 778,

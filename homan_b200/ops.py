@@ -91,8 +91,9 @@ def raster_forward(buf, ndc, faces, fill_back=True, near=NEAR, far=FAR):
     return buf.alpha
 
 
-def raster_backward(buf, grad_alpha, grad_ndc, eps=RASTER_EPS):
-    """grad_alpha [B,R,R] -> grad_ndc [B,V,3] += (approximate NMR gradient, x / y slots)."""
+def raster_backward(buf, grad_alpha, grad_ndc, eps=RASTER_EPS, grad_fixed=None):
+    """grad_alpha [B,R,R] -> grad_ndc [B,V,3] += (approximate NMR gradient, x / y slots). `grad_fixed` (int64 [B,V,3],
+    zeroed): order-independent fixed-point accumulation (test mode), folded into grad_ndc afterwards."""
     s = current_stream()
     call("hm_raster_grad_prep", ptr(grad_alpha), ptr(buf.cov_row), ptr(buf.cov_col), buf.B, buf.image_size,
          int(buf.aa), ptr(buf.m_row), ptr(buf.m_col), ptr(buf.runs), ptr(buf.run_counts), s)
@@ -100,7 +101,9 @@ def raster_backward(buf, grad_alpha, grad_ndc, eps=RASTER_EPS):
          ptr(buf.cov_row), ptr(buf.cov_col), ptr(buf.face_vis), ptr(buf.cov_blocks), ptr(buf.m_row), ptr(buf.m_col),
          ptr(buf.runs), ptr(buf.run_counts),
          buf.B, buf.V, buf.F, buf.image_size,
-         int(buf.aa), float(eps), ptr(grad_ndc), s)
+         int(buf.aa), float(eps), ptr(grad_ndc), ptr(grad_fixed), s)
+    if grad_fixed is not None:
+        call("hm_fold_fixed", ptr(grad_fixed), grad_fixed.numel(), ptr(grad_ndc), s)
     return grad_ndc
 
 

@@ -87,7 +87,12 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
                       const uint32_t *face_vis, const uint8_t *cov_blocks,
                       const uint32_t *m_row, const uint32_t *m_col, const void *runs, const uint32_t *run_counts,
                       int B, int V, int F, int image_size, int anti_aliasing, float eps, float *grad_ndc,
-                      void *stream);
+                      unsigned long long *grad_fixed, void *stream);
+/* Order-independent accumulation (test mode, SURVEY.md section 5 "deterministic reduction"): when an entry point is
+ * given a `grad_fixed` buffer (same shape as the float gradient it shadows, 64-bit, zeroed by the caller) its scattered
+ * contributions are rounded to 2^-44 fixed point and summed with integer atomics instead of float atomics, so the sum
+ * does not depend on the arrival order of CTAs / warps (|contribution| < 2^19). hm_fold_fixed: dst[i] += fixed[i] * 2^-44. */
+int hm_fold_fixed(const unsigned long long *fixed, int n, float *dst, void *stream);
 
 /* Forward of nr.Renderer.render / rasterize_rgbad for texture_size 1 (visualisation: homan/homan.py:510-613,
  * homan/visualize.py:44-128, homan/utils/nmr_renderer.py:71,164,209), on top of hm_raster_setup + hm_raster_sil_fwd:
@@ -193,7 +198,7 @@ int hm_vertex_losses(const float *verts_hand, const float *verts_obj, const floa
  * gradient to both meshes, weighted by `weight / (T * 778)`.  partials as above (CONTACT, MINDIST). */
 int hm_contact_fwd_bwd(const float *verts_hand, const float *verts_obj, int B, int T, int Vo, float thresh,
                        float weight, float *partials, float *grad_verts_hand, float *grad_verts_obj,
-                       void *stream);
+                       unsigned long long *grad_fixed_obj, void *stream);
 
 /* ---------------------------------------------------------------- SDF interpenetration
  * SDFSceneLoss.forward for (hand, object) (homan/interactions/scenesdf.py:77-148, called from

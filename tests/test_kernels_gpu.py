@@ -163,7 +163,7 @@ def test_contact_matches_oracle(mano_assets):
     gh, go = torch.zeros(B, 778, 3, device="cuda"), torch.zeros(B, vo.shape[1], 3, device="cuda")
     dh, do = torch.from_numpy(vh).cuda(), torch.from_numpy(vo).cuda()
     call("hm_contact_fwd_bwd", ptr(dh), ptr(do), B, B, vo.shape[1],
-         0.02, 2.0, ptr(part), ptr(gh), ptr(go), current_stream())
+         0.02, 2.0, ptr(part), ptr(gh), ptr(go), None, current_stream())
     torch.cuda.synchronize()
     assert abs(part[:, 11].sum().item() - float(loss)) <= 1e-5 * float(loss)
     assert _rel(gh.cpu(), 2 * th.grad) < 1e-4 and _rel(go.cpu(), 2 * to.grad) < 1e-4
