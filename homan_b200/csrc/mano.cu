@@ -118,7 +118,7 @@ __device__ __forceinline__ void mat3_mul(const float *A, const float *B, float *
 // Everything up to the posed template (steps shared by forward and backward).
 __device__ void mano_common(Shared &S, const Model &m, int ncomps, int left, const float *pca, const float *rot,
                             const float *betas, const float *mano_trans, const float *rot6d, const float *trans,
-                            const float *scale) {
+                            const float *scale, const float *vposed_in = nullptr, float *vposed_out = nullptr) {
     const int t = threadIdx.x;
     if (t < 45) {
         float h = 0.f;
@@ -182,14 +182,19 @@ __device__ void mano_common(Shared &S, const Model &m, int ncomps, int left, con
         S.pf[k] = S.R[j][e] - ((e == 0 || e == 4 || e == 8) ? 1.f : 0.f);
     }
     __syncthreads();
-    for (int i = t; i < NV3; i += NT) {
-        float v = m.v_template[i];
+    if (vposed_in) {   // the posed template kept by the forward of this iteration: no second pass over posedirs
+        for (int i = t; i < NV3; i += NT) S.vposed[i] = __ldg(vposed_in + i);
+    } else {
+        for (int i = t; i < NV3; i += NT) {
+            float v = m.v_template[i];
 #pragma unroll
-        for (int l = 0; l < 10; ++l) v += m.shapedirs[i * 10 + l] * S.beta[l];
-        float acc = 0.f;
+            for (int l = 0; l < 10; ++l) v += m.shapedirs[i * 10 + l] * S.beta[l];
+            float acc = 0.f;
 #pragma unroll 5
-        for (int k = 0; k < NPF; ++k) acc += S.pf[k] * __ldg(m.posedirs + (long)k * NV3 + i);
-        S.vposed[i] = v + acc;
+            for (int k = 0; k < NPF; ++k) acc += S.pf[k] * __ldg(m.posedirs + (long)k * NV3 + i);
+            S.vposed[i] = v + acc;
+            if (vposed_out) vposed_out[i] = v + acc;
+        }
     }
     __syncthreads();
 }
@@ -218,13 +223,13 @@ __global__ void __launch_bounds__(NT)
 mano_fwd_kernel(const float *__restrict__ blob, int ncomps, int left, const float *__restrict__ pca, int pca_stride,
                 const float *__restrict__ rot, const float *__restrict__ betas, const float *__restrict__ mano_trans,
                 const float *__restrict__ rot6d, const float *__restrict__ trans, const float *__restrict__ scale,
-                float *__restrict__ verts, float *__restrict__ joints) {
+                float *__restrict__ verts, float *__restrict__ joints, float *__restrict__ vposed) {
     __shared__ Shared S;
     const int b = blockIdx.x;
     const Model m = model_view(blob);
     mano_common(S, m, ncomps, left, pca + (long)b * pca_stride, rot + 3 * b, betas ? betas + 10 * b : nullptr,
                 mano_trans ? mano_trans + 3 * b : nullptr, rot6d ? rot6d + 6 * b : nullptr,
-                trans ? trans + 3 * b : nullptr, scale);
+                trans ? trans + 3 * b : nullptr, scale, nullptr, vposed ? vposed + (long)b * NV3 : nullptr);
     for (int v = threadIdx.x; v < NV; v += NT) {
         float Tm[12];
         blend(S, m, v, Tm);
@@ -264,8 +269,8 @@ __global__ void __launch_bounds__(NT)
 mano_bwd_kernel(const float *__restrict__ blob, int ncomps, int left, const float *__restrict__ pca, int pca_stride,
                 const float *__restrict__ rot, const float *__restrict__ betas, const float *__restrict__ mano_trans,
                 const float *__restrict__ rot6d, const float *__restrict__ trans, const float *__restrict__ scale,
-                const float *__restrict__ g_verts, const float *__restrict__ g_centroid_det,
-                float *__restrict__ g_pca, float *__restrict__ g_rot, float *__restrict__ g_betas,
+                const float *__restrict__ vposed, const float *__restrict__ g_verts,
+                const float *__restrict__ g_centroid_det, float *__restrict__ g_pca, float *__restrict__ g_rot, float *__restrict__ g_betas,
                 float *__restrict__ g_mano_trans, float *__restrict__ g_rot6d, float *__restrict__ g_trans) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Shared &S = *reinterpret_cast<Shared *>(smem_raw);
@@ -274,7 +279,7 @@ mano_bwd_kernel(const float *__restrict__ blob, int ncomps, int left, const floa
     const Model m = model_view(blob);
     mano_common(S, m, ncomps, left, pca + (long)b * pca_stride, rot + 3 * b, betas ? betas + 10 * b : nullptr,
                 mano_trans ? mano_trans + 3 * b : nullptr, rot6d ? rot6d + 6 * b : nullptr,
-                trans ? trans + 3 * b : nullptr, scale);
+                trans ? trans + 3 * b : nullptr, scale, vposed ? vposed + (long)b * NV3 : nullptr, nullptr);
     const bool rigid = rot6d != nullptr;
     const float s = rigid ? S.scale : 1.f;
     // ---- pass 1 over vertices: rigid backward, d/d v_posed
@@ -454,22 +459,22 @@ extern "C" {
 
 int hm_mano_fwd(const float *model, int ncomps, int left, const float *pca, int pca_stride, const float *rot,
                 const float *betas, const float *mano_trans, const float *rot6d, const float *trans,
-                const float *scale, int B, float *verts, float *joints, void *stream) {
+                const float *scale, int B, float *verts, float *joints, float *vposed, void *stream) {
     HM_NVTX("hm_mano_fwd");
     HM_REQUIRE(model && pca && rot && verts, "hm_mano_fwd: null pointer");
     HM_REQUIRE(B >= 0 && ncomps >= 0 && ncomps <= 45 && pca_stride >= ncomps, "hm_mano_fwd: bad sizes");
     if (B == 0) return HM_OK;
     mano_fwd_kernel<<<B, NT, 0, hm_stream(stream)>>>(model, ncomps, left, pca, pca_stride, rot, betas, mano_trans,
-                                                     rot6d, trans, scale, verts, joints);
+                                                     rot6d, trans, scale, verts, joints, vposed);
     HM_CHECK_LAUNCH("hm_mano_fwd");
     return HM_OK;
 }
 
 int hm_mano_bwd(const float *model, int ncomps, int left, const float *pca, int pca_stride, const float *rot,
                 const float *betas, const float *mano_trans, const float *rot6d, const float *trans,
-                const float *scale, int B, const float *grad_verts, const float *grad_centroid_det,
-                float *grad_pca, float *grad_rot, float *grad_betas, float *grad_mano_trans, float *grad_rot6d,
-                float *grad_trans, void *stream) {
+                const float *scale, int B, const float *vposed, const float *grad_verts,
+                const float *grad_centroid_det, float *grad_pca, float *grad_rot, float *grad_betas,
+                float *grad_mano_trans, float *grad_rot6d, float *grad_trans, void *stream) {
     HM_NVTX("hm_mano_bwd");
     HM_REQUIRE(model && pca && rot && grad_verts, "hm_mano_bwd: null pointer");
     HM_REQUIRE(B >= 0 && ncomps >= 0 && ncomps <= 45 && pca_stride >= ncomps, "hm_mano_bwd: bad sizes");
@@ -478,7 +483,7 @@ int hm_mano_bwd(const float *model, int ncomps, int left, const float *pca, int 
     static HmSmemOptIn opt_in;
     if (int rc = hm_smem_opt_in(mano_bwd_kernel, smem, opt_in, "hm_mano_bwd")) return rc;
     mano_bwd_kernel<<<B, NT, smem, hm_stream(stream)>>>(model, ncomps, left, pca, pca_stride, rot, betas, mano_trans,
-                                                        rot6d, trans, scale, grad_verts, grad_centroid_det, grad_pca,
+                                                        rot6d, trans, scale, vposed, grad_verts, grad_centroid_det, grad_pca,
                                                         grad_rot, grad_betas, grad_mano_trans, grad_rot6d, grad_trans);
     HM_CHECK_LAUNCH("hm_mano_bwd");
     return HM_OK;

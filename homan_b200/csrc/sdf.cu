@@ -84,7 +84,9 @@ __device__ __forceinline__ bool ray_x_cross(float py, float pz, const float *a, 
     return true;
 }
 
-__device__ __forceinline__ float voxel_centre(int i) { return -1.f + ((float)i + 0.5f) * 2.f / (float)G; }
+// -1 + (i + 0.5) * 2 / G as the oracle evaluates it; G is a power of two, so "* 2 / G" is one exact scaling
+static_assert((G & (G - 1)) == 0, "power-of-two grid");
+__device__ __forceinline__ float voxel_centre(int i) { return -1.f + ((float)i + 0.5f) * (2.f / (float)G); }
 
 // bit mask of the voxels i of a row whose centre x is < xs (the ray from those voxels hits at xs)
 __device__ __forceinline__ unsigned row_mask_below(float xs) {

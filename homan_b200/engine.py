@@ -145,6 +145,7 @@ class FitEngine:
         self.g_cdet = z["g_cdet"].view(B, 3)
         self.verts_obj = torch.empty(B, Vo, 3, device=dev)
         self.verts_hand = torch.empty(B, 778, 3, device=dev)
+        self.vposed = torch.empty(B, 778 * 3, device=dev)   # posed template of the iteration (hm_mano_fwd -> hm_mano_bwd)
         self.ndc_obj = torch.empty(B, Vo, 3, device=dev)
         self.ndc_hand = torch.empty(B, 778, 3, device=dev)
         self.losses = torch.zeros(self.P, NPART, device=dev)
@@ -272,7 +273,7 @@ class FitEngine:
              ptr(self.scale_obj), self.B, self.Vo, ptr(self.verts_obj), s)
         call("hm_mano_fwd", ptr(self.mano), self.ncomps, self.side_left, ptr(p["mano_pca_pose"]), self.pca_dim,
              ptr(p["mano_rot"]), ptr(p["mano_betas"]), ptr(p["mano_trans"]), ptr(p["rotations_hand"]),
-             ptr(p["translations_hand"]), ptr(self.scale_hand), self.B, ptr(self.verts_hand), None, s)
+             ptr(p["translations_hand"]), ptr(self.scale_hand), self.B, ptr(self.verts_hand), None, ptr(self.vposed), s)
         return 2
 
     def _iteration(self, adam=True):
@@ -325,7 +326,7 @@ class FitEngine:
         call("hm_mano_bwd", ptr(self.mano), self.ncomps, self.side_left, ptr(self.params["mano_pca_pose"]),
              self.pca_dim, ptr(self.params["mano_rot"]), ptr(self.params["mano_betas"]),
              ptr(self.params["mano_trans"]), ptr(self.params["rotations_hand"]), ptr(self.params["translations_hand"]),
-             ptr(self.scale_hand), B, ptr(self.g_verts_hand), ptr(self.g_cdet) if self.on_inter else None,
+             ptr(self.scale_hand), B, ptr(self.vposed), ptr(self.g_verts_hand), ptr(self.g_cdet) if self.on_inter else None,
              ptr(g["mano_pca_pose"]), ptr(g["mano_rot"]), ptr(g["mano_betas"]), ptr(g["mano_trans"]),
              ptr(g["rotations_hand"]), ptr(g["translations_hand"]), s)
         call("hm_rigid_bwd", ptr(self.mesh_obj), self.mesh_obj.shape[0], ptr(self.params["rotations_object"]), ptr(self.scale_obj), B,

@@ -39,7 +39,7 @@ class _ManoLBS(torch.autograd.Function):
         joints = torch.empty(B, 16, 3, device=p.device)
         # the layer takes the 45-D axis-angle pose directly: identity "components", zero mean in the blob
         call("hm_mano_fwd", ptr(blob), 45, 0, ptr(p), 45, ptr(r), ptr(b), ptr(t), None, None, None, B, ptr(verts),
-             ptr(joints), current_stream())
+             ptr(joints), None, current_stream())
         ctx.save_for_backward(blob, p, r, b, t)
         ctx.mark_non_differentiable(joints)
         return verts, joints
@@ -50,7 +50,7 @@ class _ManoLBS(torch.autograd.Function):
         B = p.shape[0]
         gv = g_verts.detach().contiguous().float()
         gp, gr, gb, gt = (torch.zeros_like(x) for x in (p, r, b, t))
-        call("hm_mano_bwd", ptr(blob), 45, 0, ptr(p), 45, ptr(r), ptr(b), ptr(t), None, None, None, B, ptr(gv), None,
+        call("hm_mano_bwd", ptr(blob), 45, 0, ptr(p), 45, ptr(r), ptr(b), ptr(t), None, None, None, B, None, ptr(gv), None,
              ptr(gp), ptr(gr), ptr(gb), ptr(gt), None, None, current_stream())
         return None, gp, gr, gb, gt
 

@@ -141,15 +141,17 @@ int hm_sil_loss_fwd_bwd(const float *alpha, const int8_t *target, const float *n
 #define HM_MANO_BLOB_FLOATS(ncomps) (HM_MANO_OFF_COMPS + (ncomps) * 45)
 int hm_mano_fwd(const float *model, int ncomps, int left, const float *pca, int pca_stride, const float *rot,
                 const float *betas, const float *mano_trans, const float *rot6d, const float *trans,
-                const float *scale, int B, float *verts, float *joints, void *stream);
-/* grad_verts [B,778,3]; grad_centroid_det [B,3] (may be NULL) is d loss / d mean_v(verts) through the
+                const float *scale, int B, float *verts, float *joints, float *vposed, void *stream);
+/* vposed [B,778*3] (may be NULL in both calls): the posed template (v_template + shape + pose blend shapes) that
+ * hm_mano_fwd writes and hm_mano_bwd of the same iteration reads instead of streaming posedirs a second time.
+ * grad_verts [B,778,3]; grad_centroid_det [B,3] (may be NULL) is d loss / d mean_v(verts) through the
  * mesh-detached twin of compute_transformation_persp (reaches rot6d / trans only; homan/homan.py:484-490).
  * All outputs are accumulated (+=) and may be NULL. */
 int hm_mano_bwd(const float *model, int ncomps, int left, const float *pca, int pca_stride, const float *rot,
                 const float *betas, const float *mano_trans, const float *rot6d, const float *trans,
-                const float *scale, int B, const float *grad_verts, const float *grad_centroid_det,
-                float *grad_pca, float *grad_rot, float *grad_betas, float *grad_mano_trans, float *grad_rot6d,
-                float *grad_trans, void *stream);
+                const float *scale, int B, const float *vposed, const float *grad_verts,
+                const float *grad_centroid_det, float *grad_pca, float *grad_rot, float *grad_betas,
+                float *grad_mano_trans, float *grad_rot6d, float *grad_trans, void *stream);
 
 /* ---------------------------------------------------------------- rigid placement of the object
  * HOMan.get_verts_object (homan/homan.py:298-307): verts = (|scale| * mesh) @ rot6d_to_matrix(rot6d) + trans.

@@ -13,8 +13,9 @@ def _rel(a, b):
     return float(np.abs(np.asarray(a) - np.asarray(b)).max() / max(np.abs(np.asarray(b)).max(), 1e-12))
 
 
+@pytest.mark.parametrize("use_cache", [False, True])   # backward with / without the forward's posed template
 @pytest.mark.parametrize("side", ["right", "left"])
-def test_mano_lbs_forward_backward(side, mano_assets):
+def test_mano_lbs_forward_backward(side, use_cache, mano_assets):
     from homan_b200._lib import call, current_stream, ptr
     from homan_b200.engine import mano_blob
     from oracle import homan_ref
@@ -42,16 +43,17 @@ def test_mano_lbs_forward_backward(side, mano_assets):
     blob = mano_blob(asset, 16)
     dp, dr, db, dm, d6, dt = d(pca), d(rot), d(betas), d(mtr), d(r6), d(tr)
     verts = torch.empty(B, 778, 3, device="cuda")
+    vposed = torch.empty(B, 778 * 3, device="cuda")
     s = current_stream()
     left = 1 if side == "left" else 0
     call("hm_mano_fwd", ptr(blob), 16, left, ptr(dp), 20, ptr(dr), ptr(db), ptr(dm), ptr(d6), ptr(dt), None, B,
-         ptr(verts), None, s)
+         ptr(verts), None, ptr(vposed), s)
     assert _rel(verts.cpu(), full.detach()) < 2e-6
     g = {k: torch.zeros_like(x) for k, x in dict(pca=dp, rot=dr, betas=db, mtr=dm, r6=d6, tr=dt).items()}
     dgv, dgc = d(gv), d(gc)
     call("hm_mano_bwd", ptr(blob), 16, left, ptr(dp), 20, ptr(dr), ptr(db), ptr(dm), ptr(d6), ptr(dt), None, B,
-         ptr(dgv), ptr(dgc), ptr(g["pca"]), ptr(g["rot"]), ptr(g["betas"]), ptr(g["mtr"]), ptr(g["r6"]),
-         ptr(g["tr"]), s)
+         ptr(vposed) if use_cache else None, ptr(dgv), ptr(dgc), ptr(g["pca"]), ptr(g["rot"]), ptr(g["betas"]),
+         ptr(g["mtr"]), ptr(g["r6"]), ptr(g["tr"]), s)
     torch.cuda.synchronize()
     for k in g:
         assert _rel(g[k].cpu(), tp[k].grad) < 1e-4, (k, _rel(g[k].cpu(), tp[k].grad))
@@ -70,7 +72,7 @@ def test_mano_layer_joints_match_numpy_fp64(mano_assets):
     verts, joints = torch.empty(B, 778, 3, device="cuda"), torch.empty(B, 16, 3, device="cuda")
     blob, dp, dr, db = mano_blob(mano_assets["right"], 16), d(pca), d(rot), d(betas)
     call("hm_mano_fwd", ptr(blob), 16, 0, ptr(dp), 16, ptr(dr), ptr(db),
-         None, None, None, None, B, ptr(verts), ptr(joints), current_stream())
+         None, None, None, None, B, ptr(verts), ptr(joints), None, current_stream())
     torch.cuda.synchronize()
     assert _rel(verts.cpu(), v_ref) < 2e-6 and _rel(joints.cpu(), j_ref) < 2e-6
 
