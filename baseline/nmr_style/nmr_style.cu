@@ -69,6 +69,74 @@ __global__ void face_index_map_kernel(const float *__restrict__ faces, const flo
     weight_map[3 * i] = wmin[0]; weight_map[3 * i + 1] = wmin[1]; weight_map[3 * i + 2] = wmin[2];
 }
 
+// The "fast" forward of the multiperson fork the reference installs: one thread per
+// (image, FACE) walking the face's pixel bounding box, the nearest face of a pixel kept under a per-pixel lock. The
+// lock is a 64-bit atomicMin on (depth bits, face) here: the same winner as the upstream first-minimal-face rule,
+// deterministic, and no slower than a spin-lock. A second pass unpacks the keys into the three maps upstream writes.
+__global__ void face_index_map_face_parallel_kernel(const float *__restrict__ faces, const float *__restrict__ face_inv,
+                                                    int B, int nf, int is, float near_, float far_,
+                                                    unsigned long long *__restrict__ keys) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * nf) return;
+    const int b = (int)(i / nf), fn = (int)(i % nf);
+    const float *f = faces + i * 9;
+    if (is_backface(f)) return;
+    const float *inv = face_inv + i * 9;
+    float px[3], py[3];
+    for (int k = 0; k < 3; ++k) { px[k] = 0.5f * (f[3 * k] * is + is - 1); py[k] = 0.5f * (f[3 * k + 1] * is + is - 1); }
+    const float xmin = fminf(fminf(px[0], px[1]), px[2]), xmax = fmaxf(fmaxf(px[0], px[1]), px[2]);
+    const float ymin = fminf(fminf(py[0], py[1]), py[2]), ymax = fmaxf(fmaxf(py[0], py[1]), py[2]);
+    if (!(xmin == xmin) || !(xmax == xmax) || !(ymin == ymin) || !(ymax == ymax)) return;
+    const int x0 = max(__float2int_rd(xmin) - 1, 0), x1 = min(__float2int_ru(xmax) + 1, is - 1);
+    const int y0 = max(__float2int_rd(ymin) - 1, 0), y1 = min(__float2int_ru(ymax) + 1, is - 1);
+    unsigned long long *kb = keys + (long)b * is * is;
+    for (int yi = y0; yi <= y1; ++yi) {
+        const float yp = (float)(2 * yi + 1 - is) / is;
+        for (int xi = x0; xi <= x1; ++xi) {
+            const float xp = (float)(2 * xi + 1 - is) / is;
+            if ((yp - f[1]) * (f[3] - f[0]) < (xp - f[0]) * (f[4] - f[1])) continue;
+            if ((yp - f[4]) * (f[6] - f[3]) < (xp - f[3]) * (f[7] - f[4])) continue;
+            if ((yp - f[7]) * (f[0] - f[6]) < (xp - f[6]) * (f[1] - f[7])) continue;
+            float w[3], ws = 0.f;
+            for (int k = 0; k < 3; ++k) {
+                w[k] = inv[3 * k] * xi + inv[3 * k + 1] * yi + inv[3 * k + 2];
+                w[k] = fminf(fmaxf(w[k], 0.f), 1.f);
+                ws += w[k];
+            }
+            for (int k = 0; k < 3; ++k) w[k] /= ws;
+            const float zp = 1.f / (w[0] / f[2] + w[1] / f[5] + w[2] / f[8]);
+            if (zp <= near_ || far_ <= zp) continue;
+            atomicMin(kb + (long)yi * is + xi, ((unsigned long long)__float_as_uint(zp) << 32) | (unsigned)fn);
+        }
+    }
+}
+__global__ void unpack_keys_kernel(const float *__restrict__ faces, const float *__restrict__ face_inv, int B, int nf,
+                                   int is, float far_, const unsigned long long *__restrict__ keys,
+                                   int32_t *__restrict__ face_index, float *__restrict__ weight_map,
+                                   float *__restrict__ depth_map) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long)B * is * is) return;
+    const unsigned long long k = keys[i];
+    const int fn = (int)(unsigned)k;
+    float w[3] = {0.f, 0.f, 0.f}, depth = far_;
+    if (fn >= 0) {
+        const int b = (int)(i / ((long)is * is)), pn = (int)(i % ((long)is * is));
+        const int yi = pn / is, xi = pn % is;
+        const float *inv = face_inv + ((long)b * nf + fn) * 9;
+        float ws = 0.f;
+        for (int q = 0; q < 3; ++q) {
+            w[q] = inv[3 * q] * xi + inv[3 * q + 1] * yi + inv[3 * q + 2];
+            w[q] = fminf(fmaxf(w[q], 0.f), 1.f);
+            ws += w[q];
+        }
+        for (int q = 0; q < 3; ++q) w[q] /= ws;
+        depth = __uint_as_float((unsigned)(k >> 32));
+    }
+    face_index[i] = fn;
+    depth_map[i] = depth;
+    weight_map[3 * i] = w[0]; weight_map[3 * i + 1] = w[1]; weight_map[3 * i + 2] = w[2];
+}
+
 __global__ void backward_pixel_map_kernel(const float *__restrict__ faces, const int32_t *__restrict__ face_index,
                                           const float *__restrict__ alpha, const float *__restrict__ grad_alpha, int B,
                                           int nf, int is, float eps, float *__restrict__ grad_faces) {
@@ -173,6 +241,21 @@ int nmrs_forward_face_index_map(const float *faces, float *face_inv, int B, int 
     const long px = (long)B * is * is;
     face_index_map_kernel<<<(unsigned)((px + 255) / 256), 256, 0, s>>>(faces, face_inv, B, nf, is, near_, far_,
                                                                       face_index, weight_map, depth_map);
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
+}
+
+/* keys: [B, is, is] 64-bit scratch */
+int nmrs_forward_face_index_map_fast(const float *faces, float *face_inv, int B, int nf, int is, float near_, float far_,
+                                     unsigned long long *keys, int32_t *face_index, float *weight_map, float *depth_map,
+                                     void *stream) {
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const long n = (long)B * nf, px = (long)B * is * is;
+    face_inv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(faces, (int)n, is, face_inv);
+    cudaMemsetAsync(keys, 0xff, (size_t)px * 8, s);   // empty = far depth bits all ones, face -1
+    face_index_map_face_parallel_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(faces, face_inv, B, nf, is, near_,
+                                                                                     far_, keys);
+    unpack_keys_kernel<<<(unsigned)((px + 255) / 256), 256, 0, s>>>(faces, face_inv, B, nf, is, far_, keys, face_index,
+                                                                    weight_map, depth_map);
     return cudaPeekAtLastError() == cudaSuccess ? 0 : -2;
 }
 

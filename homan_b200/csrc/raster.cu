@@ -50,7 +50,7 @@ struct __align__(16) BwdRec {
 };
 static_assert(sizeof(BwdRec) == 96 && sizeof(FaceRec) + sizeof(BwdRec) == HM_FACE_RECORD_BYTES, "record size");
 constexpr int BWD_FN_MASK = (1 << 29) - 1;
-constexpr int BWD_IRREGULAR = 1 << 29;   // a corner on an integer pixel coordinate (or not finite): never skipped
+constexpr int BWD_IRREGULAR = 1 << 29;   // a corner on an integer pixel coordinate, in (-1, 0), or not finite: never skipped
 constexpr int BWD_BOTH = 1 << 30;        // both windings are front-facing: F + f is differentiated too
 constexpr float BWD_SMAX = 128.f;        // tasks steeper than this are enumerated from the face (see the backward kernels)
 
@@ -220,6 +220,9 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
             br.v[k] = r.v[k];
             irregular |= !(fabsf(br.px[k]) < 1e30f) || !(fabsf(br.py[k]) < 1e30f) || br.px[k] == floorf(br.px[k]) ||
                          br.py[k] == floorf(br.py[k]);
+            // a coordinate in (-1, 0): backward_pixel_map truncates the end of a scan-line range towards zero, so an
+            // edge that ends there still gets scan-line 0, outside the triangle (sweep ends extrapolated)
+            irregular |= (br.px[k] > -1.f && br.px[k] < 0.f) || (br.py[k] > -1.f && br.py[k] < 0.f);
         }
 #pragma unroll
         for (int e = 0; e < 3; ++e) {

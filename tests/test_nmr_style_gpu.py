@@ -29,3 +29,6 @@ def test_comparator_matches_oracle():
     a.backward(g.cuda())
     scale = ndc_c.grad.abs().max().item()
     assert (ndc_d.grad.cpu() - ndc_c.grad).abs().max().item() <= 1e-4 * scale
+    # the face-parallel forward (organisation of the fork the reference installs) gives the same maps
+    a2, fi2 = nmr_style.render_silhouettes(ndc.cuda(), fl.cuda(), 256, True, return_face_index=True, fast=True)
+    assert torch.equal(fi2, fi) and torch.equal(a2, a.detach())

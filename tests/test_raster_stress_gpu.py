@@ -186,3 +186,23 @@ def test_empty_inputs():
     faces = torch.zeros(1, 0, 3, dtype=torch.int32, device="cuda")
     alpha, fi = ops.rasterize_silhouettes(ndc, faces, 64, True, return_face_index=True)
     assert float(alpha.abs().max()) == 0 and int(fi.max()) == -1
+
+
+def test_closed_mesh_across_the_image_border():
+    """A closed mesh straddling the left / bottom image border: faces just outside the image (a corner coordinate in
+    (-1, 0) pixels) still get scan-line 0 from the reference's truncating range arithmetic, with sweep ends
+    extrapolated outside the triangle - their in-sweeps contribute although their pixel box is fully covered."""
+    from homan_b200 import synth
+    ov, of = synth.make_object("ellipsoid500")
+    rng = np.random.default_rng(12)
+    ndcs = []
+    for k in range(6):
+        s = rng.uniform(6.0, 9.0)
+        off = np.array([-1.0 + rng.uniform(-0.15, 0.15), -1.0 + rng.uniform(-0.15, 0.15) if k % 2 else rng.uniform(-0.5, 0.5)])
+        xy = ov[:, :2] * s + off
+        ndcs.append(np.concatenate((xy, ov[:, 2:3] * s + 2.0), 1))
+    ndc = np.stack(ndcs).astype(np.float32)
+    px = 0.5 * (ndc[..., :2] * 256 + 255)
+    assert ((px > -1) & (px < 0)).any()   # the case is present
+    _check(ndc, of, 128, True)
+    _check(ndc[:2], of, 256, False)
