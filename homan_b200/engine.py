@@ -155,6 +155,7 @@ class FitEngine:
         # test mode: the scattered gradient sums (raster backward, contact) go through 64-bit fixed-point accumulators,
         # which makes an iteration bit-reproducible whatever the arrival order of CTAs and warps
         self.deterministic = bool(deterministic)
+        self.overlap_streams, self._side_streams = True, None
         self.fixed_region = None
         if self.deterministic:
             self.fixed_region = torch.zeros(2 * B * Vo * 3 + B * 778 * 3, dtype=torch.int64, device=dev)
@@ -264,8 +265,13 @@ class FitEngine:
         call("hm_sil_loss_fwd_bwd", ptr(rb.alpha), ptr(target), ptr(norm), weight, B, REND_SIZE,
              pb + 4 * PART[slot_loss], NPART, pb + 4 * PART[slot_iou], NPART, ptr(ga), s)
         ops.raster_backward(rb, ga, g_ndc, grad_fixed=fixed)
+        return 6 + (1 if fixed is not None else 0)
+
+    def _silhouette_finish(self, verts, K_roi, g_ndc, g_verts, s):
+        """d loss / d NDC -> d loss / d vertices, accumulated into the vertex gradient the other terms also write."""
+        B, V = verts.shape[:2]
         call("hm_project_bwd", ptr(verts), ptr(K_roi), B, None, None, 1.0, 1e-9, B, V, ptr(g_ndc), ptr(g_verts), 1, s)
-        return 7 + (1 if fixed is not None else 0)
+        return 1
 
     def _forward_vertices(self, s):
         p = self.params
@@ -285,15 +291,31 @@ class FitEngine:
             self.fixed_region.zero_()
             n += 1
         n += self._forward_vertices(s)
+        # The two silhouette chains (projection -> raster forward -> loss -> raster backward) only write their own
+        # buffers (NDC gradients, loss slots), so inside a CUDA-graph capture they run on two side streams next to the
+        # vertex-space terms on the main stream (fork / join: parallel branches of the graph); the projection backward,
+        # which accumulates into the shared vertex gradients, follows the join. Eager launches stay on one stream.
+        main = torch.cuda.current_stream()
+        fork = self.overlap_streams and torch.cuda.is_current_stream_capturing()
+        chains = []
         if self.on_sil_obj:
-            n += self._silhouette(self.verts_obj, self.K_roi_obj, self.faces_obj, self.rb_obj, self.target_obj,
-                                  self.norm_obj, lw["lw_sil_obj"], self.ga_obj, self.g_ndc_obj, self.g_verts_obj,
-                                  "sil_obj", "iou_obj", s, self.fx_ndc_obj if self.deterministic else None)
+            chains.append((self.verts_obj, self.K_roi_obj, self.faces_obj, self.rb_obj, self.target_obj, self.norm_obj,
+                           lw["lw_sil_obj"], self.ga_obj, self.g_ndc_obj, self.g_verts_obj, "sil_obj", "iou_obj",
+                           self.fx_ndc_obj if self.deterministic else None))
         if self.on_sil_hand:
-            n += self._silhouette(self.verts_hand, self.K_roi_hand, self.faces_hand, self.rb_hand, self.target_hand,
-                                  self.norm_hand, lw["lw_sil_hand"], self.ga_hand, self.g_ndc_hand,
-                                  self.g_verts_hand, "sil_hand", "iou_hand", s,
-                                  self.fx_ndc_hand if self.deterministic else None)
+            chains.append((self.verts_hand, self.K_roi_hand, self.faces_hand, self.rb_hand, self.target_hand,
+                           self.norm_hand, lw["lw_sil_hand"], self.ga_hand, self.g_ndc_hand, self.g_verts_hand,
+                           "sil_hand", "iou_hand", self.fx_ndc_hand if self.deterministic else None))
+        if fork:
+            if self._side_streams is None:
+                self._side_streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+            for side, c in zip(self._side_streams, chains):
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    n += self._silhouette(*c[:12], current_stream(), c[12])
+        else:
+            for c in chains:
+                n += self._silhouette(*c[:12], s, c[12])
         flags = (VL_SMOOTH if self.on_smooth else 0) | (VL_V2D if self.on_v2d else 0) | \
                 (VL_INTER if self.on_inter else 0) | (VL_PCA if self.on_pca else 0)
         if flags:
@@ -322,6 +344,11 @@ class FitEngine:
                  self.faces_obj.shape[1], 778, SDF_GRID, SDF_SCALE_FACTOR, lw["lw_collision"], ptr(self.phi_scratch),
                  ptr(self.partials), ptr(self.g_verts_hand), None, s)
             n += 2
+        if fork:
+            for side, _ in zip(self._side_streams, chains):
+                main.wait_stream(side)
+        for c in chains:
+            n += self._silhouette_finish(c[0], c[1], c[8], c[9], s)
         g = self.grads
         call("hm_mano_bwd", ptr(self.mano), self.ncomps, self.side_left, ptr(self.params["mano_pca_pose"]),
              self.pca_dim, ptr(self.params["mano_rot"]), ptr(self.params["mano_betas"]),
