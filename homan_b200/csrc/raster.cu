@@ -1640,6 +1640,177 @@ inline int *image_boxes(void *bboxes, int B, int F) {
     return reinterpret_cast<int *>(static_cast<char *>(bboxes) + off);
 }
 
+// ------------------------------------------------------------------------------------------ fused loss + sweep lists
+// hm_sil_loss_fwd_bwd + hm_raster_grad_prep in one kernel, CTA per image. The silhouette loss gradient takes nine
+// values per image (gscale * k / 4, k = -4 .. 4: alpha is a multiple of 1/4, ref and keep are 0 / 1), so the whole
+// gradient map stays in shared memory as one signed byte per output pixel while the kernel (A) streams alpha and
+// the target once (loss, IoU, grad_alpha) and (B) derives, thread per raster line, the four sweep bit lines and
+// their run-length form from those bytes and the coverage words - the gradient is never re-read from memory (the
+// unfused pair re-reads it twice and gathers it once more per set bit). Same outputs, bit for bit.
+constexpr int SLP_THREADS = 512;
+template <bool AA>
+__global__ void __launch_bounds__(SLP_THREADS, 2)
+sil_loss_prep_kernel(const float *__restrict__ alpha, const int8_t *__restrict__ target, const float *__restrict__ norm,
+                     float weight, int R, float *__restrict__ loss_img, int loss_stride, float *__restrict__ iou_img,
+                     int iou_stride, float *__restrict__ grad_alpha, const uint32_t *__restrict__ cov_row,
+                     const uint32_t *__restrict__ cov_col, uint32_t *__restrict__ m_row, uint32_t *__restrict__ m_col,
+                     uint2 *__restrict__ runs, uint32_t *__restrict__ run_counts) {
+    extern __shared__ __align__(16) signed char code[];   // [R][R + 4]: 4 * keep * (keep * alpha - ref) * sign(gscale)
+    __shared__ float scratch[3 * 32];
+    const int b = blockIdx.x, npix = R * R;
+    const int CS = R + 4;                                  // row stride of the byte map
+    unsigned *sgn_row = reinterpret_cast<unsigned *>(code + (size_t)R * CS);   // [2][R][R / 32]: byte < 0, byte > 0
+    unsigned *sgn_col = sgn_row + 2 * R * (R / 32);                            // the same by column (bit = row)
+    const int is = AA ? 2 * R : R, W = is / 32;
+    const float nb = norm[b];
+    const float gscale = 2.f * weight * nb;
+    const int sgn = gscale > 0.f ? 1 : (gscale < 0.f ? -1 : 0);
+    // ---- (A) loss, IoU, gradient
+    {
+        const float4 *a4 = reinterpret_cast<const float4 *>(alpha + (long)b * npix);
+        const char4 *t4 = reinterpret_cast<const char4 *>(target + (long)b * npix);
+        float4 *g4 = reinterpret_cast<float4 *>(grad_alpha + (long)b * npix);
+        float acc[3] = {0.f, 0.f, 0.f};  // sum sq, intersection, union
+        for (int i = threadIdx.x; i < npix / 4; i += SLP_THREADS) {
+            const float4 a = a4[i];
+            const char4 t = t4[i];
+            const float av[4] = {a.x, a.y, a.z, a.w};
+            const int tv[4] = {t.x, t.y, t.z, t.w};
+            float gv[4];
+            char4 c;
+            signed char *cv = reinterpret_cast<signed char *>(&c);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float keep = tv[k] >= 0 ? 1.f : 0.f, ref = tv[k] > 0 ? 1.f : 0.f;
+                const float img = keep * av[k];
+                const float d = img - ref;
+                acc[0] += d * d;
+                acc[1] += img * ref;
+                acc[2] += fminf(fmaxf(img + ref, 0.f), 1.f);
+                gv[k] = gscale * keep * d;
+                cv[k] = (signed char)(__float2int_rn(4.f * keep * d) * sgn);
+            }
+            g4[i] = make_float4(gv[0], gv[1], gv[2], gv[3]);
+            *reinterpret_cast<char4 *>(code + ((4 * i) / R) * CS + (4 * i) % R) = c;
+        }
+        __syncthreads();   // (block_sum's own barriers would do; explicit for the code bytes)
+        // block sum over SLP_THREADS / 32 warps
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) acc[k] = warp_sum(acc[k]);
+        if (lane == 0) { scratch[warp] = acc[0]; scratch[32 + warp] = acc[1]; scratch[64 + warp] = acc[2]; }
+        __syncthreads();
+        if (warp == 0) {
+            float x0 = lane < SLP_THREADS / 32 ? scratch[lane] : 0.f, x1 = lane < SLP_THREADS / 32 ? scratch[32 + lane] : 0.f,
+                  x2 = lane < SLP_THREADS / 32 ? scratch[64 + lane] : 0.f;
+            x0 = warp_sum(x0); x1 = warp_sum(x1); x2 = warp_sum(x2);
+            if (lane == 0) {
+                if (loss_img) loss_img[(long)b * loss_stride] = x0 * nb;
+                if (iou_img) iou_img[(long)b * iou_stride] = x1 / (x2 + 1e-6f);
+            }
+        }
+    }
+    // |grad| at raster resolution of a pixel whose byte is +-k (the expression build_runs evaluates on grad_alpha)
+    float Gk[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const float gval = gscale * 1.f * ((float)k * 0.25f);
+        Gk[k] = fabsf(AA ? 0.25f * gval : gval);
+    }
+    // ---- (B1) sign bit masks of the byte map, by output row (bit = column) and by output column (bit = row): one
+    //      ballot per 32 pixels (the row stride of the bytes is R + 4, so a warp reading down a column is conflict-free)
+    const int RW = R / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int r = warp; r < R; r += SLP_THREADS / 32)
+    for (int w = 0; w < RW; ++w) {
+        const int v = code[r * CS + 32 * w + lane];
+        const unsigned ng = __ballot_sync(0xffffffffu, v < 0), ps = __ballot_sync(0xffffffffu, v > 0);
+        if (lane == 0) { sgn_row[(0 * R + r) * RW + w] = ng; sgn_row[(1 * R + r) * RW + w] = ps; }
+        const int vc = code[(32 * w + lane) * CS + r];   // column r, rows 32 w ..
+        const unsigned ngc = __ballot_sync(0xffffffffu, vc < 0), psc = __ballot_sync(0xffffffffu, vc > 0);
+        if (lane == 0) { sgn_col[(0 * R + r) * RW + w] = ngc; sgn_col[(1 * R + r) * RW + w] = psc; }
+    }
+    __syncthreads();
+    // ---- (B2) thread per raster line: rows (lists 0 / 1), then columns (lists 2 / 3)
+    const long plane = (long)is * W;
+    for (int ln = threadIdx.x; ln < 2 * is; ln += SLP_THREADS) {
+        const bool col = ln >= is;
+        const int line = col ? ln - is : ln;
+        const uint32_t *cov = (col ? cov_col : cov_row) + ((long)b * is + line) * W;
+        uint32_t *mo = (col ? m_col : m_row) + ((long)b * 2 * is + line) * W;
+        // the line of the byte map behind this raster line: row lines read output row `o` left to right, column lines
+        // read output column `o` from the bottom row up (raster y grows as the output row shrinks)
+        const int o = col ? (AA ? line >> 1 : line) : (AA ? (is - 1 - line) >> 1 : is - 1 - line);
+        const unsigned *sg = (col ? sgn_col : sgn_row) + o * RW;
+        int n[2] = {0, 0}, rs[2] = {-1, -1}, re[2] = {-1, -1}, first[2] = {0, 0}, rk[2] = {0, 0};
+        uint2 *out[2] = {runs + (((long)b * 4 + (col ? 2 : 0)) * is + line) * RCAP,
+                         runs + (((long)b * 4 + (col ? 3 : 1)) * is + line) * RCAP};
+        // (coverage words of the line are fetched four at a time: one dependent global load per word would serialise it)
+        uint4 cov4 = make_uint4(0u, 0u, 0u, 0u);
+        for (int w = 0; w < W; ++w) {
+            if ((w & 3) == 0) cov4 = __ldg(reinterpret_cast<const uint4 *>(cov) + (w >> 2));
+            unsigned neg, pos;
+            if (AA) {   // 16 output pixels per word
+                const int p0 = col ? R - 16 * (w + 1) : 16 * w;   // first output pixel (lowest index) of the word
+                neg = (sg[p0 >> 5] >> (p0 & 31)) & 0xffffu;
+                pos = (sg[R * RW + (p0 >> 5)] >> (p0 & 31)) & 0xffffu;
+                if (col) { neg = __brev(neg) >> 16; pos = __brev(pos) >> 16; }
+                neg = dup_bits16(neg); pos = dup_bits16(pos);
+            } else {
+                const int wi = col ? RW - 1 - w : w;
+                neg = sg[wi]; pos = sg[R * RW + wi];
+                if (col) { neg = __brev(neg); pos = __brev(pos); }
+            }
+            const unsigned A = (w & 3) == 0 ? cov4.x : (w & 3) == 1 ? cov4.y : (w & 3) == 2 ? cov4.z : cov4.w;
+            const unsigned m[2] = {neg & ~A, pos & A};
+            mo[w] = m[0];
+            mo[w + plane] = m[1];
+#pragma unroll
+            for (int l = 0; l < 2; ++l) {
+                unsigned bits = m[l];
+                while (bits) {
+                    // next stretch of consecutive set bits [lo, hi] of the word, then its pixels grouped by |byte|
+                    const int lo = __ffs(bits) - 1;
+                    const unsigned rest = ~(bits >> lo);
+                    const int len = rest ? __ffs(rest) - 1 : 32 - lo;
+                    const int hi = lo + len - 1;
+                    bits = hi >= 31 ? 0u : bits & (0xffffffffu << (hi + 1));
+                    int p = lo;
+                    while (p <= hi) {
+                        const int d1 = w * 32 + p;
+                        const int op = AA ? d1 >> 1 : d1;   // output pixel along the line (raster order)
+                        int k = col ? code[(R - 1 - op) * CS + o] : code[o * CS + op];
+                        k = k < 0 ? -k : k;
+                        const int q = AA ? min(hi, p | 1) : p;   // last raster pixel of this output pixel in the stretch
+                        if (rs[l] < 0) first[l] = d1;
+                        if (rs[l] >= 0 && d1 == re[l] + 1 && k == rk[l]) {
+                            re[l] = w * 32 + q;
+                        } else {
+                            if (rs[l] >= 0) {
+                                if (n[l] < RCAP) out[l][n[l]] = make_uint2((unsigned)rs[l] | ((unsigned)re[l] << 16), __float_as_uint(Gk[rk[l]]));
+                                ++n[l];
+                            }
+                            rs[l] = d1;
+                            re[l] = w * 32 + q;
+                            rk[l] = k;
+                        }
+                        p = q + 1;
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < 2; ++l) {
+            if (rs[l] >= 0) {
+                if (n[l] < RCAP) out[l][n[l]] = make_uint2((unsigned)rs[l] | ((unsigned)re[l] << 16), __float_as_uint(Gk[rk[l]]));
+                ++n[l];
+            }
+            run_counts[((long)b * 4 + (col ? 2 : 0) + l) * is + line] =
+                (n[l] > RCAP ? RUN_OVERFLOW : (unsigned)n[l]) | ((unsigned)first[l] << 4) | ((unsigned)max(re[l], 0) << 16);
+        }
+    }
+}
+
 int check_raster_size(int image_size, int aa, int *is_out) {
     const int is = aa ? 2 * image_size : image_size;
     HM_REQUIRE(image_size > 0, "image_size must be positive");
@@ -1814,6 +1985,36 @@ int hm_face_lighting(const float *verts, const int32_t *faces, int faces_batch, 
         color_ambient[0], color_ambient[1], color_ambient[2], color_directional[0], color_directional[1],
         color_directional[2], direction[0], direction[1], direction[2], lit);
     HM_CHECK_LAUNCH("hm_face_lighting");
+    return HM_OK;
+}
+
+int hm_sil_loss_prep(const float *alpha, const int8_t *target, const float *norm, float weight, int B, int image_size,
+                     int anti_aliasing, float *loss_img, int loss_stride, float *iou_img, int iou_stride,
+                     float *grad_alpha, const uint32_t *cov_row, const uint32_t *cov_col, uint32_t *m_row,
+                     uint32_t *m_col, void *runs, uint32_t *run_counts, void *stream) {
+    HM_NVTX("hm_sil_loss_prep");
+    HM_REQUIRE(B >= 0 && image_size > 0, "hm_sil_loss_prep: bad sizes");
+    int is;
+    if (int rc = check_raster_size(image_size, anti_aliasing, &is)) return rc;
+    HM_UNSUPPORTED(image_size % 32 != 0 || image_size > 384,
+                   "hm_sil_loss_prep: image size %d (a multiple of 32, at most 384)", image_size);
+    if (B == 0) return HM_OK;
+    HM_REQUIRE(alpha && target && norm && grad_alpha && cov_row && cov_col && m_row && m_col && runs && run_counts,
+               "hm_sil_loss_prep: null pointer");
+    const size_t smem = (size_t)image_size * (image_size + 4) + 4 * (size_t)image_size * (image_size / 32) * sizeof(unsigned);
+    static HmSmemOptIn opt_in[2];
+    if (anti_aliasing) {
+        if (int rc = hm_smem_opt_in(sil_loss_prep_kernel<true>, smem, opt_in[1], "hm_sil_loss_prep")) return rc;
+        sil_loss_prep_kernel<true><<<B, SLP_THREADS, smem, hm_stream(stream)>>>(
+            alpha, target, norm, weight, image_size, loss_img, loss_stride, iou_img, iou_stride, grad_alpha, cov_row,
+            cov_col, m_row, m_col, static_cast<uint2 *>(runs), run_counts);
+    } else {
+        if (int rc = hm_smem_opt_in(sil_loss_prep_kernel<false>, smem, opt_in[0], "hm_sil_loss_prep")) return rc;
+        sil_loss_prep_kernel<false><<<B, SLP_THREADS, smem, hm_stream(stream)>>>(
+            alpha, target, norm, weight, image_size, loss_img, loss_stride, iou_img, iou_stride, grad_alpha, cov_row,
+            cov_col, m_row, m_col, static_cast<uint2 *>(runs), run_counts);
+    }
+    HM_CHECK_LAUNCH("hm_sil_loss_prep");
     return HM_OK;
 }
 

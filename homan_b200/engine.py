@@ -156,6 +156,7 @@ class FitEngine:
         # which makes an iteration bit-reproducible whatever the arrival order of CTAs and warps
         self.deterministic = bool(deterministic)
         self.overlap_streams, self._side_streams = True, None
+        self.fused_prep = True   # hm_sil_loss_prep instead of hm_sil_loss_fwd_bwd + hm_raster_grad_prep (same outputs)
         self.fixed_region = None
         if self.deterministic:
             self.fixed_region = torch.zeros(2 * B * Vo * 3 + B * 778 * 3, dtype=torch.int64, device=dev)
@@ -262,10 +263,15 @@ class FitEngine:
         call("hm_project_fwd", ptr(verts), ptr(K_roi), B, None, None, None, 0, 1.0, 1e-9, B, V, ptr(ndc), s)
         ops.raster_forward(rb, ndc, faces)
         pb = self.partials.data_ptr()
-        call("hm_sil_loss_fwd_bwd", ptr(rb.alpha), ptr(target), ptr(norm), weight, B, REND_SIZE,
-             pb + 4 * PART[slot_loss], NPART, pb + 4 * PART[slot_iou], NPART, ptr(ga), s)
-        ops.raster_backward(rb, ga, g_ndc, grad_fixed=fixed)
-        return 6 + (1 if fixed is not None else 0)
+        if self.fused_prep:   # loss + gradient + sweep masks / run lists in one kernel
+            call("hm_sil_loss_prep", ptr(rb.alpha), ptr(target), ptr(norm), weight, B, REND_SIZE, 1,
+                 pb + 4 * PART[slot_loss], NPART, pb + 4 * PART[slot_iou], NPART, ptr(ga), ptr(rb.cov_row),
+                 ptr(rb.cov_col), ptr(rb.m_row), ptr(rb.m_col), ptr(rb.runs), ptr(rb.run_counts), s)
+        else:
+            call("hm_sil_loss_fwd_bwd", ptr(rb.alpha), ptr(target), ptr(norm), weight, B, REND_SIZE,
+                 pb + 4 * PART[slot_loss], NPART, pb + 4 * PART[slot_iou], NPART, ptr(ga), s)
+        ops.raster_backward(rb, ga, g_ndc, grad_fixed=fixed, prepared=self.fused_prep)
+        return (5 if self.fused_prep else 7) + (1 if fixed is not None else 0)
 
     def _silhouette_finish(self, verts, K_roi, g_ndc, g_verts, s):
         """d loss / d NDC -> d loss / d vertices, accumulated into the vertex gradient the other terms also write."""
@@ -290,13 +296,39 @@ class FitEngine:
         if self.deterministic:
             self.fixed_region.zero_()
             n += 1
-        n += self._forward_vertices(s)
+        main = torch.cuda.current_stream()
+        fork = self.overlap_streams and torch.cuda.is_current_stream_capturing()
+        if fork and self._side_streams is None:
+            self._side_streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        if fork and self.on_sil_obj and self.on_sil_hand:
+            # each chain starts from its own vertices: object placement on the first side stream, MANO on the second
+            sa, sb = self._side_streams
+            p = self.params
+            sa.wait_stream(main)
+            sb.wait_stream(main)
+            with torch.cuda.stream(sa):
+                call("hm_rigid_fwd", ptr(self.mesh_obj), self.mesh_obj.shape[0], ptr(p["rotations_object"]),
+                     ptr(p["translations_object"]), ptr(self.scale_obj), self.B, self.Vo, ptr(self.verts_obj), current_stream())
+                ev_obj = torch.cuda.Event()
+                ev_obj.record(sa)
+            with torch.cuda.stream(sb):
+                call("hm_mano_fwd", ptr(self.mano), self.ncomps, self.side_left, ptr(p["mano_pca_pose"]), self.pca_dim,
+                     ptr(p["mano_rot"]), ptr(p["mano_betas"]), ptr(p["mano_trans"]), ptr(p["rotations_hand"]),
+                     ptr(p["translations_hand"]), ptr(self.scale_hand), self.B, ptr(self.verts_hand), None,
+                     ptr(self.vposed), current_stream())
+                ev_hand = torch.cuda.Event()
+                ev_hand.record(sb)
+            main.wait_event(ev_obj)
+            main.wait_event(ev_hand)
+            n += 2
+            verts_on_sides = True
+        else:
+            n += self._forward_vertices(s)
+            verts_on_sides = False
         # The two silhouette chains (projection -> raster forward -> loss -> raster backward) only write their own
         # buffers (NDC gradients, loss slots), so inside a CUDA-graph capture they run on two side streams next to the
         # vertex-space terms on the main stream (fork / join: parallel branches of the graph); the projection backward,
         # which accumulates into the shared vertex gradients, follows the join. Eager launches stay on one stream.
-        main = torch.cuda.current_stream()
-        fork = self.overlap_streams and torch.cuda.is_current_stream_capturing()
         chains = []
         if self.on_sil_obj:
             chains.append((self.verts_obj, self.K_roi_obj, self.faces_obj, self.rb_obj, self.target_obj, self.norm_obj,
@@ -307,10 +339,9 @@ class FitEngine:
                            self.norm_hand, lw["lw_sil_hand"], self.ga_hand, self.g_ndc_hand, self.g_verts_hand,
                            "sil_hand", "iou_hand", self.fx_ndc_hand if self.deterministic else None))
         if fork:
-            if self._side_streams is None:
-                self._side_streams = [torch.cuda.Stream(), torch.cuda.Stream()]
             for side, c in zip(self._side_streams, chains):
-                side.wait_stream(main)
+                if not verts_on_sides:
+                    side.wait_stream(main)
                 with torch.cuda.stream(side):
                     n += self._silhouette(*c[:12], current_stream(), c[12])
         else:

@@ -91,12 +91,14 @@ def raster_forward(buf, ndc, faces, fill_back=True, near=NEAR, far=FAR):
     return buf.alpha
 
 
-def raster_backward(buf, grad_alpha, grad_ndc, eps=RASTER_EPS, grad_fixed=None):
+def raster_backward(buf, grad_alpha, grad_ndc, eps=RASTER_EPS, grad_fixed=None, prepared=False):
     """grad_alpha [B,R,R] -> grad_ndc [B,V,3] += (approximate NMR gradient, x / y slots). `grad_fixed` (int64 [B,V,3],
-    zeroed): order-independent fixed-point accumulation (test mode), folded into grad_ndc afterwards."""
+    zeroed): order-independent fixed-point accumulation (test mode), folded into grad_ndc afterwards. `prepared`: the
+    sweep masks / run lists of `buf` were already produced for this gradient (hm_sil_loss_prep)."""
     s = current_stream()
-    call("hm_raster_grad_prep", ptr(grad_alpha), ptr(buf.cov_row), ptr(buf.cov_col), buf.B, buf.image_size,
-         int(buf.aa), ptr(buf.m_row), ptr(buf.m_col), ptr(buf.runs), ptr(buf.run_counts), s)
+    if not prepared:
+        call("hm_raster_grad_prep", ptr(grad_alpha), ptr(buf.cov_row), ptr(buf.cov_col), buf.B, buf.image_size,
+             int(buf.aa), ptr(buf.m_row), ptr(buf.m_col), ptr(buf.runs), ptr(buf.run_counts), s)
     call("hm_raster_sil_bwd", ptr(buf.records), ptr(buf.bboxes), ptr(buf.face_index), ptr(grad_alpha),
          ptr(buf.cov_row), ptr(buf.cov_col), ptr(buf.face_vis), ptr(buf.cov_blocks), ptr(buf.m_row), ptr(buf.m_col),
          ptr(buf.runs), ptr(buf.run_counts),

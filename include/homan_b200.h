@@ -117,6 +117,14 @@ int hm_raster_shade(const void *records, const int32_t *face_index, const float 
 int hm_sil_loss_fwd_bwd(const float *alpha, const int8_t *target, const float *norm, float weight, int B,
                         int image_size, float *loss_img, int loss_stride, float *iou_img, int iou_stride,
                         float *grad_alpha, void *stream);
+/* hm_sil_loss_fwd_bwd followed by hm_raster_grad_prep in one kernel (same outputs, bit for bit): the loss gradient of
+ * a silhouette rendered by hm_raster_sil_fwd takes nine values per image, so it is kept as one byte per pixel in shared
+ * memory and the sweep masks / run lists are derived from it without re-reading grad_alpha. Precondition: alpha is the
+ * output of hm_raster_sil_fwd (multiples of 1/4). image_size a multiple of 32, at most 384. */
+int hm_sil_loss_prep(const float *alpha, const int8_t *target, const float *norm, float weight, int B, int image_size,
+                     int anti_aliasing, float *loss_img, int loss_stride, float *iou_img, int iou_stride,
+                     float *grad_alpha, const uint32_t *cov_row, const uint32_t *cov_col, uint32_t *m_row,
+                     uint32_t *m_col, void *runs, uint32_t *run_counts, void *stream);
 
 /* ---------------------------------------------------------------- MANO + rigid placement of the hand
  * ManoModel.forward_pca (homan/manomodel.py:84-151) -> mano layer LBS (un-vendored `mano` package,

@@ -217,3 +217,44 @@ def test_inter_metrics_match_oracle(mano_assets):
     assert ref[:3].min() > 0 and ref[3] == 0   # three interpenetrating scenes, one apart
     assert np.allclose(got["pen_depths"], ref, rtol=1e-4, atol=1e-7), (got["pen_depths"], ref)
     assert got["has_contact"] == (ref > 0).tolist()
+
+
+@pytest.mark.parametrize("aa", [True, False])
+def test_fused_loss_and_sweep_lists_equal_the_two_kernels(aa, mano_assets):
+    """hm_sil_loss_prep = hm_sil_loss_fwd_bwd + hm_raster_grad_prep, bit for bit: loss, IoU, grad_alpha, the four
+    sweep bit lines, the run counts and every stored run."""
+    from homan_b200 import ops
+    from homan_b200._lib import call, current_stream, ptr
+    clip = synth.make_clip(4, "ellipsoid500", seed=17, mano_asset=mano_assets["right"])
+    verts = np.concatenate((clip["gt"]["verts_hand"], clip["gt"]["verts_hand"] + np.float32([0.004, -0.003, 0.0])))
+    K = np.concatenate((clip["K_roi_hand"], clip["K_roi_hand"])).astype(np.float32)
+    B, R = verts.shape[0], 256
+    ndc = ops.project(torch.from_numpy(verts).cuda(), torch.from_numpy(K).cuda(), orig_size=1.0)
+    faces = torch.from_numpy(mano_assets["right"]["f"].astype(np.int32)).cuda()[None]
+    bufs = [ops.RasterBuffers(B, 778, faces.shape[1], R, aa, "cuda") for _ in range(2)]
+    rng = np.random.default_rng(2)
+    target = torch.roll((ops.raster_forward(bufs[0], ndc, faces) > 0.5).to(torch.int8), shifts=(4, -6), dims=(1, 2))
+    target[:, :, 100:124] = -1
+    target = target.contiguous()
+    norm = torch.from_numpy(rng.uniform(1e-6, 2e-6, size=B).astype(np.float32)).cuda()
+    ops.raster_forward(bufs[1], ndc, faces)
+    part = [torch.zeros(B, 16, device="cuda") for _ in range(2)]
+    ga = [torch.empty(B, R, R, device="cuda") for _ in range(2)]
+    s = current_stream()
+    for b_ in bufs:   # stale contents must not matter
+        b_.m_row.fill_(-1); b_.m_col.fill_(-1); b_.runs.fill_(-1); b_.run_counts.fill_(-1)
+    call("hm_sil_loss_fwd_bwd", ptr(bufs[0].alpha), ptr(target), ptr(norm), 1.5, B, R, ptr(part[0]), 16,
+         part[0].data_ptr() + 4, 16, ptr(ga[0]), s)
+    call("hm_raster_grad_prep", ptr(ga[0]), ptr(bufs[0].cov_row), ptr(bufs[0].cov_col), B, R, int(aa), ptr(bufs[0].m_row),
+         ptr(bufs[0].m_col), ptr(bufs[0].runs), ptr(bufs[0].run_counts), s)
+    call("hm_sil_loss_prep", ptr(bufs[1].alpha), ptr(target), ptr(norm), 1.5, B, R, int(aa), ptr(part[1]), 16,
+         part[1].data_ptr() + 4, 16, ptr(ga[1]), ptr(bufs[1].cov_row), ptr(bufs[1].cov_col), ptr(bufs[1].m_row),
+         ptr(bufs[1].m_col), ptr(bufs[1].runs), ptr(bufs[1].run_counts), s)
+    torch.cuda.synchronize()
+    assert torch.equal(ga[0], ga[1]) and float(ga[0].abs().max()) > 0
+    assert torch.allclose(part[0], part[1], rtol=1e-6)   # (sums over 256 vs 512 threads)
+    assert torch.equal(bufs[0].m_row, bufs[1].m_row) and torch.equal(bufs[0].m_col, bufs[1].m_col)
+    assert torch.equal(bufs[0].run_counts, bufs[1].run_counts)
+    cnt = (bufs[0].run_counts & 15).clamp(max=8)   # overflowed lists store their first 8 runs
+    stored = torch.arange(8, device="cuda").view(1, 1, 1, 8) < cnt.unsqueeze(-1)
+    assert int(cnt.max()) >= 2 and torch.equal(bufs[0].runs[stored], bufs[1].runs[stored])
