@@ -20,3 +20,18 @@ target = torch.roll(alpha.detach(), (3, -4), (1, 2)).round()
 alpha.backward(2 * (alpha.detach() - target) / target.numel())
 torch.cuda.synchronize()
 print("race input ok", float(alpha.sum()), float(ndc.grad.abs().max()))
+
+# the fused loss + sweep-list kernel (shared-memory byte map, ballot masks) and the backward on its lists
+from homan_b200._lib import call, current_stream, ptr  # noqa: E402
+buf = ops.RasterBuffers(1, ndc.shape[1], f.shape[1], 64, True, "cuda")
+ops.raster_forward(buf, ndc.detach(), f)
+tgt = target.to(torch.int8).contiguous()
+norm = torch.full((1,), 1e-4, device="cuda")
+part = torch.zeros(1, 16, device="cuda")
+ga = torch.empty(1, 64, 64, device="cuda")
+call("hm_sil_loss_prep", ptr(buf.alpha), ptr(tgt), ptr(norm), 1.0, 1, 64, 1, ptr(part), 16, part.data_ptr() + 4, 16, ptr(ga),
+     ptr(buf.cov_row), ptr(buf.cov_col), ptr(buf.m_row), ptr(buf.m_col), ptr(buf.runs), ptr(buf.run_counts), current_stream())
+gn = torch.zeros(1, ndc.shape[1], 3, device="cuda")
+ops.raster_backward(buf, ga, gn, prepared=True)
+torch.cuda.synchronize()
+print("fused prep ok", float(part[0, 0]), float(gn.abs().max()))
