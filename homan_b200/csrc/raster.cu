@@ -33,7 +33,8 @@ struct __align__(16) FaceRec {
     float inv[9];  // barycentric matrix in pixel coordinates, already divided by its determinant
     float iz[3];   // 1 / z of the three corners (fast depth of the forward pass)
     int exact;     // 1: some corner depth is not a plain positive float -> forward uses the reference arithmetic only
-    float pad2[3];
+    short fb[4];   // forward box x0 y0 x1 y1: the rows / columns the forward visits (tight; = bb for slivers, see the setup)
+    float pad2;
 };
 static_assert(sizeof(FaceRec) == 128, "record size");
 
@@ -55,8 +56,11 @@ constexpr int BWD_BOTH = 1 << 30;        // both windings are front-facing: F + 
 constexpr float BWD_SMAX = 128.f;        // tasks steeper than this are enumerated from the face (see the backward kernels)
 
 struct __align__(8) FaceBox {
-    short x0, y0, x1, y1;
+    short x0, y0, x1, y1;   // y1 also carries the forward's sort key above bit 12 (FBOX_*): readers mask it off
 };
+constexpr int FBOX_MASK = 0xfff;   // image sizes <= 4096 (the backward spans pack scan-lines in 12 bits too)
+constexpr int FBOX_REV = 1 << 12;  // the stored winding is the reversed (fill_back) copy: second pass of the forward
+constexpr int FBOX_CLS = 13;       // 2 bits: 0 = forward box <= 8 rows x 29 columns, 1 = <= 16 rows, 2 = larger
 static_assert(sizeof(FaceBox) == HM_FACE_BBOX_BYTES, "bbox size");
 
 // ------------------------------------------------------------------------------------------ projection
@@ -187,6 +191,7 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
     r.fn = fn;
     r.bb[0] = (short)x0; r.bb[1] = (short)y0; r.bb[2] = (short)x1; r.bb[3] = (short)y1;
     r.pad = both ? 1 : 0;
+    int fwd_key = 0;
     {   // barycentric matrix of the stored winding (same expressions as the oracle's per-face setup)
         const float p00 = to_pix(r.c[0], is), p01 = to_pix(r.c[1], is), p10 = to_pix(r.c[3], is), p11 = to_pix(r.c[4], is),
                     p20 = to_pix(r.c[6], is), p21 = to_pix(r.c[7], is);
@@ -206,8 +211,23 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
             const float z = r.c[3 * k + 2];
             r.iz[k] = 1.f / z;
             if (!(z > 1e-20f && z < 1e20f)) r.exact = 1;
-            r.pad2[k] = 0.f;
         }
+        r.pad2 = 0.f;
+        // Forward box: a sample a whole pixel outside the bounding box of the corners cannot pass the three edge
+        // predicates unless the triangle is a needle (the margin of the test is the sample's distance to the edge
+        // lines, ~sin(apex angle) pixels, against ~1e-5 of rounding): faces with |det| >= 1e-3 |longest edge|^2 get the
+        // tight box floor(min) .. ceil(max), needles and both-winding faces keep the reference's box with 1 px of slack.
+        const float l2 = fmaxf(fmaxf((p10 - p00) * (p10 - p00) + (p11 - p01) * (p11 - p01),
+                                     (p20 - p10) * (p20 - p10) + (p21 - p11) * (p21 - p11)),
+                               (p00 - p20) * (p00 - p20) + (p01 - p21) * (p01 - p21));
+        int g0 = x0, g1 = y0, g2 = x1, g3 = y1;
+        if (x0 <= x1 && !both && fabsf(den) >= 1e-3f * l2 && l2 < 1e30f) {
+            g0 = max(__float2int_rz(floorf(xmin)), 0); g1 = max(__float2int_rz(floorf(ymin)), 0);
+            g2 = min(__float2int_rz(ceilf(xmax)), is - 1); g3 = min(__float2int_rz(ceilf(ymax)), is - 1);
+        }
+        r.fb[0] = (short)g0; r.fb[1] = (short)g1; r.fb[2] = (short)g2; r.fb[3] = (short)g3;
+        const int hf = g3 - g1 + 1, wf = g2 - g0 + 1;
+        fwd_key = (rev ? FBOX_REV : 0) | ((both ? 2 : (hf <= 8 && wf <= 29) ? 0 : hf <= 16 ? 1 : 2) << FBOX_CLS);
     }
     recs[i] = r;
     {
@@ -249,7 +269,7 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
         brecs[i] = br;
     }
     FaceBox bx;
-    bx.x0 = (short)x0; bx.y0 = (short)y0; bx.x1 = (short)x1; bx.y1 = (short)y1;
+    bx.x0 = (short)x0; bx.y0 = (short)y0; bx.x1 = (short)x1; bx.y1 = (short)(y1 | fwd_key);
     boxes[i] = bx;
     // pixel box of the whole image (all its faces): {x0, y0, -x1, -y1} under atomicMin, preset to 0x7f7f7f7f. One
     // reduction per warp over the lanes of the first lane's image, the other lanes (next image) on their own.
@@ -271,8 +291,11 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
 constexpr int LISTCAP = 2048;  // faces of one tile processed per batch
 
 constexpr int SCAN = 4 * NTHREADS;  // faces tested per scan step (four 8-byte boxes per thread)
+constexpr unsigned ENT_FACE = (1u << 29) - 1u;   // list entry: face | size class << 29
 
-// Appends to list[*cnt...] the faces of [base, base + SCAN) whose bbox touches the tile.
+// Appends the faces of [base, base + SCAN) whose bbox touches the tile: faces stored in their original winding (first
+// pass of the forward) from the front of the list, reversed copies (second pass) from its back; cnt[0], cnt[1] count
+// them. The entry carries the size class the setup kernel derived from the forward box.
 __device__ __forceinline__ void append_faces(const FaceBox *__restrict__ boxes, int base, int F, int tx0, int ty0,
                                              int *list, int *cnt) {
     const int f0 = base + 4 * threadIdx.x;
@@ -294,14 +317,16 @@ __device__ __forceinline__ void append_faces(const FaceBox *__restrict__ boxes, 
         }
     }
     const int lane = threadIdx.x & 31;
-    unsigned hits = 0;
+    unsigned hits = 0, revs = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+        const int y1 = bx[k].y1 & FBOX_MASK;
         const bool hit = bx[k].x0 <= bx[k].x1 && bx[k].x0 <= tx0 + TILE - 1 && bx[k].x1 >= tx0 &&
-                         bx[k].y0 <= ty0 + TILE - 1 && bx[k].y1 >= ty0;
+                         bx[k].y0 <= ty0 + TILE - 1 && y1 >= ty0;
         hits |= (hit ? 1u : 0u) << k;
+        revs |= ((hit && (bx[k].y1 & FBOX_REV)) ? 1u : 0u) << k;
     }
-    const int mine = __popc(hits);
+    const int mine = __popc(hits & ~revs) | (__popc(revs) << 16);   // both counts in one scan
     int incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -309,29 +334,42 @@ __device__ __forceinline__ void append_faces(const FaceBox *__restrict__ boxes, 
         if (lane >= o) incl += v;
     }
     const int total = __shfl_sync(0xffffffffu, incl, 31);
-    int wbase = 0;
-    if (lane == 31 && total) wbase = atomicAdd(cnt, total);
-    wbase = __shfl_sync(0xffffffffu, wbase, 31);
-    int pos = wbase + incl - mine;
+    int wb0 = 0, wb1 = 0;
+    if (lane == 31) {
+        if (total & 0xffff) wb0 = atomicAdd(&cnt[0], total & 0xffff);
+        if (total >> 16) wb1 = atomicAdd(&cnt[1], total >> 16);
+    }
+    wb0 = __shfl_sync(0xffffffffu, wb0, 31);
+    wb1 = __shfl_sync(0xffffffffu, wb1, 31);
+    int pos0 = wb0 + ((incl - mine) & 0xffff), pos1 = wb1 + ((incl - mine) >> 16);
 #pragma unroll
     for (int k = 0; k < 4; ++k)
-        if ((hits >> k) & 1u) list[pos++] = f0 + k;
+        if ((hits >> k) & 1u) {
+            const int ent = (f0 + k) | (((bx[k].y1 >> FBOX_CLS) & 3) << 29);
+            if ((revs >> k) & 1u) list[LISTCAP - 1 - pos1++] = ent;
+            else list[pos0++] = ent;
+        }
 }
 
-// Fills the list with the next batch of faces touching the tile (scanning from *base). Block-uniform.
+// Fills the list with the next batch of faces touching the tile (scanning from *base). Block-uniform; returns the
+// number of entries (cnt[0] from the front + cnt[1] from the back).
 __device__ __forceinline__ int next_batch(const FaceBox *__restrict__ boxes, int &base, int F, int tx0, int ty0,
-                                          int *list, int *cnt, int *next, int cap = LISTCAP) {
+                                          int *list, int *cnt, int *next) {
     __syncthreads();
-    if (threadIdx.x == 0) { *cnt = 0; *next = 0; }
+    if (threadIdx.x == 0) { cnt[0] = 0; cnt[1] = 0; *next = 0; }
     __syncthreads();
     int n = 0;
-    while (base < F && n <= cap - SCAN) {
+    while (base < F && n <= LISTCAP - SCAN) {
         append_faces(boxes, base, F, tx0, ty0, list, cnt);
         base += SCAN;
         __syncthreads();
-        n = *cnt;
+        n = cnt[0] + cnt[1];
     }
     return n;
+}
+// Entry li of the batch (front entries first).
+__device__ __forceinline__ int batch_face(const int *list, int n0, int li) {
+    return (li < n0 ? list[li] : list[LISTCAP - 1 - (li - n0)]) & (int)ENT_FACE;
 }
 
 // ------------------------------------------------------------------------------------------ forward
@@ -345,7 +383,6 @@ constexpr unsigned AMB = 48;   // ulp; the two evaluation orders differ by < 8 u
 constexpr int HZ = 4;          // hierarchical-z block edge (pixels)
 constexpr int HZN = TILE / HZ;
 constexpr int AMBCAP = NWARPS * 64;
-constexpr int FCH = 64;        // face records staged in shared memory at a time
 
 __device__ __forceinline__ bool ulp_close(unsigned a, unsigned b) {
     const unsigned d = a > b ? a - b : b - a;
@@ -398,6 +435,36 @@ __device__ __forceinline__ void clip_edge(const RowCtx &rc, float A, float xk, f
     }  // NaN slope: the comparison is false for every sample, all pass
 }
 
+// A tile no face touches: constants, four 16-byte stores per thread.
+__device__ __forceinline__ void write_untouched_tile(int b, int tx0, int ty0, int is, int aa,
+                                                     int32_t *__restrict__ face_index, float *__restrict__ alpha,
+                                                     uint32_t *__restrict__ cov_row, uint32_t *__restrict__ cov_col,
+                                                     unsigned char *__restrict__ cov_blocks) {
+    const int W = is / 32, t = threadIdx.x;
+    {
+        int4 *p = reinterpret_cast<int4 *>(face_index + ((long)b * is + ty0 + (t >> 4)) * is + tx0 + 4 * (t & 15));
+        const long rs = 4 * (long)is;   // 16 rows further, in int4 units
+        const int4 m1 = make_int4(-1, -1, -1, -1);
+        p[0] = m1; p[rs] = m1; p[2 * rs] = m1; p[3 * rs] = m1;
+    }
+    if (t < 2 * TILE) {
+        const int yl = t >> 1, w = t & 1;
+        if (cov_row) cov_row[((long)b * is + (ty0 + yl)) * W + (tx0 >> 5) + w] = 0u;
+        if (cov_col) cov_col[((long)b * is + (tx0 + yl)) * W + (ty0 >> 5) + w] = 0u;
+    }
+    if (cov_blocks && t < 2 * (TILE / 8))
+        cov_blocks[((long)b * (is / 8) + (ty0 >> 3) + (t >> 1)) * W + (tx0 >> 5) + (t & 1)] = 0xf;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (aa) {
+        const int R = is / 2, rtop = R - 1 - (ty0 >> 1);   // 32 x 32 outputs: one float4 per thread
+        *reinterpret_cast<float4 *>(alpha + ((long)b * R + (rtop - (t >> 3))) * R + (tx0 >> 1) + 4 * (t & 7)) = z4;
+    } else {
+        float4 *p = reinterpret_cast<float4 *>(alpha + ((long)b * is + (is - 1 - ty0 - (t >> 4))) * is + tx0 + 4 * (t & 15));
+        const long rs = 4 * (long)is;
+        p[0] = z4; *(p - rs) = z4; *(p - 2 * rs) = z4; *(p - 3 * rs) = z4;
+    }
+}
+
 __global__ void __launch_bounds__(NTHREADS, 4)
 raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ boxes, int F, int is, int aa,
                   float near_, float far_, int32_t *__restrict__ face_index, float *__restrict__ alpha,
@@ -405,18 +472,29 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                   unsigned char *__restrict__ cov_blocks, const int *__restrict__ img_box) {
     extern __shared__ __align__(16) unsigned long long keys[];  // [TILE * TILE] z-buffer (dynamic: static + this > 48 KB)
     __shared__ int list[LISTCAP];
-    __shared__ int cnt, next;
+    __shared__ int cnt[2], next;
     __shared__ uint32_t roww[TILE][2];
     __shared__ uint32_t amb[TILE][2];   // ambiguous pixels (see above)
     __shared__ int n_amb;
     __shared__ unsigned hiz[HZN * HZN];  // per 4x4 block: largest winning depth so far (far when a pixel is empty)
-    __shared__ unsigned short ambl[AMBCAP];
-    __shared__ __align__(16) float4 srec[FCH][8];  // staged face records
+    __shared__ __align__(4) unsigned short ambl[AMBCAP];
+    __shared__ __align__(16) float4 wrec_all[NWARPS][8];  // per warp: the record of its current face
     __shared__ short spanx[NWARPS][64], spanpre[NWARPS][64];
     const int b = blockIdx.y;
     const int tiles_x = is / TILE;
     const int tx0 = (blockIdx.x % tiles_x) * TILE, ty0 = (blockIdx.x / tiles_x) * TILE;
-    const int lane = threadIdx.x & 31;
+    // ---- tiles no face touches (outside the image's pixel box, or an empty first scan of all faces) write constants
+    bool untouched;
+    {
+        const int4 ib = __ldg(reinterpret_cast<const int4 *>(img_box) + b);   // {x0, y0, -x1, -y1}
+        untouched = F == 0 || ib.x > tx0 + TILE - 1 || -ib.z < tx0 || ib.y > ty0 + TILE - 1 || -ib.w < ty0;
+    }
+    if (untouched) {
+        write_untouched_tile(b, tx0, ty0, is, aa, face_index, alpha, cov_row, cov_col, cov_blocks);
+        return;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned FULL = 0xffffffffu;
     RowCtx rc;
     rc.is = is; rc.pow2 = (is & (is - 1)) == 0; rc.inv_is = 1.f / (float)is;
     const bool pow2 = rc.pow2;
@@ -425,51 +503,22 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
     const unsigned long long empty = ((unsigned long long)far_bits << 32) | 0xffffffffull;
     recs += (long)b * F;
     boxes += (long)b * F;
-    // ---- tiles no face touches (outside the image's pixel box, or an empty first scan of all faces) write constants
-    bool untouched;
-    {
-        const int4 ib = __ldg(reinterpret_cast<const int4 *>(img_box) + b);   // {x0, y0, -x1, -y1}
-        untouched = F == 0 || ib.x > tx0 + TILE - 1 || -ib.z < tx0 || ib.y > ty0 + TILE - 1 || -ib.w < ty0;
-    }
-    int base = 0, n_first = 0;
-    if (!untouched) {
-        n_first = next_batch(boxes, base, F, tx0, ty0, list, &cnt, &next);
-        untouched = n_first == 0 && base >= F;
-    }
-    if (untouched) {
-        const int W = is / 32;
-        for (int i = threadIdx.x; i < TILE * TILE / 4; i += NTHREADS) {
-            const int yl = i / (TILE / 4), x4 = i % (TILE / 4);
-            *reinterpret_cast<int4 *>(face_index + ((long)b * is + (ty0 + yl)) * is + tx0 + 4 * x4) = make_int4(-1, -1, -1, -1);
-        }
-        if (threadIdx.x < 2 * TILE) {
-            const int yl = threadIdx.x >> 1, w = threadIdx.x & 1;
-            if (cov_row) cov_row[((long)b * is + (ty0 + yl)) * W + (tx0 >> 5) + w] = 0u;
-            if (cov_col) cov_col[((long)b * is + (tx0 + yl)) * W + (ty0 >> 5) + w] = 0u;
-        }
-        if (cov_blocks && threadIdx.x < 2 * (TILE / 8))
-            cov_blocks[((long)b * (is / 8) + (ty0 >> 3) + (threadIdx.x >> 1)) * W + (tx0 >> 5) + (threadIdx.x & 1)] = 0xf;
-        if (aa) {
-            const int R = is / 2, rtop = R - 1 - (ty0 >> 1);
-            for (int i = threadIdx.x; i < (TILE / 2) * (TILE / 2) / 4; i += NTHREADS) {
-                const int m = i / (TILE / 8), c4 = i % (TILE / 8);
-                *reinterpret_cast<float4 *>(alpha + ((long)b * R + (rtop - m)) * R + (tx0 >> 1) + 4 * c4) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        } else {
-            for (int i = threadIdx.x; i < TILE * TILE / 4; i += NTHREADS) {
-                const int yl = i / (TILE / 4), x4 = i % (TILE / 4);
-                *reinterpret_cast<float4 *>(alpha + ((long)b * is + (is - 1 - ty0 - yl)) * is + tx0 + 4 * x4) = make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-        }
+    int base = 0;
+    int n_first = next_batch(boxes, base, F, tx0, ty0, list, cnt, &next);
+    if (n_first == 0 && base >= F) {
+        write_untouched_tile(b, tx0, ty0, is, aa, face_index, alpha, cov_row, cov_col, cov_blocks);
         return;
     }
     for (int i = threadIdx.x; i < TILE * TILE / 2; i += NTHREADS)
         reinterpret_cast<ulonglong2 *>(keys)[i] = make_ulonglong2(empty, empty);
     if (threadIdx.x < 2 * TILE) (&amb[0][0])[threadIdx.x] = 0u;
+    __syncthreads();
 
+    float4 *wrec = wrec_all[warp];
+    short *rowx = spanx[warp], *rowpre = spanpre[warp];
     bool first = true;
     while (first || base < F) {
-        const int n = first ? n_first : next_batch(boxes, base, F, tx0, ty0, list, &cnt, &next);
+        if (!first) next_batch(boxes, base, F, tx0, ty0, list, cnt, &next);
         first = false;
         // two passes: faces kept in their original winding (the outer layer of an outward-wound closed mesh)
         // first, the reversed copies second. Between them the winners are summarised per 4x4 block, so that a
@@ -478,6 +527,7 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
         if (pass == 1) {
             __syncthreads();
             hiz[threadIdx.x] = 0u;
+            if (threadIdx.x == 0) next = 0;
             __syncthreads();
             for (int k = 0; k < TILE * TILE / NTHREADS; ++k) {  // 256 keys = 4 rows = one row of blocks, conflict-free
                 unsigned m = (unsigned)(keys[k * NTHREADS + threadIdx.x] >> 32);
@@ -487,25 +537,39 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             }
             __syncthreads();
         }
-        for (int c0 = 0; c0 < n; c0 += FCH) {
-        // ---- the records of the next FCH listed faces go to shared memory with one cooperative load (a warp
-        //      walking its faces one dependent global load at a time is bound by L2 latency)
-        const int cn = min(FCH, n - c0);
-        __syncthreads();
-        for (int i = threadIdx.x; i < cn * 8; i += NTHREADS)
-            srec[i >> 3][i & 7] = __ldg(reinterpret_cast<const float4 *>(recs + list[c0 + (i >> 3)]) + (i & 7));
-        __syncthreads();
-        for (int j = threadIdx.x >> 5; j < cn; j += NWARPS) {  // faces dealt round-robin to the warps
-            const float4 *rp = srec[j];
+        const int np = cnt[pass];
+        // ---- no barrier inside a pass: a warp draws one face of the pass at a time from a shared counter, and the
+        //      128-byte record of its next face is fetched (one float4 in each of eight lanes) while the current one
+        //      is processed. (With the records staged 64 at a time behind CTA barriers the warp with the largest
+        //      faces of a chunk kept the other seven waiting: barrier stalls led the profile.)
+        int j = 0;
+        if (lane == 0) j = atomicAdd(&next, 1);
+        j = __shfl_sync(FULL, j, 0);
+        float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < np && lane < 8)
+            pre = __ldg(reinterpret_cast<const float4 *>(recs + ((pass ? list[LISTCAP - 1 - j] : list[j]) & (int)ENT_FACE)) + lane);
+        while (j < np) {
+            __syncwarp();   // the previous face is done with wrec / rowx / rowpre
+            if (lane < 8) wrec[lane] = pre;
+            __syncwarp();
+            {
+                int jn = 0;
+                if (lane == 0) jn = atomicAdd(&next, 1);
+                j = __shfl_sync(FULL, jn, 0);
+                if (j < np && lane < 8)
+                    pre = __ldg(reinterpret_cast<const float4 *>(recs + ((pass ? list[LISTCAP - 1 - j] : list[j]) & (int)ENT_FACE)) + lane);
+            }
+            const int sub = lane;
+            const float4 *rp = wrec;
             const float4 q2 = rp[2];
-            if ((__float_as_int(q2.y) >= F ? 1 : 0) != pass) continue;
             const int4 q3 = *reinterpret_cast<const int4 *>(rp + 3);
             const float4 q0 = rp[0], q1 = rp[1];
             const float f0 = q0.x, f1 = q0.y, f2 = q0.z, f3 = q0.w, f4 = q1.x, f5 = q1.y, f6 = q1.z, f7 = q1.w,
                         f8 = q2.x;
             const int fn = __float_as_int(q2.y);
-            const int bx0 = (short)(q3.y & 0xffff), by0 = (short)(q3.y >> 16);
-            const int bx1 = (short)(q3.z & 0xffff), by1 = (short)(q3.z >> 16);
+            const int4 q7 = *reinterpret_cast<const int4 *>(rp + 7);
+            const int bx0 = (short)(q7.y & 0xffff), by0 = (short)(q7.y >> 16);   // forward box
+            const int bx1 = (short)(q7.z & 0xffff), by1 = (short)(q7.z >> 16);
             const int X0 = max(bx0, tx0), X1 = min(bx1, tx0 + TILE - 1);
             const int Y0 = max(by0, ty0), Y1 = min(by1, ty0 + TILE - 1);
             const int w = X1 - X0 + 1, h = Y1 - Y0 + 1;
@@ -532,19 +596,17 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 bool vis = false;
                 if (hx <= hx1)
                     for (int hy = hy0 + (lane >> 4); hy <= hy1; hy += 2) vis |= !(zmin_bits > hiz[hy * HZN + hx]);
-                if (!__any_sync(0xffffffffu, vis)) continue;
+                if (!__any_sync(FULL, vis)) continue;
             }
-            // Covered pixels: per row of the bbox the exact interval of samples inside the triangle (clip_edge), then
-            // the pixels of all rows flattened over the lanes through a prefix sum of the interval lengths -
-            // slivers and diagonal faces cost their area, not their bounding box, and no sample is tested twice.
-            short *rowx = spanx[threadIdx.x >> 5], *rowpre = spanpre[threadIdx.x >> 5];
+            // Covered pixels: per row of the box the exact interval of samples inside the triangle (clip_edge), then
+            // the pixels of all rows flattened over the lanes of the group through a prefix sum of the interval
+            // lengths - slivers and diagonal faces cost their area, not their bounding box, and no sample is tested twice.
             int n_px;
             {
-                int len[2] = {0, 0}, xlo[2] = {X0, X0};
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    if (half == 1 && h <= 32) break;  // (warp-uniform)
-                    const int r = lane + 32 * half;
+                int len0 = 0, len1 = 0, xlo0 = X0, xlo1 = X0;
+                const bool two = h > 32;   // (warp-uniform)
+                for (int half = 0; half < (two ? 2 : 1); ++half) {
+                    const int r = sub + 32 * half;
                     if (r < h) {
                         const int yi = Y0 + r;
                         const float yp = pow2 ? (float)(2 * yi + 1 - is) * inv_is : (float)(2 * yi + 1 - is) / (float)is;
@@ -552,45 +614,50 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                         clip_edge(rc, (yp - f1) * e0x, f0, e0y, X0, X1, lo, hi);
                         clip_edge(rc, (yp - f4) * e1x, f3, e1y, X0, X1, lo, hi);
                         clip_edge(rc, (yp - f7) * e2x, f6, e2y, X0, X1, lo, hi);
-                        xlo[half] = lo;
-                        len[half] = max(hi - lo + 1, 0);
+                        const int ln = max(hi - lo + 1, 0);
+                        if (half == 0) { xlo0 = lo; len0 = ln; } else { xlo1 = lo; len1 = ln; }
                     }
                 }
-                int inc0 = len[0], inc1 = len[1];
+                int inc0 = len0, inc1 = len1;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const int v0 = __shfl_up_sync(0xffffffffu, inc0, o), v1 = __shfl_up_sync(0xffffffffu, inc1, o);
+                    const int v0 = __shfl_up_sync(FULL, inc0, o), v1 = __shfl_up_sync(FULL, inc1, o);
                     if (lane >= o) { inc0 += v0; inc1 += v1; }
                 }
-                const int tot0 = __shfl_sync(0xffffffffu, inc0, 31), tot1 = __shfl_sync(0xffffffffu, inc1, 31);
-                __syncwarp();
-                rowx[lane] = (short)xlo[0]; rowpre[lane] = (short)(inc0 - len[0]);
-                rowx[lane + 32] = (short)xlo[1]; rowpre[lane + 32] = (short)(tot0 + inc1 - len[1]);
+                const int tot0 = __shfl_sync(FULL, inc0, 31), tot1 = __shfl_sync(FULL, inc1, 31);
+                rowx[lane] = (short)xlo0; rowpre[lane] = (short)(inc0 - len0);
+                rowx[lane + 32] = (short)xlo1; rowpre[lane + 32] = (short)(tot0 + inc1 - len1);
                 n_px = tot0 + tot1;
                 __syncwarp();
             }
-            if (n_px == 0) continue;  // the bounding box touches the tile, the triangle covers no sample of it
+            if (n_px == 0) continue;  // the box touches the tile, the triangle covers no sample of it
             // barycentric matrix in pixel coordinates and corner 1/z, prepared once per face by the setup kernel
             float inv[9], iz0, iz1, iz2;
-            int exact_face;
             {
                 const float4 i0 = rp[4], i1 = rp[5], i2 = rp[6];
                 inv[0] = i0.x; inv[1] = i0.y; inv[2] = i0.z; inv[3] = i0.w;
                 inv[4] = i1.x; inv[5] = i1.y; inv[6] = i1.z; inv[7] = i1.w;
                 inv[8] = i2.x; iz0 = i2.y; iz1 = i2.z; iz2 = i2.w;
-                exact_face = __float_as_int(rp[7].x);
             }
-            int row = 0;
-            for (int i = lane; i < n_px; i += 32) {
-                if (i == lane) {   // first pixel of the lane: binary search over the rows; afterwards the row only advances
-                    if (h > 32 && rowpre[32] <= i) row = 32;
+            const int exact_face = q7.x;
+            const short *gx = rowx, *gpre = rowpre;
+            int row = 0, rend = 0, xoff = 0;   // current row, first pixel index of the next non-visited row, x - i of the row
+            for (int i = sub; i < n_px; i += 32) {
+                if (i == sub) {   // first pixel of the lane: binary search over the rows; afterwards the row only advances
+                    if (h > 32 && gpre[32] <= i) row = 32;
 #pragma unroll
                     for (int sft = 16; sft > 0; sft >>= 1)
-                        if (row + sft < h && rowpre[row + sft] <= i) row += sft;
+                        if (row + sft < h && gpre[row + sft] <= i) row += sft;
+                    rend = row + 1 < h ? gpre[row + 1] : 0x7fffffff;
+                    xoff = gx[row] - gpre[row];
                 } else {
-                    while (row + 1 < h && rowpre[row + 1] <= i) ++row;
+                    while (i >= rend) {
+                        ++row;
+                        xoff = gx[row] - rend;
+                        rend = row + 1 < h ? gpre[row + 1] : 0x7fffffff;
+                    }
                 }
-                const int xi = rowx[row] + (i - rowpre[row]), yi = Y0 + row;
+                const int xi = xoff + i, yi = Y0 + row;
                 const int xl = xi - tx0, yl = yi - ty0;
                 unsigned long long *kp = &keys[yl * TILE + xl];
                 const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
@@ -617,8 +684,6 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 }
                 if (flag) atomicOr(&amb[yl][xl >> 5], 1u << (xl & 31));
             }
-            __syncwarp();  // rowx / rowpre are rewritten by the next face
-        }
         }
         }
     }
@@ -649,9 +714,10 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
         if (na == 0) break;
         int base2 = 0;
         while (base2 < F) {
-            const int n = next_batch(boxes, base2, F, tx0, ty0, list, &cnt, &next);
+            const int n = next_batch(boxes, base2, F, tx0, ty0, list, cnt, &next);
+            const int n_front = cnt[0];
             for (int li = threadIdx.x >> 5; li < n; li += NWARPS) {
-                const FaceRec *rp = recs + list[li];
+                const FaceRec *rp = recs + batch_face(list, n_front, li);
                 int fn = __ldg(reinterpret_cast<const int *>(rp) + 9);
                 if (fn < 0) continue;
                 float f[9], inv[9];
@@ -1263,7 +1329,8 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ 
                 // irregular faces and faces with a steep task (sweep ends extrapolated with large slopes) always sweep
                 bool boundary = (q3.w & BWD_IRREGULAR) || ((s4.x | s4.y | s4.z | s4.w | s5.x | s5.y) & (1u << 25));
                 if (!boundary) {
-                    const FaceBox bx = boxes[f];   // clamped pixel bbox with one pixel of slack
+                    FaceBox bx = boxes[f];   // clamped pixel bbox with one pixel of slack
+                    bx.y1 &= FBOX_MASK;
                     const int w0 = bx.x0 >> 5, w1 = bx.x1 >> 5;
                     for (int band = bx.y0 >> 3; band <= (bx.y1 >> 3) && !boundary; ++band)
                         for (int w = w0; w <= w1; ++w) {

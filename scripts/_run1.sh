@@ -1,9 +1,24 @@
-timeout 900 python -m pytest tests/test_raster_gpu.py tests/test_raster_stress_gpu.py tests/test_fullsize_gpu.py -m gpu -q --no-header -x 2>&1 | tail -15
-for v in new old; do
-if [ $v = old ]; then export HOMAN_B200_BWD_OLD=1; fi
-timeout 300 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_a.json 2> gpurun_out/bench_a.err; python - <<PY
+#!/bin/bash
+# Development: raster tests on the new library, A/B bench against _variants/*.so, full ncu capture of the forward.
+mkdir -p gpurun_out
+python -m oracle.build > /dev/null
+timeout 900 python -m pytest tests/test_raster_gpu.py tests/test_raster_stress_gpu.py tests/test_fullsize_gpu.py -m gpu -q --no-header -x 2>&1 | tail -8
+ab() {
+timeout 300 python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_$1.json 2> gpurun_out/bench_$1.err; python - <<PY
 import json
-d=json.load(open("gpurun_out/bench_a.json")); b=d["breakdown_us"]
-print("$v", d["value"], d["ms_per_step"], {k:v["us_each"] for k,v in b.items() if "raster" in k})
+d=json.load(open("gpurun_out/bench_$1.json")); b=d["breakdown_us"]
+print("$1", round(d["value"],1), round(d["ms_per_step"],3), {k:v["us_each"] for k,v in b.items() if "raster" in k or "prep" in k or "sdf" in k})
 PY
+}
+ab new
+cp homan_b200/libhoman_b200.so /tmp/lib_new.so
+for f in homan_b200/_variants/*.so; do
+  cp $f homan_b200/libhoman_b200.so
+  ab $(basename $f .so)
 done
+cp /tmp/lib_new.so homan_b200/libhoman_b200.so
+if [ -n "$PROF" ]; then
+ncu --set full --clock-control none --import-source on -k regex:"$PROF" -s ${PROF_SKIP:-4} -c ${PROF_N:-2} -f \
+    -o gpurun_out/prof_one python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_one.log 2>&1
+tail -2 gpurun_out/prof_one.log | cut -c1-200
+fi
