@@ -56,11 +56,11 @@ constexpr int BWD_BOTH = 1 << 30;        // both windings are front-facing: F + 
 constexpr float BWD_SMAX = 128.f;        // tasks steeper than this are enumerated from the face (see the backward kernels)
 
 struct __align__(8) FaceBox {
-    short x0, y0, x1, y1;   // y1 also carries the forward's sort key above bit 12 (FBOX_*): readers mask it off
+    short x0, y0, x1, y1;   // y1 also carries the forward's pass bit (FBOX_REV): readers mask it off
 };
 constexpr int FBOX_MASK = 0xfff;   // image sizes <= 4096 (the backward spans pack scan-lines in 12 bits too)
 constexpr int FBOX_REV = 1 << 12;  // the stored winding is the reversed (fill_back) copy: second pass of the forward
-constexpr int FBOX_CLS = 13;       // 2 bits: 0 = forward box <= 8 rows x 29 columns, 1 = <= 16 rows, 2 = larger
+
 static_assert(sizeof(FaceBox) == HM_FACE_BBOX_BYTES, "bbox size");
 
 // ------------------------------------------------------------------------------------------ projection
@@ -226,8 +226,7 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
             g2 = min(__float2int_rz(ceilf(xmax)), is - 1); g3 = min(__float2int_rz(ceilf(ymax)), is - 1);
         }
         r.fb[0] = (short)g0; r.fb[1] = (short)g1; r.fb[2] = (short)g2; r.fb[3] = (short)g3;
-        const int hf = g3 - g1 + 1, wf = g2 - g0 + 1;
-        fwd_key = (rev ? FBOX_REV : 0) | ((both ? 2 : (hf <= 8 && wf <= 29) ? 0 : hf <= 16 ? 1 : 2) << FBOX_CLS);
+        fwd_key = rev ? FBOX_REV : 0;
     }
     recs[i] = r;
     {
@@ -291,11 +290,10 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
 constexpr int LISTCAP = 2048;  // faces of one tile processed per batch
 
 constexpr int SCAN = 4 * NTHREADS;  // faces tested per scan step (four 8-byte boxes per thread)
-constexpr unsigned ENT_FACE = (1u << 29) - 1u;   // list entry: face | size class << 29
 
 // Appends the faces of [base, base + SCAN) whose bbox touches the tile: faces stored in their original winding (first
 // pass of the forward) from the front of the list, reversed copies (second pass) from its back; cnt[0], cnt[1] count
-// them. The entry carries the size class the setup kernel derived from the forward box.
+// them.
 __device__ __forceinline__ void append_faces(const FaceBox *__restrict__ boxes, int base, int F, int tx0, int ty0,
                                              int *list, int *cnt) {
     const int f0 = base + 4 * threadIdx.x;
@@ -345,9 +343,8 @@ __device__ __forceinline__ void append_faces(const FaceBox *__restrict__ boxes, 
 #pragma unroll
     for (int k = 0; k < 4; ++k)
         if ((hits >> k) & 1u) {
-            const int ent = (f0 + k) | (((bx[k].y1 >> FBOX_CLS) & 3) << 29);
-            if ((revs >> k) & 1u) list[LISTCAP - 1 - pos1++] = ent;
-            else list[pos0++] = ent;
+            if ((revs >> k) & 1u) list[LISTCAP - 1 - pos1++] = f0 + k;
+            else list[pos0++] = f0 + k;
         }
 }
 
@@ -369,7 +366,7 @@ __device__ __forceinline__ int next_batch(const FaceBox *__restrict__ boxes, int
 }
 // Entry li of the batch (front entries first).
 __device__ __forceinline__ int batch_face(const int *list, int n0, int li) {
-    return (li < n0 ? list[li] : list[LISTCAP - 1 - (li - n0)]) & (int)ENT_FACE;
+    return li < n0 ? list[li] : list[LISTCAP - 1 - (li - n0)];
 }
 
 // ------------------------------------------------------------------------------------------ forward
@@ -547,7 +544,7 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
         j = __shfl_sync(FULL, j, 0);
         float4 pre = make_float4(0.f, 0.f, 0.f, 0.f);
         if (j < np && lane < 8)
-            pre = __ldg(reinterpret_cast<const float4 *>(recs + ((pass ? list[LISTCAP - 1 - j] : list[j]) & (int)ENT_FACE)) + lane);
+            pre = __ldg(reinterpret_cast<const float4 *>(recs + (pass ? list[LISTCAP - 1 - j] : list[j])) + lane);
         while (j < np) {
             __syncwarp();   // the previous face is done with wrec / rowx / rowpre
             if (lane < 8) wrec[lane] = pre;
@@ -557,9 +554,8 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 if (lane == 0) jn = atomicAdd(&next, 1);
                 j = __shfl_sync(FULL, jn, 0);
                 if (j < np && lane < 8)
-                    pre = __ldg(reinterpret_cast<const float4 *>(recs + ((pass ? list[LISTCAP - 1 - j] : list[j]) & (int)ENT_FACE)) + lane);
+                    pre = __ldg(reinterpret_cast<const float4 *>(recs + (pass ? list[LISTCAP - 1 - j] : list[j])) + lane);
             }
-            const int sub = lane;
             const float4 *rp = wrec;
             const float4 q2 = rp[2];
             const int4 q3 = *reinterpret_cast<const int4 *>(rp + 3);
@@ -606,7 +602,7 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 int len0 = 0, len1 = 0, xlo0 = X0, xlo1 = X0;
                 const bool two = h > 32;   // (warp-uniform)
                 for (int half = 0; half < (two ? 2 : 1); ++half) {
-                    const int r = sub + 32 * half;
+                    const int r = lane + 32 * half;
                     if (r < h) {
                         const int yi = Y0 + r;
                         const float yp = pow2 ? (float)(2 * yi + 1 - is) * inv_is : (float)(2 * yi + 1 - is) / (float)is;
@@ -642,8 +638,8 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             const int exact_face = q7.x;
             const short *gx = rowx, *gpre = rowpre;
             int row = 0, rend = 0, xoff = 0;   // current row, first pixel index of the next non-visited row, x - i of the row
-            for (int i = sub; i < n_px; i += 32) {
-                if (i == sub) {   // first pixel of the lane: binary search over the rows; afterwards the row only advances
+            for (int i = lane; i < n_px; i += 32) {
+                if (i == lane) {   // first pixel of the lane: binary search over the rows; afterwards the row only advances
                     if (h > 32 && gpre[32] <= i) row = 32;
 #pragma unroll
                     for (int sft = 16; sft > 0; sft >>= 1)

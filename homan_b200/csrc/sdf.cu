@@ -125,6 +125,7 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
     __shared__ float box[4];  // centre xyz, scale
     __shared__ unsigned short vlist[VLIST];
     __shared__ int wtot[PNT / 32];
+    __shared__ unsigned short wq[PNT / 32][64];   // per warp: faces waiting for the exact distance test
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *vg = verts_g + (long)b * Vg * 3;
     const float *vs = verts_s + (long)b * Vs * 3;
@@ -183,22 +184,30 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
         sph[f] = make_float4(mx_, my_, mz_, sqrtf(r2) * 1.0001f + 1e-6f);
     }
     __syncthreads();
-    // ---- 3. ray parity of every touched row (warp per row, lanes over faces)
-    for (int row = warp; row < G * G; row += PNT / 32) {
-        const unsigned need = needed[row];
-        if (!need) continue;
-        const float py = voxel_centre(row % G), pz = voxel_centre(row / G);
-        unsigned parity = 0u;
-        for (int f = lane; f < Fg; f += 32) {
-            const float4 sp = sph[f];
-            if (fabsf(py - sp.y) > sp.w || fabsf(pz - sp.z) > sp.w) continue;  // the ray misses the face's sphere
-            const int i0 = __ldg(faces + 3 * f), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
-            float xs;
-            if (ray_x_cross(py, pz, lv + 3 * i0, lv + 3 * i1, lv + 3 * i2, xs)) parity ^= row_mask_below(xs);
-        }
-        parity = __reduce_xor_sync(0xffffffffu, parity);
-        if (lane == 0) inside[row] = parity & need;
+    // ---- 3. ray parity of every touched row. A +x ray from the row (y, z) can only pierce faces whose y-z bounding
+    //         box contains the row, so the loop runs over faces (thread per face) and the few rows of their boxes, and
+    //         the crossings are folded into the row's parity word with atomicXor (order-independent): ~10 (face, row)
+    //         tests per face instead of one sphere test per (touched row, face). The box carries 1e-4 of slack in the
+    //         cube's units (the piercing test itself is the oracle's, rounding ~1e-7).
+    for (int f = tid; f < Fg; f += PNT) {
+        const float *a = lv + 3 * __ldg(faces + 3 * f), *bq = lv + 3 * __ldg(faces + 3 * f + 1),
+                    *c = lv + 3 * __ldg(faces + 3 * f + 2);
+        const float ymin = fminf(fminf(a[1], bq[1]), c[1]) - 1e-4f, ymax = fmaxf(fmaxf(a[1], bq[1]), c[1]) + 1e-4f;
+        const float zmin = fminf(fminf(a[2], bq[2]), c[2]) - 1e-4f, zmax = fmaxf(fmaxf(a[2], bq[2]), c[2]) + 1e-4f;
+        // voxel_centre(j) = -1 + (j + 0.5) / 16 in [ymin, ymax]  (clamped before the int conversion)
+        const int j0 = __float2int_rz(fminf(fmaxf(ceilf((ymin + 1.f) * (0.5f * G) - 0.5f), 0.f), (float)G));
+        const int j1 = __float2int_rz(fminf(fmaxf(floorf((ymax + 1.f) * (0.5f * G) - 0.5f), -1.f), (float)(G - 1)));
+        const int k0 = __float2int_rz(fminf(fmaxf(ceilf((zmin + 1.f) * (0.5f * G) - 0.5f), 0.f), (float)G));
+        const int k1 = __float2int_rz(fminf(fmaxf(floorf((zmax + 1.f) * (0.5f * G) - 0.5f), -1.f), (float)(G - 1)));
+        for (int k = k0; k <= k1; ++k)
+            for (int j = j0; j <= j1; ++j) {
+                if (!needed[k * G + j]) continue;
+                float xs;
+                if (ray_x_cross(voxel_centre(j), voxel_centre(k), a, bq, c, xs)) atomicXor(&inside[k * G + j], row_mask_below(xs));
+            }
     }
+    __syncthreads();
+    for (int i = tid; i < G * G; i += PNT) inside[i] &= needed[i];
     __syncthreads();
     // ---- 4. distance of the touched inside voxels: compact them (deterministic prefix sum over the rows),
     //         then one warp per voxel, lanes over faces
@@ -237,28 +246,70 @@ sdf_pair_kernel(const float *__restrict__ verts_g, const int32_t *__restrict__ f
         }
         __syncthreads();
         const int nv = min(total - base, VLIST);
-        for (int i = warp; i < nv; i += PNT / 32) {
+        // a warp takes a contiguous stretch of the list (neighbouring voxels): only its first voxel needs the pass
+        // over all bounding spheres for an upper bound of its distance - afterwards the previous voxel's distance plus
+        // the step between the two centres is one (triangle inequality), and usually a tighter one
+        const int per = (nv + PNT / 32 - 1) / (PNT / 32);
+        float prev_d = -1.f, pp[3] = {0.f, 0.f, 0.f};
+        for (int i = warp * per; i < min(nv, (warp + 1) * per); ++i) {
             const int vox = vlist[i];
             const int row = vox / G, ix = vox % G;
             const float p[3] = {voxel_centre(ix), voxel_centre(row % G), voxel_centre(row / G)};
-            // upper bound of the distance from the spheres, then exact tests only where the lower bound allows
-            float ub = INFINITY;
-            for (int f = lane; f < Fg; f += 32) {
-                const float4 sp = sph[f];
-                const float dx = p[0] - sp.x, dy = p[1] - sp.y, dz = p[2] - sp.z;
-                ub = fminf(ub, sqrtf(dx * dx + dy * dy + dz * dz) + sp.w);
+            float ub;
+            if (prev_d >= 0.f) {
+                const float sx = p[0] - pp[0], sy = p[1] - pp[1], sz = p[2] - pp[2];
+                ub = prev_d + sqrtf(sx * sx + sy * sy + sz * sz);
+            } else {
+                ub = INFINITY;
+                for (int f = lane; f < Fg; f += 32) {
+                    const float4 sp = sph[f];
+                    const float dx = p[0] - sp.x, dy = p[1] - sp.y, dz = p[2] - sp.z;
+                    ub = fminf(ub, sqrtf(dx * dx + dy * dy + dz * dz) + sp.w);
+                }
+                ub = warp_min(ub);
             }
-            ub = warp_min(ub) * 1.0001f + 1e-6f;
+            ub = ub * 1.0001f + 1e-6f;
+            // faces whose sphere reaches inside the bound are queued per warp and evaluated 32 at a time: the exact
+            // point-triangle distance is ~150 divergent instructions and only a few lanes of every 32 spheres pass
             float best = INFINITY;
-            for (int f = lane; f < Fg; f += 32) {
-                const float4 sp = sph[f];
-                const float dx = p[0] - sp.x, dy = p[1] - sp.y, dz = p[2] - sp.z;
-                if (sqrtf(dx * dx + dy * dy + dz * dz) - sp.w > ub) continue;
-                const int i0 = __ldg(faces + 3 * f), i1 = __ldg(faces + 3 * f + 1), i2 = __ldg(faces + 3 * f + 2);
+            int qn = 0;
+            unsigned short *q = wq[warp];
+            for (int f0 = 0; f0 < Fg; f0 += 32) {
+                const int f = f0 + lane;
+                bool cand = false;
+                if (f < Fg) {
+                    const float4 sp = sph[f];
+                    const float dx = p[0] - sp.x, dy = p[1] - sp.y, dz = p[2] - sp.z, t = ub + sp.w;
+                    cand = !(dx * dx + dy * dy + dz * dz > t * t);
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, cand);
+                if (m == 0u) continue;
+                if (cand) q[qn + __popc(m & ((1u << lane) - 1u))] = (unsigned short)f;
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32) {
+                    const int fq = q[lane];
+                    const int i0 = __ldg(faces + 3 * fq), i1 = __ldg(faces + 3 * fq + 1), i2 = __ldg(faces + 3 * fq + 2);
+                    best = fminf(best, point_tri_dist2(p, lv + 3 * i0, lv + 3 * i1, lv + 3 * i2));
+                    const int rest = qn - 32;
+                    const int mv = lane < rest ? q[32 + lane] : 0;
+                    __syncwarp();
+                    if (lane < rest) q[lane] = (unsigned short)mv;
+                    qn = rest;
+                    __syncwarp();
+                }
+            }
+            if (lane < qn) {
+                const int fq = q[lane];
+                const int i0 = __ldg(faces + 3 * fq), i1 = __ldg(faces + 3 * fq + 1), i2 = __ldg(faces + 3 * fq + 2);
                 best = fminf(best, point_tri_dist2(p, lv + 3 * i0, lv + 3 * i1, lv + 3 * i2));
             }
+            __syncwarp();
             best = warp_min(best);
-            if (lane == 0) phi[vox] = sqrtf(best);
+            const float d = sqrtf(best);
+            if (lane == 0) phi[vox] = d;
+            prev_d = d < INFINITY ? d : -1.f;   // (an empty mesh or non-finite vertices: keep using the sphere pass)
+            pp[0] = p[0]; pp[1] = p[1]; pp[2] = p[2];
         }
         __syncthreads();
     }
