@@ -34,7 +34,7 @@ struct __align__(16) FaceRec {
     float iz[3];   // 1 / z of the three corners (fast depth of the forward pass)
     int exact;     // 1: some corner depth is not a plain positive float -> forward uses the reference arithmetic only
     short fb[4];   // forward box x0 y0 x1 y1: the rows / columns the forward visits (tight; = bb for slivers, see the setup)
-    float pad2;
+    float pad2;    // min corner depth
 };
 static_assert(sizeof(FaceRec) == 128, "record size");
 
@@ -212,7 +212,7 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
             r.iz[k] = 1.f / z;
             if (!(z > 1e-20f && z < 1e20f)) r.exact = 1;
         }
-        r.pad2 = 0.f;
+        r.pad2 = fminf(fminf(r.c[2], r.c[5]), r.c[8]);   // nearest corner (hidden-layer test of the forward)
         // Forward box: a sample a whole pixel outside the bounding box of the corners cannot pass the three edge
         // predicates unless the triangle is a needle (the margin of the test is the sample's distance to the edge
         // lines, ~sin(apex angle) pixels, against ~1e-5 of rounding): faces with |det| >= 1e-3 |longest edge|^2 get the
@@ -379,6 +379,9 @@ __device__ __forceinline__ int batch_face(const int *list, int n0, int li) {
 constexpr unsigned AMB = 48;   // ulp; the two evaluation orders differ by < 8 ulp each
 constexpr int HZ = 4;          // hierarchical-z block edge (pixels)
 constexpr int HZN = TILE / HZ;
+#ifndef HM_FWD_FILTER_MIN
+#define HM_FWD_FILTER_MIN 32   // hidden-layer entries of a tile from which the thread-per-entry filter pays
+#endif
 constexpr int AMBCAP = NWARPS * 64;
 
 __device__ __forceinline__ bool ulp_close(unsigned a, unsigned b) {
@@ -520,6 +523,7 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
         // two passes: faces kept in their original winding (the outer layer of an outward-wound closed mesh)
         // first, the reversed copies second. Between them the winners are summarised per 4x4 block, so that a
         // hidden-layer face is dropped with one comparison per block instead of one per sample.
+        bool filtered = false;
         for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1) {
             __syncthreads();
@@ -532,6 +536,41 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 m = max(m, __shfl_xor_sync(0xffffffffu, m, 2));
                 if ((lane & 3) == 0) atomicMax(&hiz[k * HZN + (threadIdx.x % TILE) / HZ], m);
             }
+            if (threadIdx.x == 0) n_amb = 0;   // (free until the passes end: counts the entries that survive)
+            __syncthreads();
+            // hidden-layer faces, thread per list entry: the interpolated depth is a convex combination of the corner
+            // depths, so a face whose nearest corner (minus rounding slack) is behind the winner of every pixel of the
+            // 4x4 blocks its box touches cannot win a pixel - dropped from the list here (one 16-byte load and a few
+            // shared-memory reads per face) instead of by a whole warp in the face loop
+            const int n1 = cnt[1];
+            filtered = n1 >= HM_FWD_FILTER_MIN;   // (short lists: the barriers cost more than the warps' own test)
+            for (int r0 = 0; filtered && r0 < n1; r0 += NTHREADS) {
+                const int jj = r0 + threadIdx.x;
+                int fce = -1;
+                bool keep = false;
+                if (jj < n1) {
+                    fce = list[LISTCAP - 1 - jj];
+                    const int4 q7 = __ldg(reinterpret_cast<const int4 *>(recs + fce) + 7);
+                    const int X0 = max((int)(short)(q7.y & 0xffff), tx0), X1 = min((int)(short)(q7.z & 0xffff), tx0 + TILE - 1);
+                    const int Y0 = max((int)(short)(q7.y >> 16), ty0), Y1 = min((int)(short)(q7.z >> 16), ty0 + TILE - 1);
+                    if (X0 <= X1 && Y0 <= Y1) {
+                        const float zmin = __int_as_float(q7.w);
+                        const unsigned zmin_bits = zmin > 0.f ? __float_as_uint(zmin * (1.f - 1e-5f)) : 0u;
+                        const int hx0 = (X0 - tx0) / HZ, hx1 = (X1 - tx0) / HZ, hy1 = (Y1 - ty0) / HZ;
+                        for (int hy = (Y0 - ty0) / HZ; hy <= hy1 && !keep; ++hy)
+                            for (int hx = hx0; hx <= hx1; ++hx)
+                                if (!(zmin_bits > hiz[hy * HZN + hx])) { keep = true; break; }
+                    }
+                }
+                __syncthreads();   // every entry of this round is read before the survivors are written over them
+                const unsigned km = __ballot_sync(0xffffffffu, keep);
+                int at = 0;
+                if (lane == 0 && km) at = atomicAdd(&n_amb, __popc(km));
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (keep) list[LISTCAP - 1 - (at + __popc(km & ((1u << lane) - 1u)))] = fce;
+                __syncthreads();
+            }
+            if (filtered && threadIdx.x == 0) cnt[1] = n_amb;
             __syncthreads();
         }
         const int np = cnt[pass];
@@ -586,7 +625,7 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
             // nearest corner (minus rounding slack) is behind the current winner of a pixel cannot win it
             const float zmin = fminf(fminf(f2, f5), f8);
             const unsigned zmin_bits = zmin > 0.f ? __float_as_uint(zmin * (1.f - 1e-5f)) : 0u;
-            if (pass == 1) {
+            if (pass == 1 && !filtered) {
                 const int hx0 = (X0 - tx0) / HZ, hx1 = (X1 - tx0) / HZ, hy0 = (Y0 - ty0) / HZ, hy1 = (Y1 - ty0) / HZ;
                 const int hx = hx0 + (lane & (HZN - 1));  // lanes: 16 block columns x 2 block rows
                 bool vis = false;
@@ -636,6 +675,9 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                 inv[8] = i2.x; iz0 = i2.y; iz1 = i2.z; iz2 = i2.w;
             }
             const int exact_face = q7.x;
+            // a sample's depth lies between the corner depths (plus rounding): a face whose corners are clear of the
+            // near / far planes needs no closeness test against them per sample
+            const bool planes = exact_face || !(zmin > near_ * 1.0001f && fmaxf(fmaxf(f2, f5), f8) < far_ * 0.9999f);
             const short *gx = rowx, *gpre = rowpre;
             int row = 0, rend = 0, xoff = 0;   // current row, first pixel index of the next non-visited row, x - i of the row
             for (int i = lane; i < n_px; i += 32) {
@@ -671,7 +713,7 @@ raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ 
                     zp = __fdividef(w0 + w1 + w2, w0 * iz0 + w1 * iz1 + w2 * iz2);
                 }
                 const unsigned zb = __float_as_uint(zp);
-                bool flag = ulp_close(zb, near_bits) || ulp_close(zb, far_bits);
+                bool flag = planes && (ulp_close(zb, near_bits) || ulp_close(zb, far_bits));
                 if (zp > near_ && zp < far_) {  // also rejects NaN
                     const unsigned long long key = ((unsigned long long)zb << 32) | (unsigned)fn;
                     unsigned long long seen = cur;
@@ -1207,6 +1249,9 @@ __device__ __forceinline__ SweepSrc sweep_src(int b, int is, int aa, float eps, 
 #endif
 constexpr int B2_SEG = HM_BWD_SEG;       // scan-lines per segment (a multiple of 4, <= 8)
 constexpr int B2_CAP = 2048;            // list entries per slice
+#ifndef HM_BWD_SMALL_MESH
+#define HM_BWD_SMALL_MESH 768            // meshes up to this many faces take half-size rounds
+#endif
 
 __device__ __noinline__ void sweep_walk(const SweepSrc &S, int ls, int d0, int ra, int rc, float x, float K0, float K1,
                                         unsigned flags, float &a0, float &a1) {
@@ -1286,7 +1331,7 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ 
                    const uint32_t *__restrict__ face_vis, const unsigned char *__restrict__ cov_blocks,
                    const uint32_t *__restrict__ m_row, const uint32_t *__restrict__ m_col,
                    const uint2 *__restrict__ runs, const uint32_t *__restrict__ run_info, float *__restrict__ grad_ndc,
-                   unsigned long long *__restrict__ grad_fixed) {
+                   unsigned long long *__restrict__ grad_fixed, int fpr) {
     __shared__ uint32_t list[B2_CAP];
     __shared__ int wsum[NWARPS];
     __shared__ SweepSrc S;
@@ -1308,11 +1353,13 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ 
     face_vis += (long)b * HM_FACE_VIS_WORDS(F);
     cov_blocks += (long)b * (is / 8) * W;
     if (threadIdx.x == 0) S = sweep_src(b, is, aa, eps, grad_alpha, m_row, m_col, runs, run_info);
-    const int n_rounds = (F + NTHREADS - 1) / NTHREADS;
+    // fpr = faces per round (<= NTHREADS, thread per face in phase 1): small meshes take rounds of 128 faces so that
+    // the launch has enough CTAs for even waves (500 faces x 480 images: 960 CTAs of 256 faces = 1.6 waves)
+    const int n_rounds = (F + fpr - 1) / fpr;
     for (int round = blockIdx.x; round < n_rounds; round += gridDim.x) {
         // ---- (1) thread per face: is it visible (owns a pixel: out-sweeps), can it have in-sweeps (an uncovered pixel
         //      in the 8x8 blocks its pixel bounding box touches, or irregular), how many segments do its tasks have
-        const int f = round * NTHREADS + threadIdx.x;
+        const int f = (int)threadIdx.x < fpr ? round * fpr + (int)threadIdx.x : F;
         unsigned ns = 0, ns_hi = 0;   // segments per task, 8 bits each
         int n_f = 0;
         unsigned fflags = 0;          // 1: boundary, 2: first copy visible, 4: there is a second copy, 8: second copy visible
@@ -1416,7 +1463,7 @@ raster_bwd_kernel(const BwdRec *__restrict__ brecs, const FaceBox *__restrict__ 
                 const unsigned ent = valid ? list[j] : 0u;
                 const int t = (ent >> 8) & 7, e = t >> 1, axis = t & 1, k = ent >> 14;
                 const bool bnd = (ent >> 12) & 1u, vis = (ent >> 13) & 1u;
-                BwdFace bf = load_bwd_face(brecs + (valid ? round * NTHREADS + (int)(ent & 0xffu) : 0));
+                BwdFace bf = load_bwd_face(brecs + (valid ? round * fpr + (int)(ent & 0xffu) : 0));
                 if ((ent >> 11) & 1u) reverse_bwd_face(bf, F);
                 const TaskGeom g = task_geom(bf, e, axis, is);
                 const int d0a = g.d0_from + k * B2_SEG;
@@ -2011,10 +2058,12 @@ int hm_raster_sil_bwd(const void *records, const void *bboxes, const int32_t *fa
     HM_REQUIRE(V > 0, "hm_raster_sil_bwd: bad sizes");
     HM_UNSUPPORTED(is > 1024, "hm_raster_sil_bwd: raster size %d > 1024 is not supported", is);
     const BwdRec *brecs = reinterpret_cast<const BwdRec *>(static_cast<const FaceRec *>(records) + (long)B * F);
-    const int n_rounds = (F + NTHREADS - 1) / NTHREADS;
+    const int fpr = F <= HM_BWD_SMALL_MESH ? NTHREADS / 2 : NTHREADS;   // faces per CTA round (see the kernel)
+    const int n_rounds = (F + fpr - 1) / fpr;
     raster_bwd_kernel<<<dim3(min(n_rounds, 8), B), NTHREADS, 0, hm_stream(stream)>>>(
         brecs, static_cast<const FaceBox *>(bboxes), F, V, is, anti_aliasing, eps, face_index, grad_alpha, cov_row,
-        cov_col, face_vis, cov_blocks, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc, grad_fixed);
+        cov_col, face_vis, cov_blocks, m_row, m_col, static_cast<const uint2 *>(runs), run_counts, grad_ndc, grad_fixed,
+        fpr);
     HM_CHECK_LAUNCH("hm_raster_sil_bwd");
     return HM_OK;
 }

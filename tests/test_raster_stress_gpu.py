@@ -206,3 +206,37 @@ def test_closed_mesh_across_the_image_border():
     assert ((px > -1) & (px < 0)).any()   # the case is present
     _check(ndc, of, 128, True)
     _check(ndc[:2], of, 256, False)
+
+
+@pytest.mark.parametrize("aa", [True, False])
+def test_needles_and_the_tight_forward_box(aa):
+    """The forward visits only the rows / columns of floor(min) .. ceil(max) of a face's corners unless the face is a
+    needle (|det| < 1e-3 |longest edge|^2, raster.cu face_setup_kernel), for which it keeps the reference's box with a
+    pixel of slack. Needles of every aspect ratio around that threshold, at random orientations, with tips and edges
+    landing between, on and next to pixel centres, over a backdrop so that depth ranking runs too."""
+    rng = np.random.default_rng(17)
+    tris, n = [], 0
+    for aspect in (3.0, 30.0, 300.0, 1e3, 3e3, 1e4, 1e5, 1e6, 1e7):
+        for _ in range(40):
+            c = rng.uniform(-0.8, 0.8, size=2)
+            th = rng.uniform(0, 2 * np.pi)
+            L = rng.uniform(0.05, 0.9)
+            d = np.array([np.cos(th), np.sin(th)])
+            nrm = np.array([-d[1], d[0]])
+            a = c - 0.5 * L * d
+            b = c + 0.5 * L * d + rng.uniform(-1, 1) * (L / aspect) * nrm
+            tip = c + rng.uniform(-0.5, 0.5) * L * d + (L / aspect) * nrm
+            z = rng.uniform(0.5, 1.5, size=(3, 1))
+            tris.append(np.concatenate((np.stack((a, b, tip)), z), 1))
+            n += 1
+    # snap some corners onto pixel centres / integer pixel coordinates of the raster
+    S = 256 if aa else 128
+    t = np.stack(tris)
+    snap = rng.random(t.shape[:2]) < 0.2
+    px = np.round(0.5 * (t[..., :2] * S + S - 1))
+    t[..., :2] = np.where(snap[..., None], (2 * px + 1 - S) / S, t[..., :2])
+    backdrop = np.array([[[-0.9, -0.9, 2.0], [0.9, -0.9, 2.0], [0.0, 0.9, 2.0]]])
+    verts = np.concatenate((t, backdrop)).reshape(-1, 3).astype(np.float32)
+    faces = np.arange(verts.shape[0]).reshape(-1, 3)
+    ndc = np.stack((verts, verts * np.array([-1, 1, 1], np.float32)))
+    _check(ndc, faces, 128, aa)
