@@ -11,6 +11,8 @@ All state lives in caller-visible torch CUDA tensors; kernels are reached throug
 Scope: one hand per frame, hand_proj_mode="persp", optimize_mano=True, optimize_mano_beta=True,
 optimize_object_scale=False (the README configuration of the reference, README.md:207-238).
 """
+import os
+
 import numpy as np
 import torch
 
@@ -299,7 +301,10 @@ class FitEngine:
         main = torch.cuda.current_stream()
         fork = self.overlap_streams and torch.cuda.is_current_stream_capturing()
         if fork and self._side_streams is None:
-            self._side_streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+            # the hand chain ends in the MANO backward, a launch that leaves most of the GPU idle: it gets the higher
+            # priority so that it finishes first and that tail runs under the object chain's last kernels
+            hp = int(os.environ.get("HOMAN_B200_HAND_PRIORITY", "-1"))
+            self._side_streams = [torch.cuda.Stream(), torch.cuda.Stream(priority=hp)]
         if fork and self.on_sil_obj and self.on_sil_hand:
             # each chain starts from its own vertices: object placement on the first side stream, MANO on the second
             sa, sb = self._side_streams
@@ -375,20 +380,43 @@ class FitEngine:
                  self.faces_obj.shape[1], 778, SDF_GRID, SDF_SCALE_FACTOR, lw["lw_collision"], ptr(self.phi_scratch),
                  ptr(self.partials), ptr(self.g_verts_hand), None, s)
             n += 2
-        if fork:
-            for side, _ in zip(self._side_streams, chains):
-                main.wait_stream(side)
-        for c in chains:
-            n += self._silhouette_finish(c[0], c[1], c[8], c[9], s)
         g = self.grads
+        obj_tail = None   # side stream that carries the object's projection / placement backward, if any
+        if fork and os.environ.get("HOMAN_B200_TAIL_OVERLAP", "1") != "0":
+            # join per chain: the object's tail (projection backward -> rigid backward) stays on its side stream behind
+            # the vertex-space terms of the main stream, the hand's tail (projection backward -> MANO backward) runs on
+            # the main stream as soon as the hand chain is done; they meet again before the loss reduction
+            ev_terms = torch.cuda.Event()
+            ev_terms.record(main)
+            for side, c in zip(self._side_streams, chains):
+                if c[10] == "sil_obj":
+                    side.wait_event(ev_terms)
+                    with torch.cuda.stream(side):
+                        n += self._silhouette_finish(c[0], c[1], c[8], c[9], current_stream())
+                        call("hm_rigid_bwd", ptr(self.mesh_obj), self.mesh_obj.shape[0], ptr(self.params["rotations_object"]),
+                             ptr(self.scale_obj), B, self.Vo, ptr(self.g_verts_obj), ptr(g["rotations_object"]),
+                             ptr(g["translations_object"]), current_stream())
+                    obj_tail = side
+                else:
+                    main.wait_stream(side)
+                    n += self._silhouette_finish(c[0], c[1], c[8], c[9], s)
+        else:
+            if fork:
+                for side, _ in zip(self._side_streams, chains):
+                    main.wait_stream(side)
+            for c in chains:
+                n += self._silhouette_finish(c[0], c[1], c[8], c[9], s)
         call("hm_mano_bwd", ptr(self.mano), self.ncomps, self.side_left, ptr(self.params["mano_pca_pose"]),
              self.pca_dim, ptr(self.params["mano_rot"]), ptr(self.params["mano_betas"]),
              ptr(self.params["mano_trans"]), ptr(self.params["rotations_hand"]), ptr(self.params["translations_hand"]),
              ptr(self.scale_hand), B, ptr(self.vposed), ptr(self.g_verts_hand), ptr(self.g_cdet) if self.on_inter else None,
              ptr(g["mano_pca_pose"]), ptr(g["mano_rot"]), ptr(g["mano_betas"]), ptr(g["mano_trans"]),
              ptr(g["rotations_hand"]), ptr(g["translations_hand"]), s)
-        call("hm_rigid_bwd", ptr(self.mesh_obj), self.mesh_obj.shape[0], ptr(self.params["rotations_object"]), ptr(self.scale_obj), B,
-             self.Vo, ptr(self.g_verts_obj), ptr(g["rotations_object"]), ptr(g["translations_object"]), s)
+        if obj_tail is None:
+            call("hm_rigid_bwd", ptr(self.mesh_obj), self.mesh_obj.shape[0], ptr(self.params["rotations_object"]), ptr(self.scale_obj), B,
+                 self.Vo, ptr(self.g_verts_obj), ptr(g["rotations_object"]), ptr(g["translations_object"]), s)
+        else:
+            main.wait_stream(obj_tail)
         call("hm_finalize_losses", ptr(self.partials), ptr(self.weights_part), self.P, T, ptr(self.losses),
              ptr(self.total), ptr(self.step_counter) if adam else None, s)   # forward-only: Adam's step count untouched
         n += 3
@@ -416,7 +444,8 @@ class FitEngine:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        mp = int(os.environ.get("HOMAN_B200_MAIN_PRIORITY", "-1"))
+        with torch.cuda.graph(graph, stream=torch.cuda.Stream(priority=mp)):
             self._iteration()
         for dst, src in zip((self.flat, self.exp_avg, self.exp_avg_sq, self.step_counter), saved):
             dst.copy_(src)

@@ -10,6 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 ncu --set full --clock-control none --import-source on -k regex:'raster_bwd|raster_fwd|sdf_pair|mano_bwd|sil_loss_prep' -s 16 -c 9 -f \
     -o gpurun_out/prof_final python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_final.log 2>&1
 python scripts/bench_raster_vs_nmr_style.py > gpurun_out/raster_vs_nmr_style.json 2> gpurun_out/raster_vs_nmr_style.err
+python scripts/bench_iteration_vs_nmr_style.py --iters 5 --out gpurun_out/iteration_vs_nmr_style.json > /dev/null 2> gpurun_out/iteration_vs_nmr_style.err
 python scripts/bench_pose_init.py --out gpurun_out/pose_init.json > /dev/null 2> gpurun_out/pose_init.err
 python bench.py --workload cfg5 --steps 20 --no-cpu-baseline > gpurun_out/bench_cfg5_n1.json 2> gpurun_out/bench_cfg5_n1.err
 python bench.py --workload cfg2 --steps 50 --no-cpu-baseline > gpurun_out/bench_cfg2_n1.json 2> gpurun_out/bench_cfg2_n1.err
