@@ -287,9 +287,15 @@ __global__ void face_setup_kernel(const float *__restrict__ ndc, const int32_t *
     }
 }
 
-constexpr int LISTCAP = 2048;  // faces of one tile processed per batch
+// 1600 entries (with the 32 KB z-buffer: 44.4 KB per CTA) and 48 registers let five CTAs share an SM (40 warps; the
+// kernel is latency-bound): 5 x (44.4 + 1) KB is just inside the 227 KB an SM gives its CTAs.
+#ifndef HM_FWD_LISTCAP
+#define HM_FWD_LISTCAP 1600
+#endif
+constexpr int LISTCAP = HM_FWD_LISTCAP;  // faces of one tile processed per batch
 
 constexpr int SCAN = 4 * NTHREADS;  // faces tested per scan step (four 8-byte boxes per thread)
+static_assert(LISTCAP >= SCAN, "a batch must hold one scan step (the scan continues while n <= LISTCAP - SCAN)");
 
 // Appends the faces of [base, base + SCAN) whose bbox touches the tile: faces stored in their original winding (first
 // pass of the forward) from the front of the list, reversed copies (second pass) from its back; cnt[0], cnt[1] count
@@ -465,7 +471,10 @@ __device__ __forceinline__ void write_untouched_tile(int b, int tx0, int ty0, in
     }
 }
 
-__global__ void __launch_bounds__(NTHREADS, 4)
+#ifndef HM_FWD_MINB
+#define HM_FWD_MINB 5
+#endif
+__global__ void __launch_bounds__(NTHREADS, HM_FWD_MINB)
 raster_fwd_kernel(const FaceRec *__restrict__ recs, const FaceBox *__restrict__ boxes, int F, int is, int aa,
                   float near_, float far_, int32_t *__restrict__ face_index, float *__restrict__ alpha,
                   uint32_t *__restrict__ cov_row, uint32_t *__restrict__ cov_col, uint32_t *__restrict__ face_vis,
