@@ -115,6 +115,9 @@ def cpu_reference_iteration_rate(workload, steps, warmup, batch, lw, asset):
     return float(np.mean(times))
 
 
+_LINE = []   # the JSON line of this process (rank 0), printed by main() once stdout is restored
+
+
 def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
@@ -152,7 +155,7 @@ def run_reference(args):
                                    f"time x {P} = one whole-batch iteration; oracle/homan_ref.py (torch CPU + OpenMP C)"},
         "e2e": {"value": value, "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _LINE.append(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
@@ -326,7 +329,7 @@ def run_ours(args):
         "gpu_launches": eng.gpu_launches_per_step * args.steps,
         "roofline": roofline, "cpu_baseline": cpu, "breakdown_us": bd,
     }
-    print(json.dumps(line), flush=True)
+    _LINE.append(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -343,10 +346,22 @@ def main():
                     help="triangulation of the synthetic hand: well-shaped faces (default) or the round-1 polar slivers")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # The contract is ONE JSON line on stdout: whatever libraries write to file descriptor 1 while the job runs (NCCL
+    # prints its version banner there when NCCL_DEBUG is set) goes to stderr instead; the line itself is printed last.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if _LINE:
+        print(_LINE[0], flush=True)
 
 
 if __name__ == "__main__":
