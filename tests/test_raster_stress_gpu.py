@@ -240,3 +240,31 @@ def test_needles_and_the_tight_forward_box(aa):
     faces = np.arange(verts.shape[0]).reshape(-1, 3)
     ndc = np.stack((verts, verts * np.array([-1, 1, 1], np.float32)))
     _check(ndc, faces, 128, aa)
+
+
+@pytest.mark.parametrize("aa", [True, False])
+def test_dense_soup_of_small_and_large_faces(aa):
+    """A soup of 5000 triangles of mixed sizes - mostly a few pixels, some spanning tiles -, interleaved in the tile
+    lists, with exact duplicates and near-duplicates (depth ties), vertices snapped onto pixel centres, faces crossing
+    the near plane and the image border: several batches per tile list, long hidden-layer lists (thread-per-entry
+    filter), the lean path of untouched tiles next to crowded ones."""
+    rng = np.random.default_rng(23)
+    small_v, _ = _soup(rng, 4200, 0.02)
+    mid_v, _ = _soup(rng, 600, 0.08)
+    big_v, _ = _soup(rng, 40, 0.6)
+    t = np.concatenate((small_v, mid_v, big_v)).reshape(-1, 3, 3)
+    rng.shuffle(t)   # small and large faces interleaved in the tile lists
+    t[:50, :, 2] = rng.uniform(0.05, 0.15, size=(50, 3))          # across the near plane (0.1)
+    t[50:120, :, :2] += np.sign(t[50:120, :1, :2]) * 0.35          # across the image border
+    S = 256 if aa else 128
+    snap = rng.random(t.shape[:2]) < 0.1
+    px = np.round(0.5 * (t[..., :2] * S + S - 1))
+    t[..., :2] = np.where(snap[..., None], (2 * px + 1 - S) / S, t[..., :2])
+    dup = t[200:400].copy()
+    near = t[400:600].copy()
+    near[:, :, 2] *= np.float32(1 + 3e-7)
+    verts = np.concatenate((t, dup, near)).reshape(-1, 3).astype(np.float32)
+    faces = np.arange(verts.shape[0]).reshape(-1, 3)
+    assert faces.shape[0] >= 4096
+    ndc = np.stack((verts, verts * np.array([1, -1, 1], np.float32)))
+    _check(ndc, faces, 128, aa)
