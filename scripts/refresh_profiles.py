@@ -21,7 +21,8 @@ COPY = {"bench_cfg3_n1.json": "bench_cfg3_n1.json", "bench_cfg2_n1.json": "bench
         "bench_cfg3_polar.json": "bench_cfg3_polar_hand.json", "bench_reference.json": "bench_reference_cfg3.json",
         "ncu_launches.csv": "ncu_launches.csv", "raster_vs_nmr_style.json": "raster_vs_nmr_style.json",
         "iteration_vs_nmr_style.json": "iteration_vs_nmr_style.json", "pose_init.json": "pose_init.json",
-        "bench_cfg3_n2.json": "bench_cfg3_n2.json", "bench_cfg4_n2.json": "bench_cfg4_n2.json"}
+        "bench_cfg3_n2.json": "bench_cfg3_n2.json", "bench_cfg4_n2.json": "bench_cfg4_n2.json",
+        "bench_cfg3_n8.json": "bench_cfg3_n8.json", "bench_cfg4_n8.json": "bench_cfg4_n8.json"}
 for src, dst in COPY.items():
     if os.path.exists(os.path.join(G, src)) and os.path.getsize(os.path.join(G, src)) > 0:
         shutil.copy(os.path.join(G, src), os.path.join(P, f"{rp}_{dst}"))
