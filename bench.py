@@ -349,15 +349,17 @@ def main():
     # The contract is ONE JSON line on stdout: whatever libraries write to file descriptor 1 while the job runs (NCCL
     # prints its version banner there when NCCL_DEBUG is set) goes to stderr instead; the line itself is printed last.
     sys.stdout.flush()
-    real_stdout = os.dup(1)
+    real_stdout, py_stdout = os.dup(1), sys.stdout
     os.dup2(2, 1)
+    sys.stdout = sys.stderr
     try:
         if args.impl == "reference":
             run_reference(args)
         else:
             run_ours(args)
     finally:
-        sys.stdout.flush()
+        sys.stderr.flush()
+        sys.stdout = py_stdout
         os.dup2(real_stdout, 1)
         os.close(real_stdout)
     if _LINE:

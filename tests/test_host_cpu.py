@@ -99,3 +99,27 @@ def test_no_cpu_fallback_eval_metrics():
     with pytest.raises(_lib.HomanB200Error):
         get_inter_metrics(torch.zeros(1, 778, 3), torch.zeros(1, 8, 3), torch.zeros(1, 12, 3, dtype=torch.int64),
                           torch.zeros(1, 12, 3, dtype=torch.int64))
+
+
+def test_bench_prints_exactly_one_json_line_on_stdout(monkeypatch, capfd):
+    """The driver parses bench.py's stdout as one JSON line: whatever a library writes to file descriptor 1 while the
+    job runs (NCCL prints its version banner there when NCCL_DEBUG is set) must end up on stderr."""
+    import importlib
+    import json
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    bench = importlib.import_module("bench")
+
+    def fake_run(args):
+        os.write(1, b"NCCL version 0.0.0+test\n")   # a native library writing to fd 1
+        print("a print from a helper")
+        bench._LINE.append(json.dumps({"metric": "m", "value": 1.0}))
+
+    monkeypatch.setattr(bench, "run_ours", fake_run)
+    monkeypatch.setattr(bench, "_LINE", [])
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--steps", "3"])
+    bench.main()
+    out, err = capfd.readouterr()
+    assert out.strip().splitlines() == ['{"metric": "m", "value": 1.0}']
+    assert "NCCL version" in err and "a print from a helper" in err
