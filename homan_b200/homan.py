@@ -148,6 +148,15 @@ class HOMan(nn.Module):
         tex = torch.cat((torch.tensor(COLORS["gold"], device=dev).expand(fo_.shape[0], 3),
                          torch.tensor(COLORS["grey"], device=dev).expand(fh_.shape[0], 3)))
         self.textures = tex.view(1, -1, 1, 1, 1, 3).repeat(B, 1, 1, 1, 1, 1)
+        # ground-truth overlays (homan/homan.py:200-217): the same topology in green / blue, and prediction + ground truth
+        # as one mesh of four parts
+        tex_gt = torch.cat((torch.tensor(COLORS["green"], device=dev).expand(fo_.shape[0], 3),
+                            torch.tensor(COLORS["blue"], device=dev).expand(fh_.shape[0], 3)))
+        self.textures_gt = tex_gt.view(1, -1, 1, 1, 1, 3).repeat(B, 1, 1, 1, 1, 1)
+        self.faces_gt = self.faces
+        nv = batch["obj_verts_can"].shape[0] + 778
+        self.faces_with_gt = torch.cat((self.faces, self.faces + nv), 1)
+        self.textures_with_gt = torch.cat((self.textures, self.textures_gt), 1)
 
     # ------------------------------------------------------------------ engine plumbing
     def _build_engine(self, loss_weights):
@@ -202,6 +211,82 @@ class HOMan(nn.Module):
             K = K.repeat(verts.shape[0] // K.shape[0], 1, 1) if verts.shape[0] % K.shape[0] == 0 else K[:1].expand(verts.shape[0], -1, -1)
             return self.render_limem(renderer, verts[:viz_len].contiguous(), self.faces[:viz_len], self.textures[:viz_len],
                                      K=K[:viz_len].contiguous(), max_in_batch=max_in_batch)
+
+    def _render_meshes(self, renderer, verts, faces, textures, rotate, viz_len, max_in_batch):
+        from .visualize import rot_points
+        renderer = self.renderer if renderer is None else renderer
+        with torch.no_grad():
+            verts = verts.float()
+            if rotate:
+                verts = rot_points(verts)
+            K = renderer.K.view(-1, 3, 3)
+            K = K.repeat(verts.shape[0] // K.shape[0], 1, 1) if verts.shape[0] % K.shape[0] == 0 else K[:1].expand(verts.shape[0], -1, -1)
+            return self.render_limem(renderer, verts[:viz_len].contiguous(), faces[:viz_len], textures[:viz_len],
+                                     K=K[:viz_len].contiguous(), max_in_batch=max_in_batch)
+
+    def _gt_hand(self, verts_hand_gt):
+        """The reference passes one [T,778,3] tensor per hand (a list / stacked [H,T,778,3]) or, for one hand, the tensor."""
+        v = verts_hand_gt
+        if isinstance(v, (list, tuple)):
+            if len(v) != 1:
+                raise NotImplementedError("homan_b200.HOMan: one hand per frame")
+            v = v[0]
+        v = torch.as_tensor(_np(v) if not torch.is_tensor(v) else v).to(self.engine.device).float()
+        if v.dim() == 4:
+            if v.shape[0] != 1:
+                raise NotImplementedError("homan_b200.HOMan: one hand per frame")
+            v = v[0]
+        return v
+
+    def render_gt(self, renderer=None, verts_hand_gt=None, verts_object_gt=None, rotate=False, viz_len=10,
+                  max_in_batch=None):
+        """homan/homan.py:564-581: the ground-truth object (green) and hand (blue) alone."""
+        vo = torch.as_tensor(_np(verts_object_gt) if not torch.is_tensor(verts_object_gt) else verts_object_gt)
+        verts = torch.cat((vo.to(self.engine.device).float(), self._gt_hand(verts_hand_gt)), 1)
+        return self._render_meshes(renderer, verts, self.faces_gt, self.textures_gt, rotate, viz_len, max_in_batch)
+
+    def render_with_gt(self, renderer=None, verts_hand_gt=None, verts_object_gt=None, rotate=False, viz_len=10, init=False,
+                       max_in_batch=None):
+        """homan/homan.py:583-613: the fit (or the initialisation, `init`) in gold / grey next to the ground truth in
+        green / blue, one render."""
+        with torch.no_grad():
+            if init:
+                vo_p, vh_p = self.verts_object_init, self.verts_hand_init
+            else:
+                vo_p, vh_p = self.get_verts_object()[0], self.get_verts_hand()[0]
+        vo = torch.as_tensor(_np(verts_object_gt) if not torch.is_tensor(verts_object_gt) else verts_object_gt)
+        n = min(vo.shape[0], vo_p.shape[0])   # (a model with several problems draws its first clip)
+        verts = torch.cat((vo_p[:n], vh_p[:n], vo.to(self.engine.device).float()[:n], self._gt_hand(verts_hand_gt)[:n]), 1)
+        return self._render_meshes(renderer, verts, self.faces_with_gt, self.textures_with_gt, rotate, viz_len, max_in_batch)
+
+    def get_joints_hand(self):
+        """homan/homan.py:309-339: the 21 hand joints (16 MANO joints + 5 finger tips, reordered) placed in the camera
+        frame like the vertices -> (joints [B,21,3], the same) - evaluation helper, not on the fitting path."""
+        from .pose_optimization import rot6d_to_matrix
+        eng, p = self.engine, self.engine.params
+        B = eng.B
+        with torch.no_grad():
+            verts = torch.empty(B, 778, 3, device=eng.device)
+            joints = torch.empty(B, 16, 3, device=eng.device)
+            _lib.call("hm_mano_fwd", _lib.ptr(eng.mano), eng.ncomps, eng.side_left, _lib.ptr(p["mano_pca_pose"]), eng.pca_dim,
+                      _lib.ptr(p["mano_rot"]), _lib.ptr(p["mano_betas"]), _lib.ptr(p["mano_trans"]), None, None, None, B,
+                      _lib.ptr(verts), _lib.ptr(joints), None, _lib.current_stream())
+            full = torch.cat((joints, verts[:, [745, 317, 444, 556, 673]]), 1)
+            full = full[:, [0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20]]
+            R = rot6d_to_matrix(p["rotations_hand"].reshape(B, 3, 2))
+            out = torch.matmul(eng.scale_hand.view(-1, 1, 1) * full, R) + p["translations_hand"].reshape(B, 1, 3)
+        return out, out.clone()
+
+    def save_obj(self, fname):
+        """homan/homan.py:615-626: the first frame's object + hand as a Wavefront .obj."""
+        with torch.no_grad():
+            verts = torch.cat((self.get_verts_object()[0][:1], self.get_verts_hand()[0][:1]), 1)[0].cpu().numpy()
+        faces = self.faces[0].cpu().numpy()
+        with open(fname, "w") as fp:
+            for v in verts:
+                fp.write(f"v {v[0]:f} {v[1]:f} {v[2]:f}\n")
+            for f in faces:
+                fp.write(f"f {f[0] + 1:d} {f[1] + 1:d} {f[2] + 1:d}\n")
 
     def forward(self, loss_weights=None):
         if loss_weights is None:

@@ -28,10 +28,18 @@ def rot_points(points, centers=None, axisang=(0, 1, 1)):
 def visualize_hand_object(model, images, verts_hand_gt=None, verts_object_gt=None, dist=3, viz_len=7, init=False,
                           gt_only=False, image_size=640, max_in_batch=2):
     """-> (frontal [N,H,W,3] uint8: the render composited over `images`, top_down [N,S,S,3] uint8: the rotated view).
-    Ground-truth overlays (`verts_*_gt`, `gt_only`) are not built."""
-    if verts_hand_gt is not None or gt_only:
-        raise NotImplementedError("homan_b200.visualize: ground-truth overlays are not built")
-    rends, masks = model.render(model.renderer, viz_len=viz_len, max_in_batch=max_in_batch)
+    With `verts_hand_gt` / `verts_object_gt` the ground truth is drawn next to the fit (green / blue), `gt_only` draws it
+    alone, `init` draws the initialisation instead of the current fit (homan/visualize.py:54-76,108-128)."""
+    def draw(rotate):
+        if gt_only:
+            return model.render_gt(model.renderer, verts_hand_gt=verts_hand_gt, verts_object_gt=verts_object_gt,
+                                   rotate=rotate, viz_len=viz_len, max_in_batch=max_in_batch)
+        if verts_hand_gt is None:
+            return model.render(model.renderer, rotate=rotate, viz_len=viz_len, max_in_batch=max_in_batch)
+        return model.render_with_gt(model.renderer, verts_hand_gt=verts_hand_gt, verts_object_gt=verts_object_gt,
+                                    rotate=rotate, viz_len=viz_len, init=init, max_in_batch=max_in_batch)
+
+    rends, masks = draw(False)
     new_images = []
     for image, rend, mask in zip(images, rends, masks):
         image = np.asarray(image, dtype=np.float32)
@@ -46,5 +54,5 @@ def visualize_hand_object(model, images, verts_hand_gt=None, verts_object_gt=Non
             rend, mask = rend[ys][:, xs], mask[ys][:, xs]
         new_image[mask] = rend[mask]
         new_images.append((new_image[:h, :w] * 255).astype(np.uint8))
-    top_down, _ = model.render(model.renderer, rotate=True, viz_len=viz_len, max_in_batch=max_in_batch)
+    top_down, _ = draw(True)
     return np.stack(new_images), (top_down * 255).astype(np.uint8)

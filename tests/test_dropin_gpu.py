@@ -132,3 +132,60 @@ def test_visualisation_inside_the_loop(mano_assets, tmp_path):
     # the loss values are those of the run without pictures
     ref = z["ev_loss_p0"]
     assert np.all(np.abs(np.asarray(ev["loss"])[:2] - ref[:2]) <= 1e-4 * np.abs(ref[:2]))
+
+
+def test_ground_truth_overlays_joints_and_obj_export(mano_assets, tmp_path):
+    """The rest of HOMan's reference surface: render_gt / render_with_gt (homan/homan.py:564-613) and their use by
+    visualize_hand_object (homan/visualize.py:54-128), get_joints_hand (homan.py:309-339, checked against the oracle's
+    MANO layer + placement), save_obj (homan.py:615-626)."""
+    from homan_b200.jointopt import optimize_hand_object
+    from homan_b200.visualize import visualize_hand_object
+    from oracle import homan_ref
+    z, batch, lw, iters = load("ref_small_step2", mano_assets["right"])
+    inp = reference_inputs(batch, 0, mano_assets["right"])
+    T = batch["T"]
+    model, _, _ = optimize_hand_object(loss_weights=lw, num_iterations=3, lr=1e-2, viz_folder=str(tmp_path),
+                                       optimize_mano=True, optimize_mano_beta=True, image_size=640,
+                                       mano_asset=mano_assets["right"], **inp)
+    n = min(3, T)
+    # ---- ground truth = the initialisation shifted sideways: both sets of meshes must show up, in their colours
+    vo_gt = model.verts_object_init + torch.tensor([0.03, 0.0, 0.0], device=model.verts_object_init.device)
+    vh_gt = model.verts_hand_init + torch.tensor([0.03, 0.0, 0.0], device=model.verts_hand_init.device)
+    r_fit, m_fit = model.render(viz_len=n)
+    r_gt, m_gt = model.render_gt(verts_hand_gt=vh_gt, verts_object_gt=vo_gt, viz_len=n)
+    r_both, m_both = model.render_with_gt(verts_hand_gt=[vh_gt], verts_object_gt=vo_gt, viz_len=n)
+    assert r_gt.shape == r_fit.shape == r_both.shape == (n, 640, 640, 3)
+    assert m_gt.any() and (m_gt != m_fit).any()
+    assert ((m_fit | m_gt) == m_both).mean() > 0.999            # the union of the two silhouettes (up to edge samples)
+    green = r_gt[m_gt]
+    assert (green[:, 1] > green[:, 0]).any() and (green[:, 2] > green[:, 0]).any()   # green object, blue hand
+    only_gt = m_both & ~m_fit
+    assert only_gt.any() and (r_both[only_gt][:, 2] > 0.3).all()  # gold has no blue: these pixels are ground truth
+    frames = [np.full((480, 640, 3), 64, np.uint8) for _ in range(T)]
+    front, top = visualize_hand_object(model, frames, verts_hand_gt=[vh_gt], verts_object_gt=vo_gt, viz_len=n)
+    assert front.shape == (n, 480, 640, 3) and top.shape == (n, 640, 640, 3) and front.std() > 5
+    front_gt, _ = visualize_hand_object(model, frames, verts_hand_gt=vh_gt, verts_object_gt=vo_gt, viz_len=n, gt_only=True)
+    assert (front_gt != front).any()
+    # ---- joints against the oracle
+    joints, _ = model.get_joints_hand()
+    assert joints.shape == (T, 21, 3)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    mano = homan_ref.ManoPca(mano_assets["right"])
+    v, j = mano(sd["mano_pca_pose"], sd["mano_rot"], sd["mano_betas"], "right")
+    full = torch.cat((j, v[:, [745, 317, 444, 556, 673]]), 1)[:, [0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12,
+                                                                 19, 7, 8, 9, 20]]
+    full = full + sd["mano_trans"].unsqueeze(1)
+    ref, _ = homan_ref.transform_persp(full, sd["translations_hand"].view(T, 1, 3),
+                                       homan_ref.rot6d_to_matrix(sd["rotations_hand"]), torch.ones(1))
+    assert (joints.cpu() - ref).abs().max() <= 1e-5 * ref.abs().max()
+    # the wrist is a MANO joint, the finger tips are vertices of the fitted mesh
+    vh = model.get_verts_hand()[0]
+    assert torch.allclose(joints[:, [4, 8, 12, 16, 20]], vh[:, [745, 317, 444, 556, 673]], atol=1e-5)
+    # ---- .obj export of the first frame
+    path = tmp_path / "scene.obj"
+    model.save_obj(str(path))
+    lines = path.read_text().splitlines()
+    nv = batch["obj_verts_can"].shape[0] + 778
+    assert sum(l.startswith("v ") for l in lines) == nv
+    assert sum(l.startswith("f ") for l in lines) == np.asarray(batch["obj_faces"]).shape[0] + 1538
+    assert max(int(t) for l in lines if l.startswith("f ") for t in l.split()[1:]) == nv
