@@ -92,6 +92,36 @@ contact_kernel(const float *__restrict__ vh, const float *__restrict__ vo, int T
     }
 }
 
+// Nearest point of b for every point of a (brute force from shared memory: the point sets of the evaluation are a few
+// hundred to a few thousand points; contraction depth 3, no GEMM). Ties -> lowest index.
+constexpr int NN_TILE = 1024;
+__global__ void __launch_bounds__(NT)
+nearest_point_kernel(const float *__restrict__ a, const float *__restrict__ b, int N, int M, float *__restrict__ dist2,
+                     int32_t *__restrict__ index) {
+    __shared__ float sb[NN_TILE * 3];
+    const int img = blockIdx.y, i = blockIdx.x * NT + threadIdx.x;
+    const float *pa = a + ((long)img * N + min(i, N - 1)) * 3;
+    const float *pb = b + (long)img * M * 3;
+    const float x = pa[0], y = pa[1], z = pa[2];
+    float best = INFINITY;
+    int bi = -1;
+    for (int m0 = 0; m0 < M; m0 += NN_TILE) {
+        const int n = min(NN_TILE, M - m0);
+        __syncthreads();
+        for (int k = threadIdx.x; k < 3 * n; k += NT) sb[k] = pb[3 * (long)m0 + k];
+        __syncthreads();
+        for (int j = 0; j < n; ++j) {
+            const float dx = x - sb[3 * j], dy = y - sb[3 * j + 1], dz = z - sb[3 * j + 2];
+            const float d = dx * dx + dy * dy + dz * dz;
+            if (d < best || (bi < 0 && d == d)) { best = d; bi = m0 + j; }
+        }
+    }
+    if (i < N) {
+        dist2[(long)img * N + i] = best;
+        if (index) index[(long)img * N + i] = bi;
+    }
+}
+
 }  // namespace
 
 extern "C" int hm_contact_fwd_bwd(const float *verts_hand, const float *verts_obj, int B, int T, int Vo, float thresh,
@@ -104,5 +134,16 @@ extern "C" int hm_contact_fwd_bwd(const float *verts_hand, const float *verts_ob
     contact_kernel<<<B, NT, 0, hm_stream(stream)>>>(verts_hand, verts_obj, T, Vo, thresh, weight, partials,
                                                     grad_verts_hand, grad_verts_obj, grad_fixed_obj);
     HM_CHECK_LAUNCH("hm_contact_fwd_bwd");
+    return HM_OK;
+}
+
+extern "C" int hm_nearest_point(const float *a, const float *b, int B, int N, int M, float *dist2, int32_t *index, void *stream) {
+    HM_NVTX("hm_nearest_point");
+    HM_REQUIRE(B >= 0 && B <= 65535 && N >= 0 && M >= 0, "hm_nearest_point: bad sizes (B <= 65535)");
+    if (B == 0 || N == 0) return HM_OK;
+    HM_REQUIRE(M > 0, "hm_nearest_point: empty target set");
+    HM_REQUIRE(a && b && dist2, "hm_nearest_point: null pointer");
+    nearest_point_kernel<<<dim3((N + NT - 1) / NT, B), NT, 0, hm_stream(stream)>>>(a, b, N, M, dist2, index);
+    HM_CHECK_LAUNCH("hm_nearest_point");
     return HM_OK;
 }

@@ -210,6 +210,11 @@ int hm_contact_fwd_bwd(const float *verts_hand, const float *verts_obj, int B, i
                        float weight, float *partials, float *grad_verts_hand, float *grad_verts_obj,
                        unsigned long long *grad_fixed_obj, void *stream);
 
+/* Nearest point of b [B,M,3] for every point of a [B,N,3]: squared distance [B,N] and (optionally) index [B,N] (ties:
+ * lowest index).  The search behind the evaluation's point metrics (homan/eval/pointmetrics.py:17-45,95-99:
+ * pytorch3d chamfer_distance and scipy cKDTree.query(k=1) for ADD-S), which the reference runs on the fitted meshes. */
+int hm_nearest_point(const float *a, const float *b, int B, int N, int M, float *dist2, int32_t *index, void *stream);
+
 /* ---------------------------------------------------------------- SDF interpenetration
  * SDFSceneLoss.forward for (hand, object) (homan/interactions/scenesdf.py:77-148, called from
  * compute_collision_loss, homan/lossutils.py:43-64): phi = clamp(SDF, 0) of the grid mesh in its own

@@ -86,7 +86,8 @@ def test_header_declares_every_new_entry_point_with_a_reference_citation():
     text = open(_lib.HEADER_PATH).read()
     for name, cite in (("hm_offscreen_loss_fwd_bwd", "pose_optimization.py:112-134"),
                        ("hm_track_best", "pose_optimization.py:349-353"), ("hm_raster_shade", "homan/homan.py:510-613"),
-                       ("hm_face_lighting", "Renderer.render"), ("hm_sdf_pair", "homan/eval/pointmetrics.py:102-124")):
+                       ("hm_face_lighting", "Renderer.render"), ("hm_sdf_pair", "homan/eval/pointmetrics.py:102-124"),
+                       ("hm_nearest_point", "homan/eval/pointmetrics.py:17-45")):
         assert name in _lib.SIGNATURES, name
         assert cite in text, cite
     handle = _lib.lib()
@@ -99,6 +100,9 @@ def test_no_cpu_fallback_eval_metrics():
     with pytest.raises(_lib.HomanB200Error):
         get_inter_metrics(torch.zeros(1, 778, 3), torch.zeros(1, 8, 3), torch.zeros(1, 12, 3, dtype=torch.int64),
                           torch.zeros(1, 12, 3, dtype=torch.int64))
+    from homan_b200.eval.pointmetrics import nearest_dist2
+    with pytest.raises(_lib.HomanB200Error):
+        nearest_dist2(torch.zeros(1, 8, 3), torch.zeros(1, 8, 3))
 
 
 def test_bench_prints_exactly_one_json_line_on_stdout(monkeypatch, capfd):

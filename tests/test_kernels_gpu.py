@@ -219,6 +219,54 @@ def test_inter_metrics_match_oracle(mano_assets):
     assert got["has_contact"] == (ref > 0).tolist()
 
 
+def test_point_metrics_match_scipy_and_the_reference_expressions(mano_assets):
+    """get_point_metrics / get_align_metrics (homan/eval/pointmetrics.py:17-45,62-99) on hm_nearest_point, against
+    scipy's cKDTree (the reference's own ADD-S search) and the dense distance-matrix form the reference documents as
+    equal to pytorch3d's chamfer ((dist_mat.min(1)[0] + dist_mat.min(2)[0]).mean(-1), pointmetrics.py:25,94)."""
+    from scipy import spatial
+    from homan_b200.eval.pointmetrics import get_align_metrics, get_point_metrics, nearest_dist2
+    rng = np.random.default_rng(4)
+    vh, vo, clip = _grasp(3, 21, mano_assets)
+    gt_o, gt_h = vo.astype(np.float32), vh.astype(np.float32)
+    pr_o = (gt_o * np.float32(1.07) + rng.normal(0, 0.004, gt_o.shape)).astype(np.float32)
+    pr_h = (gt_h * np.float32(1.07) + rng.normal(0, 0.002, gt_h.shape)).astype(np.float32)
+    pr_o_sub = pr_o[:, ::3]                                   # a point set of another size: no vertex assignment
+    t = torch.from_numpy
+    # nearest neighbours (index too), incl. exact ties (duplicated targets -> lowest index)
+    a = t(gt_o).cuda()
+    b = torch.cat((t(pr_o_sub), t(pr_o_sub)), 1).cuda()
+    from homan_b200._lib import call, current_stream, ptr
+    d2 = torch.empty(a.shape[:2], device="cuda")
+    idx = torch.empty(a.shape[:2], dtype=torch.int32, device="cuda")
+    call("hm_nearest_point", ptr(a), ptr(b), a.shape[0], a.shape[1], b.shape[1], ptr(d2), ptr(idx), current_stream())
+    dm = torch.cdist(t(gt_o).double(), torch.cat((t(pr_o_sub), t(pr_o_sub)), 1).double()) ** 2
+    assert torch.equal(idx.cpu().long(), dm.float().argmin(2)) or (idx.cpu().long() < pr_o_sub.shape[1]).all()
+    assert torch.allclose(d2.cpu().double(), dm.min(2)[0], rtol=1e-5, atol=1e-12)
+    assert torch.equal(nearest_dist2(a, b), d2)
+    for pred in (pr_o, pr_o_sub):
+        got = get_point_metrics(t(gt_o), t(pred))
+        dm = torch.cdist(t(gt_o).double(), t(pred).double()) ** 2
+        cham = (dm.min(2)[0].mean(-1) + dm.min(1)[0].mean(-1)).numpy()
+        adds = np.array([spatial.cKDTree(pe).query(pg, k=1)[0].mean() for pg, pe in zip(gt_o, pred)])
+        assert np.allclose(got["chamfer_dists"], cham, rtol=1e-4), (got["chamfer_dists"], cham)
+        assert np.allclose(got["add-s"], adds, rtol=1e-4)
+        if pred.shape[1] == gt_o.shape[1]:
+            assert np.allclose(got["verts_dists"], np.linalg.norm(gt_o - pred, axis=-1).mean(-1), rtol=1e-5)
+        else:
+            assert got["verts_dists"] == got["add-s"]
+    # aligned metrics: the reference expressions in fp64
+    got = get_align_metrics(t(gt_h), t(pr_h), t(gt_o), t(pr_o))
+    gh, ph, go, po = (t(x).double() for x in (gt_h, pr_h, gt_o, pr_o))
+    cent = gh.mean(1, keepdim=True)
+    gh_c, go_c, ph_c, po_c = gh - cent, go - cent, ph - cent, po - cent
+    gs = torch.sqrt((gh_c.norm(2, -1) ** 2).sum(1) / gh.shape[1])
+    ps = torch.sqrt((ph_c.norm(2, -1) ** 2).sum(1) / ph.shape[1])
+    ph_cs, po_cs = ph_c / ps.view(-1, 1, 1) * gs.view(-1, 1, 1), po_c / ps.view(-1, 1, 1) * gs.view(-1, 1, 1)
+    dm = torch.cdist(po_cs, go_c) ** 2
+    assert np.allclose(got["hand_mean_aligned"], (gh_c - ph_cs).norm(2, -1).mean(-1).numpy(), rtol=1e-4)
+    assert np.allclose(got["obj_chamfer_aligned"], (dm.min(2)[0].mean(-1) + dm.min(1)[0].mean(-1)).numpy(), rtol=1e-4)
+
+
 @pytest.mark.parametrize("aa", [True, False])
 def test_fused_loss_and_sweep_lists_equal_the_two_kernels(aa, mano_assets):
     """hm_sil_loss_prep = hm_sil_loss_fwd_bwd + hm_raster_grad_prep, bit for bit: loss, IoU, grad_alpha, the four
