@@ -12,7 +12,9 @@ plus the helpers it needs (`compute_random_rotations`, homan/utils/geometry.py:8
 `find_optimal_pose` runs on `PoseFitEngine`: one iteration = rigid placement -> projection -> hard z-buffered
 silhouette (anti-aliasing off) -> masked L2 + off-screen penalty -> backward -> Adam -> best-ever tracking, a
 fixed sequence of C-ABI kernels replayed as a CUDA graph, all N candidates in one batch. GPU only, no fallback.
-Not provided: the chamfer term (lw_chamfer is 0 in every reference call) and the debug plots.
+The chamfer term (max-pool edges x distance transform, lw_chamfer = 0 in every reference call) is evaluated by the
+drop-in module only (torch max-pool on the rasteriser's output); the fused fitter runs the reference's configuration.
+Not provided: the debug plots.
 """
 import math
 
@@ -303,8 +305,6 @@ class PoseOptimizer(nn.Module):
                  num_initializations=1, kernel_size=7, K=None, power=0.25, lw_chamfer=0):
         assert ref_image.shape[0] == ref_image.shape[1], "Must be square."
         super().__init__()
-        if lw_chamfer != 0:
-            raise NotImplementedError("homan_b200 PoseOptimizer: the chamfer term (lw_chamfer != 0) is not provided")
         dev = torch.device("cuda")
         vertices = torch.as_tensor(vertices).float().to(dev)
         faces = torch.as_tensor(faces).to(dev)
@@ -324,9 +324,20 @@ class PoseOptimizer(nn.Module):
         self.K = torch.as_tensor(K).float().to(dev)
         self.renderer = _Renderer(ref.shape[0], self.K)
         self.lw_chamfer = lw_chamfer
+        # edge / distance-transform term (pose_optimization.py:74-88): edges of the reference mask by a max-pool, their
+        # Euclidean distance transform to the power 2 * power, once, on the host (scipy, as upstream)
+        self.pool = torch.nn.MaxPool2d(kernel_size=kernel_size, stride=1, padding=kernel_size // 2)
+        from scipy.ndimage import distance_transform_edt
+        mask_edge = self.compute_edges(self.image_ref[:1]).cpu().numpy()
+        edt = distance_transform_edt(1 - (mask_edge > 0)) ** (power * 2)
+        self.register_buffer("edt_ref_edge", torch.from_numpy(edt).float().to(dev).repeat(num_initializations, 1, 1))
 
     def apply_transformation(self):
         return torch.matmul(self.vertices, rot6d_to_matrix(self.rotations)) + self.translations
+
+    def compute_edges(self, silhouette):
+        """pose_optimization.py:136-137."""
+        return self.pool(silhouette) - silhouette
 
     def compute_offscreen_loss(self, verts):
         r = self.renderer
@@ -346,7 +357,10 @@ class PoseOptimizer(nn.Module):
         with torch.no_grad():
             a, b = image.detach(), self.image_ref
             iou = (a * b).sum((1, 2)) / ((a + b).clamp(0, 1).sum((1, 2)) + 1e-6)
-        loss_dict["chamfer"] = torch.zeros_like(loss_dict["mask"])
+        if self.lw_chamfer != 0:   # (0 in every call of the reference itself; the pool and the product are torch ops)
+            loss_dict["chamfer"] = self.lw_chamfer * torch.sum(self.compute_edges(image) * self.edt_ref_edge, dim=(1, 2))
+        else:
+            loss_dict["chamfer"] = torch.zeros_like(loss_dict["mask"])
         loss_dict["offscreen"] = OFFSCREEN_WEIGHT * self.compute_offscreen_loss(verts)
         return loss_dict, iou, image
 

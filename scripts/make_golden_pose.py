@@ -116,5 +116,41 @@ def main():
     print("offscreen:", out["it_offscreen"].max(), out["po_offscreen"], out["po_mask"])
 
 
+def main_chamfer():
+    """tests/golden/ref_pose_chamfer.npz: PoseOptimizer with the max-pool edge / EDT chamfer term switched on
+    (pose_optimization.py:84-88,136-149; lw_chamfer is 0 in every call of the reference itself), on the inputs of
+    ref_pose_init.npz: loss terms and the gradients of one backward."""
+    assert refshim.reference_available(), "needs /root/reference"
+    assets = {"right": synth.make_mano_asset(0, "right"), "left": synth.make_mano_asset(1, "left")}
+    refshim.install(tempfile.mkdtemp(prefix="homan_golden_pose_"), assets)
+    import homan.pose_optimization as po
+    g = np.load(os.path.join(GOLDEN, "ref_pose_init.npz"))
+    rot6 = torch.from_numpy(g["po_rot6d"].copy())
+    trans = torch.from_numpy(g["it_trans"][0][:4].copy())
+    trans[1, 0, 0] += 0.02     # candidates around the target: edges near, but not on, the reference's
+    trans[2, 0, 1] -= 0.03
+    trans[3, 0, 2] += 0.05
+    out = {"po_rot6d": rot6.numpy(), "po_trans": trans.numpy(), "lw_chamfer": np.float32(0.5), "kernel_size": np.int64(7),
+           "power": np.float32(0.25)}
+    model = po.PoseOptimizer(ref_image=g["in_mask"], vertices=torch.from_numpy(g["in_vertices"]),
+                             faces=torch.from_numpy(g["in_faces"]), textures=torch.ones(80, 1, 1, 1, 3),
+                             rotation_init=rot6, translation_init=trans, num_initializations=4,
+                             K=torch.from_numpy(g["K_roi"]), kernel_size=7, power=0.25, lw_chamfer=0.5)
+    loss_dict, iou, image = model()
+    loss_dict["chamfer"].sum().backward()
+    out.update({"po_chamfer": loss_dict["chamfer"].detach().numpy(), "po_mask": loss_dict["mask"].detach().numpy(),
+                "po_offscreen": loss_dict["offscreen"].detach().numpy(), "po_iou": iou.numpy(),
+                "po_grad_rot_chamfer": model.rotations.grad.numpy().copy(),
+                "po_grad_trans_chamfer": model.translations.grad.numpy().copy(),
+                "edt_ref_edge": model.edt_ref_edge[0].numpy()})
+    path = os.path.join(GOLDEN, "ref_pose_chamfer.npz")
+    np.savez_compressed(path, **out)
+    print(path, {k: np.asarray(v).shape for k, v in out.items()})
+    print("chamfer:", out["po_chamfer"], "grad trans:", out["po_grad_trans_chamfer"].reshape(4, 3))
+
+
 if __name__ == "__main__":
-    main()
+    if "--chamfer" in sys.argv:
+        main_chamfer()
+    else:
+        main()

@@ -74,6 +74,32 @@ def test_dropin_pose_optimizer_autograd_path():
             assert np.abs(got[i] - ref[i]).max() <= 1e-3 * np.abs(ref[i]).max(), (i, got[i], ref[i])
 
 
+def test_dropin_pose_optimizer_chamfer_term():
+    """The max-pool edge x distance-transform term of PoseOptimizer (pose_optimization.py:74-88,136-149) against the
+    unmodified reference run with lw_chamfer = 0.5 (tests/golden/ref_pose_chamfer.npz, scripts/make_golden_pose.py
+    --chamfer): the distance transform of the reference edges, the loss, and the gradients of its backward (torch's
+    max-pool backward into the rasteriser's backward with an arbitrary per-pixel gradient)."""
+    import os
+    from homan_b200.pose_optimization import PoseOptimizer
+    g = _golden()
+    c = np.load(os.path.join(os.path.dirname(__file__), "golden", "ref_pose_chamfer.npz"))
+    model = PoseOptimizer(ref_image=g["in_mask"], vertices=torch.from_numpy(g["in_vertices"]),
+                          faces=torch.from_numpy(g["in_faces"]), textures=None,
+                          rotation_init=torch.from_numpy(c["po_rot6d"]), translation_init=torch.from_numpy(c["po_trans"]),
+                          num_initializations=4, K=torch.from_numpy(g["K_roi"]), kernel_size=int(c["kernel_size"]),
+                          power=float(c["power"]), lw_chamfer=float(c["lw_chamfer"]))
+    assert np.allclose(model.edt_ref_edge[0].cpu().numpy(), c["edt_ref_edge"], rtol=1e-6)
+    loss_dict, iou, image = model()
+    loss_dict["chamfer"].sum().backward()
+    assert _close_counts(loss_dict["mask"].detach().cpu().numpy(), c["po_mask"])
+    got, ref = loss_dict["chamfer"].detach().cpu().numpy(), c["po_chamfer"]
+    assert (ref > 0).all() and np.allclose(got, ref, rtol=2e-3), (got, ref)   # (a boundary sample may differ: _close_counts)
+    for got, ref in ((model.rotations.grad.cpu().numpy(), c["po_grad_rot_chamfer"]),
+                     (model.translations.grad.cpu().numpy(), c["po_grad_trans_chamfer"])):
+        for i in range(4):
+            assert np.abs(got[i] - ref[i]).max() <= 2e-3 * np.abs(ref[i]).max(), (i, got[i], ref[i])
+
+
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_free_running_fit_follows_the_reference(use_graph):
     g = _golden()
