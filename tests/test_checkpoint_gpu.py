@@ -69,3 +69,65 @@ def test_resume_from_a_reference_checkpoint_reproduces_its_losses(mano_assets):
     before = model.translations_object.detach().clone()
     model.engine.step()
     assert not torch.equal(before, model.translations_object.detach())
+
+
+def test_step1_to_indep_fit_pickle_to_joint_fit_and_resume(mano_assets, tmp_path):
+    """The sample loop of the reference's driver end to end on a synthetic 2-frame clip (fit_vid_dataset.py:283-372):
+    object-pose initialisation (find_optimal_poses) -> `indep_fit.pkl` (the five-key dict, pickle.dump / load) ->
+    optimize_hand_object on the loaded dicts -> `joint_fit.pt` (state_dict minus mano_model.*, torch.save / load) -> a
+    second call resumed from it starts at the saved state (the reference does not save the optimiser either)."""
+    import pickle
+    from homan_b200 import pose_optimization as po, synth
+    from homan_b200.jointopt import optimize_hand_object
+    from homan_b200.workload import gpu_render_fn
+    asset = mano_assets["right"]
+    T = 2
+    clip = synth.make_clip(T, "ellipsoid80", seed=5, mano_asset=asset, render_fn=gpu_render_fn())
+    batch = synth.make_batch(clip, synth.make_inits(clip, 1, seed=9))
+    batch["T"] = T
+    inp = reference_inputs(batch, 0, asset)
+    # ---- step 1: object pose from the masks (what the detector / PointRend stage hands over per frame)
+    K_pix = np.array([[600.0, 0, 320.0], [0, 600.0, 320.0], [0, 0, 1]], dtype=np.float32)
+    annotations = []
+    for t in range(T):
+        uv = synth.project_np(clip["gt"]["verts_obj"][t].astype(np.float64), K_pix.astype(np.float64))
+        x, y, b = synth._square_roi(uv)
+        lo, hi = uv.min(0), uv.max(0)
+        annotations.append({"target_crop_mask": clip["target_masks_object"][t], "full_mask": torch.zeros(8, 8, dtype=torch.bool),
+                            "bbox": np.array([lo[0], lo[1], hi[0] - lo[0], hi[1] - lo[1]], np.float32),
+                            "square_bbox": np.array([x, y, b, b], np.float32)})
+    torch.manual_seed(0)
+    object_parameters = po.find_optimal_poses((640, 640, 3), faces=clip["obj_faces"], vertices=clip["obj_verts_can"],
+                                              annotations=annotations, images=None, Ks=[K_pix] * T, num_iterations=30,
+                                              num_initializations=256)
+    for t, fp in enumerate(object_parameters):   # the crop intrinsics the synthetic clip was rendered with, up to the
+        # half-pixel terms of libyana's get_K_crop_resize (principal point: 0.5 / 256 of the normalised crop)
+        assert torch.allclose(fp["K_roi"][0, 0].cpu(), torch.from_numpy(clip["K_roi_obj"][t]), atol=3e-3)
+    # ---- indep_fit.pkl
+    indep = {"person_parameters": inp["person_parameters"], "object_parameters": object_parameters,
+             "obj_verts_can": inp["objvertices"], "obj_faces": inp["objfaces"], "super2d_img_path": "super2d.png"}
+    path = tmp_path / "indep_fit.pkl"
+    with open(path, "wb") as fh:
+        pickle.dump(indep, fh)
+    with open(path, "rb") as fh:
+        loaded = pickle.load(fh)
+    assert set(loaded) == set(indep)
+    for a, b in zip(loaded["object_parameters"], object_parameters):
+        assert set(a) == set(b) and all(torch.equal(a[k], b[k]) for k in a)
+    # ---- step 2 on the loaded dicts, then joint_fit.pt as the driver writes it
+    _, _, lw, _ = load("ref_small_step2", asset)
+    kw = dict(loss_weights=lw, lr=1e-2, viz_folder=str(tmp_path), optimize_mano=True, optimize_mano_beta=True,
+              image_size=640, mano_asset=asset, person_parameters=loaded["person_parameters"],
+              object_parameters=loaded["object_parameters"], objvertices=loaded["obj_verts_can"],
+              objfaces=loaded["obj_faces"], camintr=inp["camintr"])
+    model, ev, _ = optimize_hand_object(num_iterations=6, **kw)
+    assert len(ev["loss"]) == 6 and np.isfinite(ev["loss"]).all()
+    assert ev["loss_sil_obj"][0] < 0.05   # the object starts on its mask: step 1 did its job
+    ckpt = tmp_path / "joint_fit.pt"
+    torch.save({"state_dict": {k: v.contiguous().cpu() for k, v in model.state_dict().items() if "mano_model" not in k}}, ckpt)
+    with torch.no_grad():
+        at_save, _ = model(lw)
+    state = {k: v.cuda() for k, v in torch.load(ckpt)["state_dict"].items()}
+    resumed, ev2, _ = optimize_hand_object(num_iterations=1, state_dict=state, **kw)
+    total = sum(float(v) * lw[k.replace("loss", "lw")] for k, v in at_save.items())
+    assert abs(ev2["loss"][0] - total) <= 1e-5 * abs(total), (ev2["loss"][0], total)
