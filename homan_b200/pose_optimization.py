@@ -49,7 +49,9 @@ def matrix_to_rot6d(rotmat):
 def compute_random_rotations(B=10, upright=False, generator=None, device="cuda"):
     """homan/utils/geometry.py:89-134, uniform branch (J. Arvo, "Fast Random Rotation Matrices")."""
     if upright:
-        raise NotImplementedError("compute_random_rotations: upright=True is not used by find_optimal_pose")
+        # (upstream's upright branch calls `euler_angles_to_matrix`, which homan/utils/geometry.py neither defines nor
+        #  imports: it raises NameError there; find_optimal_pose never asks for it)
+        raise NotImplementedError("compute_random_rotations: upright=True (broken upstream, unused by find_optimal_pose)")
     x1, x2, x3 = torch.split(torch.rand(3 * B, generator=generator).to(device), B)
     tau = 2 * math.pi
     zeros, ones = torch.zeros_like(x1), torch.ones_like(x1)
