@@ -316,6 +316,9 @@ class PoseOptimizer(nn.Module):
         self.register_buffer("image_ref", torch.from_numpy((ref > 0).astype(np.float32)).to(dev).repeat(num_initializations, 1, 1))
         self.register_buffer("keep_mask", torch.from_numpy((ref >= 0).astype(np.float32)).to(dev).repeat(num_initializations, 1, 1))
         self.ref_image = ref
+        F_ = self.faces.shape[1]
+        tex = torch.ones(F_, 1, 1, 1, 3) if textures is None else torch.as_tensor(textures).float()
+        self.register_buffer("textures", tex.to(dev).view(1, F_, *tex.shape[-4:]).repeat(num_initializations, 1, 1, 1, 1, 1))
         self.rotations = nn.Parameter(torch.as_tensor(rotation_init).clone().float().to(dev), requires_grad=True)
         translation_init = torch.as_tensor(translation_init).float().to(dev)
         if self.rotations.shape[0] != translation_init.shape[0]:
@@ -340,6 +343,15 @@ class PoseOptimizer(nn.Module):
     def compute_edges(self, silhouette):
         """pose_optimization.py:136-137."""
         return self.pool(silhouette) - silhouette
+
+    def render(self):
+        """pose_optimization.py:153-160: RGB renders [N,S,S,3] of the candidates at their current poses."""
+        from .shims.neural_renderer import Renderer
+        r = self.renderer
+        full = Renderer(image_size=r.image_size, K=r.K, R=r.R, t=r.t, orig_size=1, anti_aliasing=False)
+        with torch.no_grad():
+            images = full.render(self.apply_transformation(), self.faces, torch.tanh(self.textures))[0]
+        return images.detach().cpu().numpy().transpose(0, 2, 3, 1)
 
     def compute_offscreen_loss(self, verts):
         r = self.renderer

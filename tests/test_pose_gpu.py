@@ -64,6 +64,8 @@ def test_dropin_pose_optimizer_autograd_path():
     assert [n for n, _ in model.named_parameters()] == ["rotations", "translations"]
     loss_dict, iou, image = model()
     assert set(loss_dict) == {"mask", "chamfer", "offscreen"} and image.shape == (4, 256, 256)
+    rgb = model.render()   # pose_optimization.py:153-160: tanh(1) grey candidates on black, lit
+    assert rgb.shape == (4, 256, 256, 3) and rgb.max() <= 1.0 and ((rgb.sum(-1) > 0) == (image.detach().cpu().numpy() > 0)).mean() > 0.97
     sum(loss_dict.values()).sum().backward()
     assert _close_counts(loss_dict["mask"].detach().cpu().numpy(), g["po_mask"])
     assert np.allclose(loss_dict["offscreen"].detach().cpu().numpy(), g["po_offscreen"], rtol=1e-5)
